@@ -1,0 +1,184 @@
+/*
+ * tmb200.h - C ABI of libtmb200.so: the B200-native (sm_100a) force-evaluation + integration hot path of timemachine.
+ *
+ * Every entry point is what a binding for the reference's `timemachine.lib.custom_ops` module would call for this
+ * path; the reference's own boundary is the pybind11 module in timemachine/cpp/src/wrap_kernels.cpp, and each
+ * function below cites the lambda / method it replaces (file:line in /root/reference).  Conventions are the
+ * reference's:
+ *   - coords f64[N,3], params f64[...], box f64[3,3] row-major, index arrays int32 (uint32 where the reference has it);
+ *   - outputs are the raw FIXED-POINT accumulators (uint64 two's complement, int128 energies as {lo,hi}); conversion to
+ *     float happens on the caller's side exactly as wrap_kernels.cpp:83-89,1079-1096 does (tmb_*_fixed_to_float helps);
+ *   - a function returns 0 on success, 1 on a std::runtime_error-class failure, 2 when the GPU/driver is unusable
+ *     (the reference raises custom_ops.InvalidHardware, gpu_utils.cuh:31-53); tmb_last_error() gives the message,
+ *     which matches the reference's message text where its tests assert on it;
+ *   - not thread-safe, one CUDA device per process (potential.hpp:7 in the reference says the same).
+ * No torch / pybind types appear here: plain pointers and sizes only.
+ */
+#ifndef TMB200_H
+#define TMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tmb_i128 {
+    uint64_t lo;
+    int64_t hi;
+} tmb_i128;
+
+typedef void *tmb_potential;       /* std::shared_ptr<Potential>            (wrap_kernels.cpp:729  declare_potential) */
+typedef void *tmb_bound_potential; /* std::shared_ptr<BoundPotential>       (wrap_kernels.cpp:1133 declare_bound_potential) */
+typedef void *tmb_integrator;      /* std::shared_ptr<LangevinIntegrator>   (wrap_kernels.cpp:698) */
+typedef void *tmb_context;         /* Context                               (wrap_kernels.cpp:296) */
+typedef void *tmb_neighborlist;    /* Neighborlist<float|double>            (wrap_kernels.cpp:113) */
+typedef void *tmb_hilbert_sort;    /* HilbertSort                           (wrap_kernels.cpp:174) */
+
+#define TMB_OK 0
+#define TMB_ERROR 1
+#define TMB_INVALID_HARDWARE 2
+
+#define TMB_F32 32
+#define TMB_F64 64
+
+/* ---- library ------------------------------------------------------------------------------------------------- */
+const char *tmb_last_error(void);
+int tmb_version(void);
+uint64_t tmb_fixed_exponent(void);          /* custom_ops.FIXED_EXPONENT, wrap_kernels.cpp:2311 */
+int tmb_cuda_device_reset(void);            /* custom_ops.cuda_device_reset, wrap_kernels.cpp:2222 */
+long long tmb_kernel_launch_count(void);    /* kernels launched by this library so far */
+int tmb_set_stream(void *cuda_stream);      /* stream used by the host-buffer entry points (default: legacy stream 0) */
+int tmb_device_synchronize(void);
+
+/* ---- potentials: constructors (argument order = the reference's ctor order) ------------------------------------- */
+/* HarmonicBond_{f32,f64}(bond_idxs i32[B,2])                       wrap_kernels.cpp:1311-1322 */
+int tmb_harmonic_bond_create(int precision, const int32_t *bond_idxs, int n_values, tmb_potential *out);
+/* HarmonicAngle_{f32,f64}(angle_idxs i32[A,3])                     wrap_kernels.cpp:1396-1408 */
+int tmb_harmonic_angle_create(int precision, const int32_t *angle_idxs, int n_values, tmb_potential *out);
+/* PeriodicTorsion_{f32,f64}(torsion_idxs i32[T,4])                 wrap_kernels.cpp:1432-1444 */
+int tmb_periodic_torsion_create(int precision, const int32_t *torsion_idxs, int n_values, tmb_potential *out);
+/* NonbondedAllPairs_*(num_atoms, beta, cutoff, atom_idxs|None, disable_hilbert_sort, nblist_padding)
+ *                                                                  wrap_kernels.cpp:1446-1478 ; n_atom_idxs < 0 = None */
+int tmb_nonbonded_all_pairs_create(
+    int precision, int num_atoms, double beta, double cutoff, const int32_t *atom_idxs, int n_atom_idxs,
+    int disable_hilbert_sort, double nblist_padding, tmb_potential *out);
+int tmb_nonbonded_all_pairs_set_atom_idxs(tmb_potential pot, const int32_t *atom_idxs, int n);
+int tmb_nonbonded_all_pairs_get_num_atom_idxs(tmb_potential pot, int *out);
+int tmb_nonbonded_all_pairs_get_atom_idxs(tmb_potential pot, int32_t *out /* [num_atom_idxs] */);
+/* NonbondedInteractionGroup_*(num_atoms, row_atom_idxs, beta, cutoff, col_atom_idxs|None, disable_hilbert_sort,
+ * nblist_padding)                                                  wrap_kernels.cpp:1480-1561 ; n_col < 0 = complement */
+int tmb_nonbonded_interaction_group_create(
+    int precision, int num_atoms, const int32_t *row_atom_idxs, int n_row, double beta, double cutoff,
+    const int32_t *col_atom_idxs, int n_col, int disable_hilbert_sort, double nblist_padding, tmb_potential *out);
+int tmb_nonbonded_interaction_group_set_atom_idxs(
+    tmb_potential pot, const int32_t *row_atom_idxs, int n_row, const int32_t *col_atom_idxs, int n_col);
+/* NonbondedPairList_* / NonbondedExclusions_*(pair_idxs i32[M,2], scales f64[M,2], beta, cutoff)
+ *                                                                  wrap_kernels.cpp:1563-1589 ; negated = Exclusions */
+int tmb_nonbonded_pair_list_create(
+    int precision, int negated, const int32_t *pair_idxs, int n_pair_values, const double *scales, int n_scale_values,
+    double beta, double cutoff, tmb_potential *out);
+/* SummedPotential(potentials, params_sizes, parallel)              wrap_kernels.cpp:1661-1675 */
+int tmb_summed_potential_create(
+    const tmb_potential *potentials, int n_potentials, const int32_t *params_sizes, int n_sizes, int parallel,
+    tmb_potential *out);
+/* FanoutSummedPotential(potentials, parallel)                      wrap_kernels.cpp:1677-1691 */
+int tmb_fanout_summed_potential_create(const tmb_potential *potentials, int n_potentials, int parallel, tmb_potential *out);
+int tmb_potential_destroy(tmb_potential pot);
+
+/* ---- potentials: evaluation --------------------------------------------------------------------------------------- */
+/* Potential.execute -> execute_host: host buffers in, fixed-point host buffers out (any of the three may be NULL)
+ *                                                                  wrap_kernels.cpp:1039-1105, potential.cu:224-292 */
+int tmb_potential_execute(
+    tmb_potential pot, int N, int P, const double *coords, const double *params, const double *box, uint64_t *du_dx,
+    uint64_t *du_dp, tmb_i128 *u);
+/* Potential.execute_batch                                          wrap_kernels.cpp:736-831, potential.cu:70-144 */
+int tmb_potential_execute_batch(
+    tmb_potential pot, int coord_batches, int N, int param_batches, int P, const double *coords, const double *params,
+    const double *boxes, uint64_t *du_dx, uint64_t *du_dp, tmb_i128 *u);
+/* Potential.execute_batch_sparse                                   wrap_kernels.cpp:871-986, potential.cu:146-222 */
+int tmb_potential_execute_batch_sparse(
+    tmb_potential pot, int coords_size, int N, int params_size, int P, int batch_size, const uint32_t *coords_batch_idxs,
+    const uint32_t *params_batch_idxs, const double *coords, const double *params, const double *boxes, uint64_t *du_dx,
+    uint64_t *du_dp, tmb_i128 *u);
+/* virtual Potential::du_dp_fixed_to_float (per-column exponents for nonbonded)  potential.cu:322, nonbonded_all_pairs.cu:292 */
+int tmb_potential_du_dp_fixed_to_float(tmb_potential pot, int N, int P, const uint64_t *du_dp, double *out);
+/* Potential::execute_device: DEVICE pointers, accumulates into du_dx/du_dp, overwrites u, enqueues on `cuda_stream`
+ * without synchronising                                            potential.hpp:87-96 */
+int tmb_potential_execute_device(
+    tmb_potential pot, int N, int P, const double *d_coords, const double *d_params, const double *d_box,
+    uint64_t *d_du_dx, uint64_t *d_du_dp, tmb_i128 *d_u, void *cuda_stream);
+/* number of 32x32 interaction tiles in the cached neighbour list of a NonbondedAllPairs / InteractionGroup */
+int tmb_nonbonded_num_tiles(tmb_potential pot, unsigned int *out);
+
+/* ---- BoundPotential                                              wrap_kernels.cpp:1133-1309 ----------------------- */
+int tmb_bound_potential_create(tmb_potential pot, const double *params, int n_params, tmb_bound_potential *out);
+int tmb_bound_potential_destroy(tmb_bound_potential bp);
+int tmb_bound_potential_set_params(tmb_bound_potential bp, const double *params, int n_params);
+int tmb_bound_potential_size(tmb_bound_potential bp, int *out);
+int tmb_bound_potential_execute(
+    tmb_bound_potential bp, int N, const double *coords, const double *box, uint64_t *du_dx, tmb_i128 *u);
+int tmb_bound_potential_execute_batch(
+    tmb_bound_potential bp, int coord_batches, int N, const double *coords, const double *boxes, uint64_t *du_dx,
+    tmb_i128 *u);
+int tmb_bound_potential_set_params_device(tmb_bound_potential bp, const double *d_params, int n_params, void *cuda_stream);
+int tmb_bound_potential_execute_device(
+    tmb_bound_potential bp, int N, const double *d_coords, const double *d_box, uint64_t *d_du_dx, tmb_i128 *d_u,
+    void *cuda_stream);
+
+/* ---- LangevinIntegrator(masses, temperature, dt, friction, seed) wrap_kernels.cpp:698-715 ------------------------ */
+int tmb_langevin_integrator_create(
+    const double *masses, int N, double temperature, double dt, double friction, int seed, tmb_integrator *out);
+int tmb_langevin_integrator_destroy(tmb_integrator intg);
+/* test hook: N x 3 f32 normals used on every step instead of the in-kernel Philox stream (NULL restores Philox) */
+int tmb_langevin_integrator_set_noise(tmb_integrator intg, const float *noise);
+
+/* ---- Context(x0, v0, box, integrator, bps)                       wrap_kernels.cpp:296-689, context.cu ------------- */
+int tmb_context_create(
+    const double *x0, const double *v0, const double *box, int N, tmb_integrator intg, const tmb_bound_potential *bps,
+    int n_bps, tmb_context *out);
+int tmb_context_destroy(tmb_context ctx);
+int tmb_context_step(tmb_context ctx);
+/* Context::multiple_steps(n_steps, n_samples, h_x[n_samples,N,3], h_box[n_samples,3,3])   context.cu:216-242 */
+int tmb_context_multiple_steps(tmb_context ctx, int n_steps, int n_samples, double *h_x, double *h_box);
+int tmb_context_set_x_t(tmb_context ctx, const double *x);
+int tmb_context_set_v_t(tmb_context ctx, const double *v);
+int tmb_context_set_box(tmb_context ctx, const double *box);
+int tmb_context_get_x_t(tmb_context ctx, double *x);
+int tmb_context_get_v_t(tmb_context ctx, double *v);
+int tmb_context_get_box(tmb_context ctx, double *box);
+int tmb_context_num_atoms(tmb_context ctx, int *out);
+int tmb_context_set_stream(tmb_context ctx, void *cuda_stream); /* run the MD loop on the caller's stream */
+int tmb_context_set_use_graphs(tmb_context ctx, int on);        /* CUDA-graph replay of step blocks (default on) */
+int tmb_context_device_state(tmb_context ctx, double **d_x, double **d_v, double **d_box);
+
+/* ---- Neighborlist_{f32,f64}(N)                                   wrap_kernels.cpp:113-172 ------------------------- */
+int tmb_neighborlist_create(int precision, int N, tmb_neighborlist *out);
+int tmb_neighborlist_destroy(tmb_neighborlist nb);
+/* get_nblist in two calls: build returns the sizes, fetch copies CSR (offsets[n_row_blocks+1], atoms[n_entries]) */
+int tmb_neighborlist_build(
+    tmb_neighborlist nb, int N, const double *coords, const double *box, double cutoff, int *n_row_blocks, int *n_entries);
+int tmb_neighborlist_fetch(tmb_neighborlist nb, int32_t *offsets, int32_t *atoms);
+int tmb_neighborlist_compute_block_bounds(
+    tmb_neighborlist nb, int N, const double *coords, const double *box, double *ctrs, double *exts);
+int tmb_neighborlist_set_row_idxs(tmb_neighborlist nb, const uint32_t *idxs, int n);
+int tmb_neighborlist_reset_row_idxs(tmb_neighborlist nb);
+int tmb_neighborlist_resize(tmb_neighborlist nb, int size);
+int tmb_neighborlist_get_tile_ixn_count(tmb_neighborlist nb, unsigned int *out);
+int tmb_neighborlist_get_max_ixn_count(tmb_neighborlist nb, int *out);
+int tmb_neighborlist_get_num_row_idxs(tmb_neighborlist nb, int *out);
+
+/* ---- HilbertSort(size).sort(coords, box) -> perm u32[N]          wrap_kernels.cpp:174-194 ------------------------- */
+int tmb_hilbert_sort_create(int size, tmb_hilbert_sort *out);
+int tmb_hilbert_sort_destroy(tmb_hilbert_sort hs);
+int tmb_hilbert_sort_sort(tmb_hilbert_sort hs, int N, const double *coords, const double *box, uint32_t *perm);
+
+/* ---- test utilities ---------------------------------------------------------------------------------------------- */
+/* N x 3 standard normals from the integrator's Philox stream for (seed, step) */
+int tmb_fill_normal(float *out, int n_atoms, uint64_t seed, uint64_t step);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* TMB200_H */

@@ -1,0 +1,104 @@
+"""Build libtmb200.so (all CUDA kernels + host classes + C ABI) for sm_100a with nvcc, in-tree.
+
+    python -m timemachine_b200.build            # incremental
+    python -m timemachine_b200.build --force    # rebuild everything
+
+nvcc cross-compiles without a GPU.  Objects go to timemachine_b200/csrc/build/, the library to
+timemachine_b200/lib/libtmb200.so (git-ignored, shipped to the GPU box by gpurun).
+"""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+SRC_DIR = PKG_DIR / "csrc"
+OBJ_DIR = SRC_DIR / "build"
+LIB_DIR = PKG_DIR / "lib"
+LIB_PATH = LIB_DIR / "libtmb200.so"
+
+NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+# --fmad=false: every fused multiply-add in the kernels is written explicitly (see csrc/nb_math.cuh); the compiler
+# never contracts on its own, so a pair term is rounded identically in every kernel that evaluates it.
+NVCC_FLAGS = [
+    "-std=c++17",
+    "-O3",
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "--fmad=false",
+    "-Xcompiler",
+    "-fPIC",
+    "-Xcompiler",
+    "-Wall",
+    "-Xcudafe",
+    "--diag_suppress=177",  # unused-variable noise from templated kernels
+]
+
+
+def _sources() -> list[Path]:
+    return sorted(SRC_DIR.glob("*.cu"))
+
+
+def _headers_mtime() -> float:
+    hs = list(SRC_DIR.glob("*.cuh")) + list(SRC_DIR.glob("*.hpp")) + list(SRC_DIR.glob("*.h"))
+    hs.append(PKG_DIR.parent / "include" / "tmb200.h")
+    return max(h.stat().st_mtime for h in hs if h.exists())
+
+
+def _compile(src: Path, extra: list[str]) -> tuple[Path, str]:
+    obj = OBJ_DIR / (src.stem + ".o")
+    cmd = [NVCC, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src.name}:\n{proc.stdout}\n{proc.stderr}")
+    return obj, proc.stderr
+
+
+def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    LIB_DIR.mkdir(parents=True, exist_ok=True)
+    srcs = _sources()
+    hdr_time = _headers_mtime()
+    todo = []
+    for s in srcs:
+        obj = OBJ_DIR / (s.stem + ".o")
+        if force or not obj.exists() or obj.stat().st_mtime < max(s.stat().st_mtime, hdr_time):
+            todo.append(s)
+    extra = ["-Xptxas", "-v"] if ptxas_info else []
+    if todo:
+        if verbose:
+            print(f"[tmb200] compiling {len(todo)} translation units with {NVCC}", file=sys.stderr)
+        errors = []
+
+        def job(s):
+            try:
+                return _compile(s, extra)
+            except RuntimeError as e:  # keep going so one run reports every broken translation unit
+                errors.append(str(e))
+                return None
+
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            for res in pool.map(job, todo):
+                if res and (verbose or ptxas_info) and res[1].strip():
+                    print(res[1], file=sys.stderr)
+        if errors:
+            raise RuntimeError("\n".join(errors))
+    objs = [OBJ_DIR / (s.stem + ".o") for s in srcs]
+    if todo or not LIB_PATH.exists():
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *map(str, objs)]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError(f"link failed:\n{proc.stdout}\n{proc.stderr}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    path = build_library(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv)
+    print(path)

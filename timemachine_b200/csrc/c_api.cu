@@ -1,0 +1,571 @@
+// extern "C" surface of libtmb200.so (declared in include/tmb200.h).  Thin: argument marshalling, exception ->
+// status code + message, handle bookkeeping.  All compute goes through the classes in potential.hpp.
+#include "../../include/tmb200.h"
+#include "fixed_point.cuh"
+#include "potential.hpp"
+
+#include <cstring>
+
+using namespace tmb;
+
+static thread_local std::string g_last_error;
+
+template <typename F> static int guarded(F &&f) {
+    try {
+        f();
+        return TMB_OK;
+    } catch (const InvalidHardware &e) {
+        g_last_error = e.what();
+        return TMB_INVALID_HARDWARE;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return TMB_ERROR;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return TMB_ERROR;
+    }
+}
+
+typedef std::shared_ptr<Potential> PotPtr;
+typedef std::shared_ptr<BoundPotential> BpPtr;
+typedef std::shared_ptr<LangevinIntegrator> IntgPtr;
+
+static PotPtr &as_pot(tmb_potential h) {
+    if (h == nullptr) {
+        throw std::runtime_error("null potential handle");
+    }
+    return *static_cast<PotPtr *>(h);
+}
+static BpPtr &as_bp(tmb_bound_potential h) {
+    if (h == nullptr) {
+        throw std::runtime_error("null bound potential handle");
+    }
+    return *static_cast<BpPtr *>(h);
+}
+static IntgPtr &as_intg(tmb_integrator h) {
+    if (h == nullptr) {
+        throw std::runtime_error("null integrator handle");
+    }
+    return *static_cast<IntgPtr *>(h);
+}
+static Context &as_ctx(tmb_context h) {
+    if (h == nullptr) {
+        throw std::runtime_error("null context handle");
+    }
+    return *static_cast<Context *>(h);
+}
+
+struct NeighborlistHandle {
+    int precision;
+    std::unique_ptr<Neighborlist<float>> f32;
+    std::unique_ptr<Neighborlist<double>> f64;
+    std::vector<std::vector<int>> last; // result of the last build, served by fetch
+};
+static NeighborlistHandle &as_nb(tmb_neighborlist h) {
+    if (h == nullptr) {
+        throw std::runtime_error("null neighborlist handle");
+    }
+    return *static_cast<NeighborlistHandle *>(h);
+}
+
+static void check_precision(int precision) {
+    if (precision != TMB_F32 && precision != TMB_F64) {
+        throw std::runtime_error("precision must be 32 or 64");
+    }
+}
+
+static i128 *as_i128(tmb_i128 *p) {
+    static_assert(sizeof(tmb_i128) == sizeof(i128), "tmb_i128 must alias __int128");
+    return reinterpret_cast<i128 *>(p);
+}
+
+template <template <typename> class PotT>
+static int create_bonded(int precision, const int32_t *idxs, int n_values, tmb_potential *out) {
+    return guarded([&] {
+        check_precision(precision);
+        std::vector<int> v(idxs, idxs + (n_values > 0 ? n_values : 0));
+        PotPtr p;
+        if (precision == TMB_F32) {
+            p = std::make_shared<PotT<float>>(v);
+        } else {
+            p = std::make_shared<PotT<double>>(v);
+        }
+        *out = new PotPtr(p);
+    });
+}
+
+extern "C" {
+
+const char *tmb_last_error(void) { return g_last_error.c_str(); }
+int tmb_version(void) { return 1; }
+uint64_t tmb_fixed_exponent(void) { return FIXED_EXPONENT; }
+long long tmb_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+int tmb_cuda_device_reset(void) {
+    return guarded([&] { TMB_CUDA(cudaDeviceReset()); });
+}
+int tmb_set_stream(void *cuda_stream) {
+    return guarded([&] { set_main_stream(static_cast<cudaStream_t>(cuda_stream)); });
+}
+int tmb_device_synchronize(void) {
+    return guarded([&] { TMB_CUDA(cudaDeviceSynchronize()); });
+}
+
+// ---- constructors ---------------------------------------------------------------------------------------------
+int tmb_harmonic_bond_create(int precision, const int32_t *bond_idxs, int n_values, tmb_potential *out) {
+    return create_bonded<HarmonicBond>(precision, bond_idxs, n_values, out);
+}
+int tmb_harmonic_angle_create(int precision, const int32_t *angle_idxs, int n_values, tmb_potential *out) {
+    return create_bonded<HarmonicAngle>(precision, angle_idxs, n_values, out);
+}
+int tmb_periodic_torsion_create(int precision, const int32_t *torsion_idxs, int n_values, tmb_potential *out) {
+    return create_bonded<PeriodicTorsion>(precision, torsion_idxs, n_values, out);
+}
+
+int tmb_nonbonded_all_pairs_create(
+    int precision, int num_atoms, double beta, double cutoff, const int32_t *atom_idxs, int n_atom_idxs,
+    int disable_hilbert_sort, double nblist_padding, tmb_potential *out) {
+    return guarded([&] {
+        check_precision(precision);
+        std::optional<std::set<int>> idxs;
+        if (n_atom_idxs >= 0) {
+            // the reference converts the array to a std::set (dedup + ascending) before validating, wrap_kernels.cpp:1460
+            idxs = std::set<int>(atom_idxs, atom_idxs + n_atom_idxs);
+            std::vector<int> raw(atom_idxs, atom_idxs + n_atom_idxs);
+            verify_atom_idxs(num_atoms, raw);
+        }
+        PotPtr p;
+        if (precision == TMB_F32) {
+            p = std::make_shared<NonbondedAllPairs<float>>(num_atoms, beta, cutoff, idxs, disable_hilbert_sort != 0, nblist_padding);
+        } else {
+            p = std::make_shared<NonbondedAllPairs<double>>(num_atoms, beta, cutoff, idxs, disable_hilbert_sort != 0, nblist_padding);
+        }
+        *out = new PotPtr(p);
+    });
+}
+
+int tmb_nonbonded_all_pairs_set_atom_idxs(tmb_potential pot, const int32_t *atom_idxs, int n) {
+    return guarded([&] {
+        std::vector<int> v(atom_idxs, atom_idxs + (n > 0 ? n : 0));
+        if (auto a = std::dynamic_pointer_cast<NonbondedAllPairs<float>>(as_pot(pot))) {
+            a->set_atom_idxs(v);
+        } else if (auto b = std::dynamic_pointer_cast<NonbondedAllPairs<double>>(as_pot(pot))) {
+            b->set_atom_idxs(v);
+        } else {
+            throw std::runtime_error("not a NonbondedAllPairs potential");
+        }
+    });
+}
+
+int tmb_nonbonded_all_pairs_get_num_atom_idxs(tmb_potential pot, int *out) {
+    return guarded([&] {
+        if (auto a = std::dynamic_pointer_cast<NonbondedAllPairs<float>>(as_pot(pot))) {
+            *out = a->get_num_atom_idxs();
+        } else if (auto b = std::dynamic_pointer_cast<NonbondedAllPairs<double>>(as_pot(pot))) {
+            *out = b->get_num_atom_idxs();
+        } else {
+            throw std::runtime_error("not a NonbondedAllPairs potential");
+        }
+    });
+}
+
+int tmb_nonbonded_all_pairs_get_atom_idxs(tmb_potential pot, int32_t *out) {
+    return guarded([&] {
+        std::vector<int> v;
+        if (auto a = std::dynamic_pointer_cast<NonbondedAllPairs<float>>(as_pot(pot))) {
+            v = a->get_atom_idxs();
+        } else if (auto b = std::dynamic_pointer_cast<NonbondedAllPairs<double>>(as_pot(pot))) {
+            v = b->get_atom_idxs();
+        } else {
+            throw std::runtime_error("not a NonbondedAllPairs potential");
+        }
+        std::copy(v.begin(), v.end(), out);
+    });
+}
+
+int tmb_nonbonded_interaction_group_create(
+    int precision, int num_atoms, const int32_t *row_atom_idxs, int n_row, double beta, double cutoff,
+    const int32_t *col_atom_idxs, int n_col, int disable_hilbert_sort, double nblist_padding, tmb_potential *out) {
+    return guarded([&] {
+        check_precision(precision);
+        std::vector<int> rows(row_atom_idxs, row_atom_idxs + (n_row > 0 ? n_row : 0));
+        std::vector<int> cols;
+        if (n_col >= 0) {
+            cols.assign(col_atom_idxs, col_atom_idxs + n_col);
+        } else {
+            // None: columns are the complement of the rows (wrap_kernels.cpp:1496-1502)
+            std::set<int> rs(rows.begin(), rows.end());
+            for (int i = 0; i < num_atoms; i++) {
+                if (!rs.count(i)) {
+                    cols.push_back(i);
+                }
+            }
+        }
+        PotPtr p;
+        if (precision == TMB_F32) {
+            p = std::make_shared<NonbondedInteractionGroup<float>>(
+                num_atoms, rows, cols, beta, cutoff, disable_hilbert_sort != 0, nblist_padding);
+        } else {
+            p = std::make_shared<NonbondedInteractionGroup<double>>(
+                num_atoms, rows, cols, beta, cutoff, disable_hilbert_sort != 0, nblist_padding);
+        }
+        *out = new PotPtr(p);
+    });
+}
+
+int tmb_nonbonded_interaction_group_set_atom_idxs(
+    tmb_potential pot, const int32_t *row_atom_idxs, int n_row, const int32_t *col_atom_idxs, int n_col) {
+    return guarded([&] {
+        std::vector<int> rows(row_atom_idxs, row_atom_idxs + (n_row > 0 ? n_row : 0));
+        std::vector<int> cols(col_atom_idxs, col_atom_idxs + (n_col > 0 ? n_col : 0));
+        if (auto a = std::dynamic_pointer_cast<NonbondedInteractionGroup<float>>(as_pot(pot))) {
+            a->set_atom_idxs(rows, cols);
+        } else if (auto b = std::dynamic_pointer_cast<NonbondedInteractionGroup<double>>(as_pot(pot))) {
+            b->set_atom_idxs(rows, cols);
+        } else {
+            throw std::runtime_error("not a NonbondedInteractionGroup potential");
+        }
+    });
+}
+
+int tmb_nonbonded_pair_list_create(
+    int precision, int negated, const int32_t *pair_idxs, int n_pair_values, const double *scales, int n_scale_values,
+    double beta, double cutoff, tmb_potential *out) {
+    return guarded([&] {
+        check_precision(precision);
+        std::vector<int> pairs(pair_idxs, pair_idxs + (n_pair_values > 0 ? n_pair_values : 0));
+        std::vector<double> sc(scales, scales + (n_scale_values > 0 ? n_scale_values : 0));
+        PotPtr p;
+        if (precision == TMB_F32) {
+            if (negated) {
+                p = std::make_shared<NonbondedPairList<float, true>>(pairs, sc, beta, cutoff);
+            } else {
+                p = std::make_shared<NonbondedPairList<float, false>>(pairs, sc, beta, cutoff);
+            }
+        } else {
+            if (negated) {
+                p = std::make_shared<NonbondedPairList<double, true>>(pairs, sc, beta, cutoff);
+            } else {
+                p = std::make_shared<NonbondedPairList<double, false>>(pairs, sc, beta, cutoff);
+            }
+        }
+        *out = new PotPtr(p);
+    });
+}
+
+int tmb_summed_potential_create(
+    const tmb_potential *potentials, int n_potentials, const int32_t *params_sizes, int n_sizes, int parallel,
+    tmb_potential *out) {
+    return guarded([&] {
+        std::vector<PotPtr> pots;
+        for (int i = 0; i < n_potentials; i++) {
+            pots.push_back(as_pot(potentials[i]));
+        }
+        std::vector<int> sizes(params_sizes, params_sizes + (n_sizes > 0 ? n_sizes : 0));
+        *out = new PotPtr(std::make_shared<SummedPotential>(pots, sizes, parallel != 0));
+    });
+}
+
+int tmb_fanout_summed_potential_create(const tmb_potential *potentials, int n_potentials, int parallel, tmb_potential *out) {
+    return guarded([&] {
+        std::vector<PotPtr> pots;
+        for (int i = 0; i < n_potentials; i++) {
+            pots.push_back(as_pot(potentials[i]));
+        }
+        *out = new PotPtr(std::make_shared<FanoutSummedPotential>(pots, parallel != 0));
+    });
+}
+
+int tmb_potential_destroy(tmb_potential pot) {
+    return guarded([&] { delete static_cast<PotPtr *>(pot); });
+}
+
+// ---- evaluation -----------------------------------------------------------------------------------------------
+int tmb_potential_execute(
+    tmb_potential pot, int N, int P, const double *coords, const double *params, const double *box, uint64_t *du_dx,
+    uint64_t *du_dp, tmb_i128 *u) {
+    return guarded([&] {
+        as_pot(pot)->execute_host(N, P, coords, params, box, reinterpret_cast<u64 *>(du_dx), reinterpret_cast<u64 *>(du_dp), as_i128(u));
+    });
+}
+
+int tmb_potential_execute_batch(
+    tmb_potential pot, int coord_batches, int N, int param_batches, int P, const double *coords, const double *params,
+    const double *boxes, uint64_t *du_dx, uint64_t *du_dp, tmb_i128 *u) {
+    return guarded([&] {
+        as_pot(pot)->execute_batch_host(
+            coord_batches, N, param_batches, P, coords, params, boxes, reinterpret_cast<u64 *>(du_dx),
+            reinterpret_cast<u64 *>(du_dp), as_i128(u));
+    });
+}
+
+int tmb_potential_execute_batch_sparse(
+    tmb_potential pot, int coords_size, int N, int params_size, int P, int batch_size, const uint32_t *coords_batch_idxs,
+    const uint32_t *params_batch_idxs, const double *coords, const double *params, const double *boxes, uint64_t *du_dx,
+    uint64_t *du_dp, tmb_i128 *u) {
+    return guarded([&] {
+        as_pot(pot)->execute_batch_sparse_host(
+            coords_size, N, params_size, P, batch_size, coords_batch_idxs, params_batch_idxs, coords, params, boxes,
+            reinterpret_cast<u64 *>(du_dx), reinterpret_cast<u64 *>(du_dp), as_i128(u));
+    });
+}
+
+int tmb_potential_du_dp_fixed_to_float(tmb_potential pot, int N, int P, const uint64_t *du_dp, double *out) {
+    return guarded([&] { as_pot(pot)->du_dp_fixed_to_float(N, P, reinterpret_cast<const u64 *>(du_dp), out); });
+}
+
+int tmb_potential_execute_device(
+    tmb_potential pot, int N, int P, const double *d_coords, const double *d_params, const double *d_box,
+    uint64_t *d_du_dx, uint64_t *d_du_dp, tmb_i128 *d_u, void *cuda_stream) {
+    return guarded([&] {
+        as_pot(pot)->execute_device(
+            N, P, d_coords, d_params, d_box, reinterpret_cast<u64 *>(d_du_dx), reinterpret_cast<u64 *>(d_du_dp),
+            as_i128(d_u), static_cast<cudaStream_t>(cuda_stream));
+    });
+}
+
+int tmb_nonbonded_num_tiles(tmb_potential pot, unsigned int *out) {
+    return guarded([&] {
+        if (auto a = std::dynamic_pointer_cast<NonbondedTiled<float>>(as_pot(pot))) {
+            *out = a->num_tiles();
+        } else if (auto b = std::dynamic_pointer_cast<NonbondedTiled<double>>(as_pot(pot))) {
+            *out = b->num_tiles();
+        } else {
+            throw std::runtime_error("not a tile-list nonbonded potential");
+        }
+    });
+}
+
+// ---- BoundPotential ---------------------------------------------------------------------------------------------
+int tmb_bound_potential_create(tmb_potential pot, const double *params, int n_params, tmb_bound_potential *out) {
+    return guarded([&] {
+        std::vector<double> p(params, params + (n_params > 0 ? n_params : 0));
+        *out = new BpPtr(std::make_shared<BoundPotential>(as_pot(pot), p));
+    });
+}
+int tmb_bound_potential_destroy(tmb_bound_potential bp) {
+    return guarded([&] { delete static_cast<BpPtr *>(bp); });
+}
+int tmb_bound_potential_set_params(tmb_bound_potential bp, const double *params, int n_params) {
+    return guarded([&] {
+        std::vector<double> p(params, params + (n_params > 0 ? n_params : 0));
+        as_bp(bp)->set_params(p);
+    });
+}
+int tmb_bound_potential_size(tmb_bound_potential bp, int *out) {
+    return guarded([&] { *out = as_bp(bp)->size; });
+}
+int tmb_bound_potential_execute(
+    tmb_bound_potential bp, int N, const double *coords, const double *box, uint64_t *du_dx, tmb_i128 *u) {
+    return guarded([&] { as_bp(bp)->execute_host(N, coords, box, reinterpret_cast<u64 *>(du_dx), as_i128(u)); });
+}
+int tmb_bound_potential_execute_batch(
+    tmb_bound_potential bp, int coord_batches, int N, const double *coords, const double *boxes, uint64_t *du_dx,
+    tmb_i128 *u) {
+    return guarded([&] {
+        as_bp(bp)->execute_batch_host(coord_batches, N, coords, boxes, reinterpret_cast<u64 *>(du_dx), as_i128(u));
+    });
+}
+int tmb_bound_potential_set_params_device(tmb_bound_potential bp, const double *d_params, int n_params, void *cuda_stream) {
+    return guarded([&] { as_bp(bp)->set_params_device(n_params, d_params, static_cast<cudaStream_t>(cuda_stream)); });
+}
+int tmb_bound_potential_execute_device(
+    tmb_bound_potential bp, int N, const double *d_coords, const double *d_box, uint64_t *d_du_dx, tmb_i128 *d_u,
+    void *cuda_stream) {
+    return guarded([&] {
+        as_bp(bp)->execute_device(
+            N, d_coords, d_box, reinterpret_cast<u64 *>(d_du_dx), nullptr, as_i128(d_u), static_cast<cudaStream_t>(cuda_stream));
+    });
+}
+
+// ---- integrator / context -----------------------------------------------------------------------------------------
+int tmb_langevin_integrator_create(
+    const double *masses, int N, double temperature, double dt, double friction, int seed, tmb_integrator *out) {
+    return guarded([&] { *out = new IntgPtr(std::make_shared<LangevinIntegrator>(N, masses, temperature, dt, friction, seed)); });
+}
+int tmb_langevin_integrator_destroy(tmb_integrator intg) {
+    return guarded([&] { delete static_cast<IntgPtr *>(intg); });
+}
+int tmb_langevin_integrator_set_noise(tmb_integrator intg, const float *noise) {
+    return guarded([&] { as_intg(intg)->set_external_noise(noise); });
+}
+
+int tmb_context_create(
+    const double *x0, const double *v0, const double *box, int N, tmb_integrator intg, const tmb_bound_potential *bps,
+    int n_bps, tmb_context *out) {
+    return guarded([&] {
+        std::vector<BpPtr> v;
+        for (int i = 0; i < n_bps; i++) {
+            v.push_back(as_bp(bps[i]));
+        }
+        *out = new Context(N, x0, v0, box, as_intg(intg), v);
+    });
+}
+int tmb_context_destroy(tmb_context ctx) {
+    return guarded([&] { delete static_cast<Context *>(ctx); });
+}
+int tmb_context_step(tmb_context ctx) {
+    return guarded([&] { as_ctx(ctx).step(); });
+}
+int tmb_context_multiple_steps(tmb_context ctx, int n_steps, int n_samples, double *h_x, double *h_box) {
+    return guarded([&] { as_ctx(ctx).multiple_steps(n_steps, n_samples, h_x, h_box); });
+}
+int tmb_context_set_x_t(tmb_context ctx, const double *x) {
+    return guarded([&] { as_ctx(ctx).set_x_t(x); });
+}
+int tmb_context_set_v_t(tmb_context ctx, const double *v) {
+    return guarded([&] { as_ctx(ctx).set_v_t(v); });
+}
+int tmb_context_set_box(tmb_context ctx, const double *box) {
+    return guarded([&] { as_ctx(ctx).set_box(box); });
+}
+int tmb_context_get_x_t(tmb_context ctx, double *x) {
+    return guarded([&] { as_ctx(ctx).get_x_t(x); });
+}
+int tmb_context_get_v_t(tmb_context ctx, double *v) {
+    return guarded([&] { as_ctx(ctx).get_v_t(v); });
+}
+int tmb_context_get_box(tmb_context ctx, double *box) {
+    return guarded([&] { as_ctx(ctx).get_box(box); });
+}
+int tmb_context_num_atoms(tmb_context ctx, int *out) {
+    return guarded([&] { *out = as_ctx(ctx).num_atoms(); });
+}
+int tmb_context_set_stream(tmb_context ctx, void *cuda_stream) {
+    return guarded([&] { as_ctx(ctx).set_stream(static_cast<cudaStream_t>(cuda_stream)); });
+}
+int tmb_context_set_use_graphs(tmb_context ctx, int on) {
+    return guarded([&] { as_ctx(ctx).set_use_graphs(on != 0); });
+}
+int tmb_context_device_state(tmb_context ctx, double **d_x, double **d_v, double **d_box) {
+    return guarded([&] {
+        *d_x = as_ctx(ctx).d_x();
+        *d_v = as_ctx(ctx).d_v();
+        *d_box = as_ctx(ctx).d_box();
+    });
+}
+
+// ---- neighbour list / hilbert ---------------------------------------------------------------------------------------
+int tmb_neighborlist_create(int precision, int N, tmb_neighborlist *out) {
+    return guarded([&] {
+        check_precision(precision);
+        std::unique_ptr<NeighborlistHandle> h(new NeighborlistHandle());
+        h->precision = precision;
+        if (precision == TMB_F32) {
+            h->f32.reset(new Neighborlist<float>(N));
+        } else {
+            h->f64.reset(new Neighborlist<double>(N));
+        }
+        *out = h.release();
+    });
+}
+int tmb_neighborlist_destroy(tmb_neighborlist nb) {
+    return guarded([&] { delete static_cast<NeighborlistHandle *>(nb); });
+}
+
+#define NB_DISPATCH(h, expr_f32, expr_f64)                                                                             \
+    do {                                                                                                               \
+        if ((h).precision == TMB_F32) {                                                                                \
+            expr_f32;                                                                                                  \
+        } else {                                                                                                       \
+            expr_f64;                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+
+int tmb_neighborlist_build(
+    tmb_neighborlist nb, int N, const double *coords, const double *box, double cutoff, int *n_row_blocks, int *n_entries) {
+    return guarded([&] {
+        NeighborlistHandle &h = as_nb(nb);
+        NB_DISPATCH(h, h.last = h.f32->get_nblist_host(N, coords, box, cutoff), h.last = h.f64->get_nblist_host(N, coords, box, cutoff));
+        size_t total = 0;
+        for (auto &row : h.last) {
+            total += row.size();
+        }
+        *n_row_blocks = static_cast<int>(h.last.size());
+        *n_entries = static_cast<int>(total);
+    });
+}
+int tmb_neighborlist_fetch(tmb_neighborlist nb, int32_t *offsets, int32_t *atoms) {
+    return guarded([&] {
+        NeighborlistHandle &h = as_nb(nb);
+        int32_t off = 0;
+        for (size_t r = 0; r < h.last.size(); r++) {
+            offsets[r] = off;
+            for (int a : h.last[r]) {
+                atoms[off++] = a;
+            }
+        }
+        offsets[h.last.size()] = off;
+    });
+}
+int tmb_neighborlist_compute_block_bounds(
+    tmb_neighborlist nb, int N, const double *coords, const double *box, double *ctrs, double *exts) {
+    return guarded([&] {
+        NeighborlistHandle &h = as_nb(nb);
+        NB_DISPATCH(h, h.f32->compute_block_bounds_host(N, coords, box, ctrs, exts), h.f64->compute_block_bounds_host(N, coords, box, ctrs, exts));
+    });
+}
+int tmb_neighborlist_set_row_idxs(tmb_neighborlist nb, const uint32_t *idxs, int n) {
+    return guarded([&] {
+        NeighborlistHandle &h = as_nb(nb);
+        std::vector<unsigned int> v(idxs, idxs + (n > 0 ? n : 0));
+        NB_DISPATCH(h, h.f32->set_row_idxs(v), h.f64->set_row_idxs(v));
+    });
+}
+int tmb_neighborlist_reset_row_idxs(tmb_neighborlist nb) {
+    return guarded([&] {
+        NeighborlistHandle &h = as_nb(nb);
+        NB_DISPATCH(h, h.f32->reset_row_idxs(), h.f64->reset_row_idxs());
+    });
+}
+int tmb_neighborlist_resize(tmb_neighborlist nb, int size) {
+    return guarded([&] {
+        NeighborlistHandle &h = as_nb(nb);
+        NB_DISPATCH(h, h.f32->resize(size), h.f64->resize(size));
+    });
+}
+int tmb_neighborlist_get_tile_ixn_count(tmb_neighborlist nb, unsigned int *out) {
+    return guarded([&] {
+        NeighborlistHandle &h = as_nb(nb);
+        NB_DISPATCH(h, *out = h.f32->num_tile_ixns(), *out = h.f64->num_tile_ixns());
+    });
+}
+int tmb_neighborlist_get_max_ixn_count(tmb_neighborlist nb, int *out) {
+    return guarded([&] {
+        NeighborlistHandle &h = as_nb(nb);
+        NB_DISPATCH(h, *out = h.f32->max_ixn_count(), *out = h.f64->max_ixn_count());
+    });
+}
+int tmb_neighborlist_get_num_row_idxs(tmb_neighborlist nb, int *out) {
+    return guarded([&] {
+        NeighborlistHandle &h = as_nb(nb);
+        NB_DISPATCH(h, *out = h.f32->get_num_row_idxs(), *out = h.f64->get_num_row_idxs());
+    });
+}
+
+int tmb_hilbert_sort_create(int size, tmb_hilbert_sort *out) {
+    return guarded([&] { *out = new HilbertSort(size); });
+}
+int tmb_hilbert_sort_destroy(tmb_hilbert_sort hs) {
+    return guarded([&] { delete static_cast<HilbertSort *>(hs); });
+}
+int tmb_hilbert_sort_sort(tmb_hilbert_sort hs, int N, const double *coords, const double *box, uint32_t *perm) {
+    return guarded([&] {
+        if (hs == nullptr) {
+            throw std::runtime_error("null hilbert sort handle");
+        }
+        std::vector<unsigned int> p = static_cast<HilbertSort *>(hs)->sort_host(N, coords, box);
+        std::copy(p.begin(), p.end(), perm);
+    });
+}
+
+int tmb_fill_normal(float *out, int n_atoms, uint64_t seed, uint64_t step) {
+    return guarded([&] {
+        DeviceBuffer<float> d(static_cast<size_t>(n_atoms) * 3);
+        launch_fill_normal(d.data, n_atoms, seed, step, main_stream());
+        TMB_CUDA(cudaStreamSynchronize(main_stream()));
+        d.copy_to(out);
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,234 @@
+// LangevinIntegrator and Context: the MD loop lives in C++ (reference langevin_integrator.cu:13-111, context.cu:28-322).
+//
+// B200 design: the steady-state step has no host decision in it (the neighbour-list rebuild is decided on the device),
+// so blocks of GRAPH_STEPS steps are captured once into a CUDA graph and replayed; the only eager steps are the ones
+// that re-sort atoms along the Hilbert curve (every 100th evaluation) and the remainders.
+#include "potential.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace tmb {
+
+constexpr double BOLTZ = 0.0083144621; // kJ/mol/K, reference timemachine/cpp/src/constants.hpp / constants.py:8
+
+__global__ void k_set_u64(unsigned long long *p, unsigned long long v) { *p = v; }
+
+LangevinIntegrator::LangevinIntegrator(int N, const double *masses, double temperature, double dt, double friction, int seed)
+    : N_(N), temperature_(temperature), dt_(static_cast<float>(dt)), seed_(static_cast<unsigned long long>(static_cast<long long>(seed))),
+      d_cbs_(N), d_ccs_(N), d_du_dx_(static_cast<size_t>(N) * 3), d_step_base_(1) {
+    ca_ = static_cast<float>(std::exp(-friction * dt));
+    const double kT = BOLTZ * temperature;
+    const double ccs_adjustment = std::sqrt(1 - std::exp(-2 * friction * dt));
+    std::vector<float> h_cbs(N), h_ccs(N);
+    for (int i = 0; i < N; i++) {
+        // dt_ is already rounded to f32 here, exactly as the reference does (langevin_integrator.cu:27)
+        h_cbs[i] = static_cast<float>(dt_ / masses[i]);
+        h_ccs[i] = static_cast<float>(ccs_adjustment * std::sqrt(kT / masses[i]));
+    }
+    d_cbs_.copy_from(h_cbs.data());
+    d_ccs_.copy_from(h_ccs.data());
+    d_du_dx_.zero(); // the update kernel re-zeroes the forces every step
+    d_step_base_.zero();
+    TMB_CUDA(cudaDeviceSynchronize());
+}
+
+void LangevinIntegrator::set_external_noise(const float *h_noise) {
+    if (h_noise == nullptr) {
+        external_noise_ = false;
+        return;
+    }
+    d_noise_.realloc(static_cast<size_t>(N_) * 3);
+    d_noise_.copy_from(h_noise);
+    external_noise_ = true;
+}
+
+void LangevinIntegrator::step_fwd(
+    std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box, unsigned int *d_idxs,
+    cudaStream_t stream, int graph_offset) {
+    const int n = static_cast<int>(bps.size());
+    // one stream per bound potential, forked from and joined back into `stream`
+    // (reference streamed_potential_runner.cu:10-29)
+    for (int i = 0; i < n; i++) {
+        cudaStream_t s = n > 1 ? fan_.fork(i, stream) : stream;
+        bps[i]->execute_device(N_, d_x, d_box, d_du_dx_.data, nullptr, nullptr, s);
+    }
+    if (n > 1) {
+        for (int i = 0; i < n; i++) {
+            fan_.join(i, stream);
+        }
+    }
+    BaoabArgs a;
+    a.N = N_;
+    a.ca = ca_;
+    a.idxs = d_idxs;
+    a.cbs = d_cbs_.data;
+    a.ccs = d_ccs_.data;
+    a.noise = external_noise_ ? d_noise_.data : nullptr;
+    a.seed = seed_;
+    if (graph_offset >= 0) {
+        a.step = static_cast<unsigned long long>(graph_offset);
+        a.step_base = d_step_base_.data;
+    } else {
+        a.step = static_cast<unsigned long long>(step_);
+        a.step_base = nullptr;
+    }
+    a.x = d_x;
+    a.v = d_v;
+    a.du_dx = d_du_dx_.data;
+    a.dt = dt_;
+    launch_baoab(a, stream);
+    step_++;
+}
+
+void LangevinIntegrator::publish_step_base(cudaStream_t stream) {
+    TMB_LAUNCH(k_set_u64, 1, 1, 0, stream, d_step_base_.data, static_cast<unsigned long long>(step_));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GRAPH_STEPS = 10;
+
+Context::Context(
+    int N, const double *x0, const double *v0, const double *box0, std::shared_ptr<LangevinIntegrator> intg,
+    std::vector<std::shared_ptr<BoundPotential>> bps)
+    : N_(N), d_x_(static_cast<size_t>(N) * 3), d_v_(static_cast<size_t>(N) * 3), d_box_(9), intg_(std::move(intg)),
+      bps_(std::move(bps)) {
+    if (intg_->num_atoms() != N) {
+        throw std::runtime_error("integrator N != x0 N");
+    }
+    d_x_.copy_from(x0);
+    d_v_.copy_from(v0);
+    d_box_.copy_from(box0);
+    for (auto &bp : bps_) {
+        collect_nonbonded_cutoffs(bp->potential, nb_cutoffs_with_padding_);
+    }
+    TMB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+}
+
+Context::~Context() {
+    destroy_graph();
+    if (stream_) {
+        cudaStreamDestroy(stream_);
+    }
+}
+
+void Context::destroy_graph() {
+    if (graph_exec_) {
+        cudaGraphExecDestroy(graph_exec_);
+        graph_exec_ = nullptr;
+    }
+}
+
+void Context::set_stream(cudaStream_t s) {
+    destroy_graph();
+    user_stream_ = s;
+}
+
+void Context::run_steps(int n, cudaStream_t stream) {
+    int remaining = n;
+    while (remaining > 0) {
+        int cap = 1 << 30;
+        for (auto &bp : bps_) {
+            cap = std::min(cap, bp->potential->capturable_steps());
+        }
+        if (use_graphs_ && cap >= GRAPH_STEPS && remaining >= GRAPH_STEPS) {
+            intg_->publish_step_base(stream);
+            if (graph_exec_ == nullptr || graph_stream_ != stream) {
+                destroy_graph();
+                cudaGraph_t graph = nullptr;
+                const long long launches_before = g_kernel_launches.load();
+                TMB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+                try {
+                    for (int s = 0; s < GRAPH_STEPS; s++) {
+                        intg_->step_fwd(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream, s);
+                    }
+                } catch (...) {
+                    cudaStreamEndCapture(stream, &graph);
+                    if (graph) {
+                        cudaGraphDestroy(graph);
+                    }
+                    throw;
+                }
+                TMB_CUDA(cudaStreamEndCapture(stream, &graph));
+                TMB_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
+                TMB_CUDA(cudaGraphDestroy(graph));
+                graph_stream_ = stream;
+                // the capture pass already advanced the host-side counters of the potentials and the integrator, and
+                // counted its kernels once (they run on the first launch below)
+                graph_kernels_ = g_kernel_launches.load() - launches_before;
+            } else {
+                for (auto &bp : bps_) {
+                    bp->potential->advance(GRAPH_STEPS);
+                }
+                intg_->advance(GRAPH_STEPS);
+                g_kernel_launches.fetch_add(graph_kernels_, std::memory_order_relaxed);
+            }
+            TMB_CUDA(cudaGraphLaunch(graph_exec_, stream));
+            remaining -= GRAPH_STEPS;
+        } else {
+            intg_->step_fwd(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream, -1);
+            remaining -= 1;
+        }
+    }
+}
+
+void Context::step() {
+    cudaStream_t stream = active_stream();
+    intg_->step_fwd(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream, -1);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Context::verify_frame(const double *h_x, const double *h_box) const {
+    if (nb_cutoffs_with_padding_.empty()) {
+        return;
+    }
+    for (double c : nb_cutoffs_with_padding_) {
+        for (int i = 0; i < 3; i++) {
+            if (h_box[i * 3 + i] < 2 * c) {
+                throw std::runtime_error(
+                    "cutoff with padding is more than half of the box width, neighborlist is no longer reliable");
+            }
+        }
+    }
+    const double max_box = std::max(h_box[0], std::max(h_box[4], h_box[8]));
+    const auto mm = std::minmax_element(h_x, h_x + static_cast<size_t>(N_) * 3);
+    if (max_box * 100.0 < (*mm.second - *mm.first)) {
+        throw std::runtime_error(
+            "simulation unstable: dimensions of coordinates two orders of magnitude larger than max box dimension");
+    }
+}
+
+void Context::multiple_steps(int n_steps, int n_samples, double *h_x, double *h_box) {
+    if (n_samples < 0) {
+        throw std::runtime_error("n_samples < 0");
+    }
+    const int interval = n_samples > 0 ? n_steps / n_samples : n_steps + 1;
+    cudaStream_t stream = active_stream();
+    int done = 0;
+    int stored = 0;
+    while (done < n_steps) {
+        const int next_store = (done / interval + 1) * interval;
+        const int chunk = std::min(n_steps, next_store) - done;
+        run_steps(chunk, stream);
+        done += chunk;
+        if (done % interval == 0 && stored < n_samples) {
+            double *xp = h_x + static_cast<size_t>(stored) * N_ * 3;
+            double *bp = h_box + static_cast<size_t>(stored) * 9;
+            TMB_CUDA(cudaMemcpyAsync(xp, d_x_.data, d_x_.bytes(), cudaMemcpyDeviceToHost, stream));
+            TMB_CUDA(cudaMemcpyAsync(bp, d_box_.data, d_box_.bytes(), cudaMemcpyDeviceToHost, stream));
+            TMB_CUDA(cudaStreamSynchronize(stream));
+            verify_frame(xp, bp);
+            stored++;
+        }
+    }
+    TMB_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Context::set_x_t(const double *h) { d_x_.copy_from(h); }
+void Context::set_v_t(const double *h) { d_v_.copy_from(h); }
+void Context::set_box(const double *h) { d_box_.copy_from(h); }
+void Context::get_x_t(double *h) const { d_x_.copy_to(h); }
+void Context::get_v_t(double *h) const { d_v_.copy_to(h); }
+void Context::get_box(double *h) const { d_box_.copy_to(h); }
+
+} // namespace tmb

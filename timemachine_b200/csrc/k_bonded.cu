@@ -1,0 +1,255 @@
+// Bonded terms: harmonic bond, harmonic angle (4-D regularised, Kahan-stable), periodic torsion.
+// One thread per term, fixed-point atomics for du/dx and du/dp, int128 energy reduced in-kernel.
+// Functional forms follow reference k_harmonic_bond.cuh:7-60, k_harmonic_angle.cuh:10-146, k_periodic_torsion.cuh:20-131.
+// Compiled with --fmad=false: products and sums are individually rounded, which is what gives the reference's
+// bitwise i<->k (angle) and cross-product anti-commutativity (torsion) symmetries without special intrinsics.
+#include "fixed_point.cuh"
+#include "kernels.hpp"
+#include "reduce.cuh"
+
+namespace tmb {
+
+constexpr int BD_THREADS = 128;
+
+int bonded_grid(int n_terms) {
+    int g = ceil_div(n_terms, BD_THREADS);
+    const int cap = sm_count() * 8;
+    return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
+template <typename Real> struct V3 {
+    Real x, y, z;
+};
+
+template <typename Real> __device__ __forceinline__ V3<Real> load3(const double *__restrict__ x, int idx) {
+    V3<Real> r;
+    r.x = static_cast<Real>(x[idx * 3 + 0]);
+    r.y = static_cast<Real>(x[idx * 3 + 1]);
+    r.z = static_cast<Real>(x[idx * 3 + 2]);
+    return r;
+}
+template <typename Real> __device__ __forceinline__ V3<Real> sub3(const V3<Real> &a, const V3<Real> &b) {
+    return {a.x - b.x, a.y - b.y, a.z - b.z};
+}
+template <typename Real> __device__ __forceinline__ Real dot3(const V3<Real> &a, const V3<Real> &b) {
+    return a.x * b.x + a.y * b.y + a.z * b.z;
+}
+template <typename Real> __device__ __forceinline__ V3<Real> cross3(const V3<Real> &a, const V3<Real> &b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ void add_force(u64 *__restrict__ du_dx, int atom, u64 fx, u64 fy, u64 fz) {
+    atomicAdd(du_dx + atom * 3 + 0, fx);
+    atomicAdd(du_dx + atom * 3 + 1, fy);
+    atomicAdd(du_dx + atom * 3 + 2, fz);
+}
+
+// ---- u = k/2 (|x_i - x_j| - b0)^2 -----------------------------------------------------------------------------
+template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_harmonic_bond(const BondedArgs a) {
+    __shared__ i128 scratch[BD_THREADS / WARP];
+    i128 energy = 0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.n_terms; b += gridDim.x * blockDim.x) {
+        const int src = a.idxs[b * 2 + 0];
+        const int dst = a.idxs[b * 2 + 1];
+        const V3<Real> d = sub3(load3<Real>(a.x, src), load3<Real>(a.x, dst));
+        const Real kb = static_cast<Real>(a.p[b * 2 + 0]);
+        const Real b0 = static_cast<Real>(a.p[b * 2 + 1]);
+        const Real r = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+        const Real db = r - b0;
+        if (a.du_dx != nullptr) {
+            const Real inv_r = 1 / r;
+            // b0 == 0 is the "spring to a point" case: the gradient is k * delta without the 0/0
+            const Real gx = b0 != 0 ? kb * db * d.x * inv_r : kb * d.x;
+            const Real gy = b0 != 0 ? kb * db * d.y * inv_r : kb * d.y;
+            const Real gz = b0 != 0 ? kb * db * d.z * inv_r : kb * d.z;
+            add_force(a.du_dx, src, to_fixed_force(gx), to_fixed_force(gy), to_fixed_force(gz));
+            add_force(a.du_dx, dst, to_fixed_force(-gx), to_fixed_force(-gy), to_fixed_force(-gz));
+        }
+        if (a.du_dp != nullptr) {
+            // du/dk is formed in double even for the f32 kernel (reference k_harmonic_bond.cuh:52: `0.5 * db * db`)
+            atomicAdd(a.du_dp + b * 2 + 0, to_fixed_force(0.5 * static_cast<double>(db) * static_cast<double>(db)));
+            atomicAdd(a.du_dp + b * 2 + 1, to_fixed_force(-kb * db));
+        }
+        if (a.d_u != nullptr) {
+            energy += energy_to_fixed<Real>(kb / 2 * db * db);
+        }
+    }
+    if (a.d_u != nullptr) {
+        grid_finish_energy(energy, scratch, a.u_partials, a.ticket, a.d_u);
+    }
+}
+
+// ---- u = k/2 (theta - a0)^2, theta from the stable 2 atan2(|n_jk r_ji - n_ji r_jk|, |n_jk r_ji + n_ji r_jk|) ---
+// The vectors carry a 4th component eps (a parameter) so that collinear geometries stay differentiable.
+template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_harmonic_angle(const BondedArgs a) {
+    __shared__ i128 scratch[BD_THREADS / WARP];
+    i128 energy = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_terms; t += gridDim.x * blockDim.x) {
+        const int i = a.idxs[t * 3 + 0];
+        const int j = a.idxs[t * 3 + 1];
+        const int k = a.idxs[t * 3 + 2];
+        const Real ka = static_cast<Real>(a.p[t * 3 + 0]);
+        const Real a0 = static_cast<Real>(a.p[t * 3 + 1]);
+        const Real eps = static_cast<Real>(a.p[t * 3 + 2]);
+
+        const V3<Real> xj = load3<Real>(a.x, j);
+        const V3<Real> vji = sub3(load3<Real>(a.x, i), xj);
+        const V3<Real> vjk = sub3(load3<Real>(a.x, k), xj);
+        const Real rji[4] = {vji.x, vji.y, vji.z, eps};
+        const Real rjk[4] = {vjk.x, vjk.y, vjk.z, eps};
+        Real sji = 0, sjk = 0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            sji += rji[d] * rji[d];
+            sjk += rjk[d] * rjk[d];
+        }
+        const Real nji = sqrt(sji + eps * eps);
+        const Real njk = sqrt(sjk + eps * eps);
+
+        Real hi = 0, lo = 0;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const Real p = njk * rji[d];
+            const Real q = nji * rjk[d];
+            const Real m = p - q;
+            const Real s = p + q;
+            hi += m * m;
+            lo += s * s;
+        }
+        const Real theta = 2 * atan2(sqrt(hi), sqrt(lo));
+        const Real delta = theta - a0;
+
+        // gradient direction via a x (b x c) = b (a.c) - c (a.b), in 4-D
+        Real a_dot_b = 0, a_dot_a = 0, b_dot_b = 0;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            a_dot_b += rji[d] * rjk[d];
+            a_dot_a += rji[d] * rji[d];
+            b_dot_b += rjk[d] * rjk[d];
+        }
+        Real aab[4], bba[4];
+        Real aab2 = 0, bba2 = 0;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            aab[d] = rji[d] * a_dot_b - rjk[d] * a_dot_a;
+            bba[d] = rjk[d] * a_dot_b - rji[d] * b_dot_b;
+            aab2 += aab[d] * aab[d];
+            bba2 += bba[d] * bba[d];
+        }
+        const Real aab_n = sqrt(aab2);
+        const Real bba_n = sqrt(bba2);
+        const Real pref = ka * delta;
+        const Real coeff_i = pref * (1 / nji);
+        const Real coeff_k = pref * (1 / njk);
+
+        if (a.du_dx != nullptr) {
+            Real gi[3], gk[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                gi[d] = coeff_i * (aab_n == 0 ? static_cast<Real>(0) : aab[d] / aab_n);
+                gk[d] = coeff_k * (bba_n == 0 ? static_cast<Real>(0) : bba[d] / bba_n);
+            }
+            add_force(a.du_dx, i, to_fixed_force(gi[0]), to_fixed_force(gi[1]), to_fixed_force(gi[2]));
+            add_force(a.du_dx, k, to_fixed_force(gk[0]), to_fixed_force(gk[1]), to_fixed_force(gk[2]));
+            add_force(
+                a.du_dx, j, to_fixed_force(-gi[0] - gk[0]), to_fixed_force(-gi[1] - gk[1]), to_fixed_force(-gi[2] - gk[2]));
+        }
+        if (a.du_dp != nullptr) {
+            atomicAdd(a.du_dp + t * 3 + 0, to_fixed_force(delta * delta / 2));
+            atomicAdd(a.du_dp + t * 3 + 1, to_fixed_force(-delta * ka));
+            const Real e0 = aab_n == 0 ? static_cast<Real>(0) : coeff_i * aab[3] / aab_n;
+            const Real e1 = bba_n == 0 ? static_cast<Real>(0) : coeff_k * bba[3] / bba_n;
+            atomicAdd(a.du_dp + t * 3 + 2, to_fixed_force(e0 + e1));
+        }
+        if (a.d_u != nullptr) {
+            energy += energy_to_fixed<Real>((ka / 2) * delta * delta);
+        }
+    }
+    if (a.d_u != nullptr) {
+        grid_finish_energy(energy, scratch, a.u_partials, a.ticket, a.d_u);
+    }
+}
+
+// ---- u = k (1 + cos(n phi - phi0)), phi = atan2((n1 x n2).r_kj/|r_kj|, n1.n2) ----------------------------------
+template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_periodic_torsion(const BondedArgs a) {
+    __shared__ i128 scratch[BD_THREADS / WARP];
+    i128 energy = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_terms; t += gridDim.x * blockDim.x) {
+        const int i = a.idxs[t * 4 + 0];
+        const int j = a.idxs[t * 4 + 1];
+        const int k = a.idxs[t * 4 + 2];
+        const int l = a.idxs[t * 4 + 3];
+        const V3<Real> xi = load3<Real>(a.x, i), xj = load3<Real>(a.x, j), xk = load3<Real>(a.x, k), xl = load3<Real>(a.x, l);
+        const V3<Real> rij = sub3(xj, xi);
+        V3<Real> rkj = sub3(xj, xk);
+        const V3<Real> rkl = sub3(xl, xk);
+
+        const Real rkj2 = dot3(rkj, rkj);
+        const Real rkj_n = sqrt(rkj2);
+        const V3<Real> n1 = cross3(rij, rkj);
+        const V3<Real> n2 = cross3(rkj, rkl);
+        const Real n1_2 = dot3(n1, n1);
+        const Real n2_2 = dot3(n2, n2);
+        const V3<Real> n3 = cross3(n1, n2);
+        const Real rij_rkj = dot3(rij, rkj);
+        const Real rkl_rkj = dot3(rkl, rkj);
+
+        const Real c0 = rkj_n / n1_2;
+        const Real c3 = -rkj_n / n2_2;
+        const Real n1v[3] = {n1.x, n1.y, n1.z};
+        const Real n2v[3] = {n2.x, n2.y, n2.z};
+        Real dR0[3], dR1[3], dR2[3], dR3[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            dR0[d] = c0 * n1v[d];
+            dR3[d] = c3 * n2v[d];
+            dR1[d] = (rij_rkj / rkj2 - 1) * dR0[d] - dR3[d] * rkl_rkj / rkj2;
+            dR2[d] = (rkl_rkj / rkj2 - 1) * dR3[d] - dR0[d] * rij_rkj / rkj2;
+        }
+        rkj.x /= rkj_n;
+        rkj.y /= rkj_n;
+        rkj.z /= rkj_n;
+        const Real phi = atan2(dot3(n3, rkj), dot3(n1, n2));
+
+        const Real kt = static_cast<Real>(a.p[t * 3 + 0]);
+        const Real phase = static_cast<Real>(a.p[t * 3 + 1]);
+        const Real period = static_cast<Real>(a.p[t * 3 + 2]);
+        const Real arg = period * phi - phase;
+        const Real pref = kt * sin(arg) * period;
+
+        if (a.du_dx != nullptr) {
+            add_force(a.du_dx, i, to_fixed_force(dR0[0] * pref), to_fixed_force(dR0[1] * pref), to_fixed_force(dR0[2] * pref));
+            add_force(a.du_dx, j, to_fixed_force(dR1[0] * pref), to_fixed_force(dR1[1] * pref), to_fixed_force(dR1[2] * pref));
+            add_force(a.du_dx, k, to_fixed_force(dR2[0] * pref), to_fixed_force(dR2[1] * pref), to_fixed_force(dR2[2] * pref));
+            add_force(a.du_dx, l, to_fixed_force(dR3[0] * pref), to_fixed_force(dR3[1] * pref), to_fixed_force(dR3[2] * pref));
+        }
+        if (a.du_dp != nullptr) {
+            atomicAdd(a.du_dp + t * 3 + 0, to_fixed_force(1 + cos(arg)));
+            atomicAdd(a.du_dp + t * 3 + 1, to_fixed_force(kt * sin(arg)));
+            atomicAdd(a.du_dp + t * 3 + 2, to_fixed_force(-kt * sin(arg) * phi));
+        }
+        if (a.d_u != nullptr) {
+            energy += energy_to_fixed<Real>(kt * (1 + cos(arg)));
+        }
+    }
+    if (a.d_u != nullptr) {
+        grid_finish_energy(energy, scratch, a.u_partials, a.ticket, a.d_u);
+    }
+}
+
+template <typename Real> void launch_harmonic_bond(const BondedArgs &args, cudaStream_t stream) {
+    TMB_LAUNCH(k_harmonic_bond<Real>, bonded_grid(args.n_terms), BD_THREADS, 0, stream, args);
+}
+template <typename Real> void launch_harmonic_angle(const BondedArgs &args, cudaStream_t stream) {
+    TMB_LAUNCH(k_harmonic_angle<Real>, bonded_grid(args.n_terms), BD_THREADS, 0, stream, args);
+}
+template <typename Real> void launch_periodic_torsion(const BondedArgs &args, cudaStream_t stream) {
+    TMB_LAUNCH(k_periodic_torsion<Real>, bonded_grid(args.n_terms), BD_THREADS, 0, stream, args);
+}
+template void launch_harmonic_bond<float>(const BondedArgs &, cudaStream_t);
+template void launch_harmonic_bond<double>(const BondedArgs &, cudaStream_t);
+template void launch_harmonic_angle<float>(const BondedArgs &, cudaStream_t);
+template void launch_harmonic_angle<double>(const BondedArgs &, cudaStream_t);
+template void launch_periodic_torsion<float>(const BondedArgs &, cudaStream_t);
+template void launch_periodic_torsion<double>(const BondedArgs &, cudaStream_t);
+
+} // namespace tmb

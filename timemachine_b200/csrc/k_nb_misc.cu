@@ -1,0 +1,157 @@
+// Gather/cast + device-side rebuild decision, scatter-accumulate, build-time snapshot and small utilities.
+#include "fixed_point.cuh"
+#include "kernels.hpp"
+#include "reduce.cuh"
+
+namespace tmb {
+
+constexpr int MISC_THREADS = 128;
+
+// One thread per sorted slot: gather atom perm[k] from the f64 API buffers, cast to Real and pack for 128-bit loads.
+// In the same pass decide whether the neighbour list must be rebuilt: any atom moved more than padding/2 since the
+// last build, or the box changed (reference k_check_rebuild_coords_and_box_gather, k_nonbonded.cuh:11-56).  The flag
+// stays on the device: the reference copies it to the host and blocks on an event EVERY step
+// (nonbonded_all_pairs.cu:217-235).  The flag is only ever SET here; the tile kernel of the same evaluation, which
+// runs after the (conditional) build in stream order, clears it.
+template <typename Real> __global__ void __launch_bounds__(MISC_THREADS) k_nb_prepare(const NbPrepareArgs<Real> a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int *my_flag = a.flag;
+    if (k == 0 && a.force_rebuild) {
+        *my_flag = 1;
+    }
+    if (k < 9) {
+        if (a.box[k] != a.box_build[k]) {
+            *my_flag = 1;
+        }
+    }
+    if (k >= a.K) {
+        return;
+    }
+    const unsigned int atom = a.perm[k];
+    const double x = a.x[atom * 3 + 0];
+    const double y = a.x[atom * 3 + 1];
+    const double z = a.x[atom * 3 + 2];
+    const double *p = a.p + static_cast<size_t>(atom) * P_PER_ATOM;
+
+    Vec4<Real> c, q;
+    c.x = static_cast<Real>(x);
+    c.y = static_cast<Real>(y);
+    c.z = static_cast<Real>(z);
+    c.w = static_cast<Real>(p[P_W]);
+    q.x = static_cast<Real>(p[P_CHARGE]);
+    q.y = static_cast<Real>(p[P_SIG]);
+    q.z = static_cast<Real>(p[P_EPS]);
+    q.w = static_cast<Real>(0);
+    a.xw[k] = c;
+    a.qse[k] = q;
+
+    const Real ox = static_cast<Real>(a.x_build[atom * 3 + 0]);
+    const Real oy = static_cast<Real>(a.x_build[atom * 3 + 1]);
+    const Real oz = static_cast<Real>(a.x_build[atom * 3 + 2]);
+    const Real dx = ox - c.x;
+    const Real dy = oy - c.y;
+    const Real dz = oz - c.z;
+    const Real d2 = dx * dx + dy * dy + dz * dz;
+    if (static_cast<double>(d2) > 0.25 * a.padding * a.padding) {
+        *my_flag = 1; // benign race: every writer stores the same value
+    }
+}
+
+template <typename Real> void launch_nb_prepare(const NbPrepareArgs<Real> &args, cudaStream_t stream) {
+    const int n = args.K > 9 ? args.K : 9;
+    TMB_LAUNCH(k_nb_prepare<Real>, ceil_div(n, MISC_THREADS), MISC_THREADS, 0, stream, args);
+}
+template void launch_nb_prepare<float>(const NbPrepareArgs<float> &, cudaStream_t);
+template void launch_nb_prepare<double>(const NbPrepareArgs<double> &, cudaStream_t);
+
+// out[perm[k], d] += acc[d][k]; acc[d][k] = 0
+template <int D>
+__global__ void __launch_bounds__(MISC_THREADS)
+    k_scatter_accum(const int K, const int Kpad, const unsigned int *__restrict__ perm, u64 *__restrict__ acc, u64 *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) {
+        return;
+    }
+    const unsigned int atom = perm[k];
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        const u64 v = acc[d * Kpad + k];
+        if (v != 0) {
+            atomicAdd(out + static_cast<size_t>(atom) * D + d, v);
+            acc[d * Kpad + k] = 0;
+        }
+    }
+}
+
+void launch_scatter_accum(
+    int K, int Kpad, int D, const unsigned int *perm, u64 *acc_sorted, u64 *out, cudaStream_t stream) {
+    if (K <= 0) {
+        return;
+    }
+    if (D == 3) {
+        TMB_LAUNCH(k_scatter_accum<3>, ceil_div(K, MISC_THREADS), MISC_THREADS, 0, stream, K, Kpad, perm, acc_sorted, out);
+    } else if (D == 4) {
+        TMB_LAUNCH(k_scatter_accum<4>, ceil_div(K, MISC_THREADS), MISC_THREADS, 0, stream, K, Kpad, perm, acc_sorted, out);
+    } else {
+        throw std::runtime_error("scatter_accum: unsupported D");
+    }
+}
+
+__global__ void __launch_bounds__(MISC_THREADS) k_snapshot_if(
+    const unsigned int *__restrict__ flag,
+    const int n,
+    const double *__restrict__ x,
+    double *__restrict__ x_build,
+    const double *__restrict__ box,
+    double *__restrict__ box_build) {
+    if (*flag == 0) {
+        return;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        x_build[i] = x[i];
+    }
+    if (i < 9) {
+        box_build[i] = box[i];
+    }
+}
+
+void launch_snapshot_if(
+    const unsigned int *flag, int n_doubles, const double *x, double *x_build, const double *box, double *box_build,
+    cudaStream_t stream) {
+    const int n = n_doubles > 9 ? n_doubles : 9;
+    TMB_LAUNCH(k_snapshot_if, ceil_div(n, MISC_THREADS), MISC_THREADS, 0, stream, flag, n_doubles, x, x_build, box, box_build);
+}
+
+// single-CTA int128 sum (used by Summed/Fanout potentials over a handful of child energies)
+__global__ void __launch_bounds__(256) k_sum_i128(const i128 *__restrict__ in, const int n, i128 *__restrict__ out) {
+    __shared__ i128 scratch[8];
+    i128 acc = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        acc += in[i];
+    }
+    i128 total = block_sum_i128(acc, scratch);
+    if (threadIdx.x == 0) {
+        *out = total;
+    }
+}
+
+void launch_sum_i128(const i128 *in, int n, i128 *out, cudaStream_t stream) {
+    TMB_LAUNCH(k_sum_i128, 1, 256, 0, stream, in, n, out);
+}
+
+__global__ void k_iota(unsigned int *__restrict__ out, const int n, const unsigned int base) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        out[i] = base + i;
+    }
+}
+
+void launch_iota(unsigned int *out, int n, unsigned int base, cudaStream_t stream) {
+    if (n <= 0) {
+        return;
+    }
+    TMB_LAUNCH(k_iota, ceil_div(n, MISC_THREADS), MISC_THREADS, 0, stream, out, n, base);
+}
+
+} // namespace tmb

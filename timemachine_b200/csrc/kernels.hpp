@@ -1,0 +1,176 @@
+// Host-callable launchers for every CUDA kernel of the hot path. Each launcher enqueues on `stream` and never
+// synchronises; all control decisions that the reference takes on the host after a D2H copy (neighbour-list rebuild,
+// nonbonded_all_pairs.cu:207-236) are taken on the device here.
+#pragma once
+
+#include "common.cuh"
+#include "nb_types.cuh"
+
+namespace tmb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Nonbonded tile kernel (reference k_nonbonded_unified, k_nonbonded.cuh:329)
+template <typename Real> struct NbTileArgs {
+    int K;    // gathered atoms (sorted slots); padding column entries are >= K
+    int NR;   // row slots are [0, NR); NR == K means all-pairs (upper triangle, i < j)
+    int Kpad; // stride of the SoA accumulators
+    const unsigned int *tile_count;
+    const int *tile_rows;
+    const unsigned int *tile_cols;
+    const Vec4<Real> *xw;
+    const Vec4<Real> *qse;
+    const double *box;
+    double beta;
+    double cutoff;
+    u64 *acc_dx; // [3][Kpad] sorted-order fixed-point du/dx accumulators (must be zero on entry)
+    u64 *acc_dp; // [4][Kpad] sorted-order fixed-point du/dp accumulators (must be zero on entry)
+    i128 *u_partials;
+    unsigned int *ticket;
+    i128 *d_u; // overwritten
+    unsigned int *rebuild_flag; // cleared by this kernel (the build, if any, ran before it in stream order)
+    unsigned int tile_capacity;
+};
+template <typename Real> int nb_tiles_max_grid();
+template <typename Real>
+void launch_nb_tiles(const NbTileArgs<Real> &args, bool with_u, bool with_dx, bool with_dp, cudaStream_t stream);
+
+// Gather + cast + rebuild decision (reference k_gather_coords_and_params k_nonbonded.cuh:58 and
+// k_check_rebuild_coords_and_box_gather :11, fused; the flag never leaves the device).
+template <typename Real> struct NbPrepareArgs {
+    int K;
+    const unsigned int *perm; // [K] sorted slot -> atom index
+    const double *x;          // [N,3]
+    const double *p;          // [N,4]
+    const double *box;        // [9]
+    const double *x_build;    // [N,3] coordinates at the last neighbour-list build
+    const double *box_build;  // [9]
+    double padding;
+    int force_rebuild;        // host-known (after a sort / set_atom_idxs)
+    unsigned int *flag;       // [1] rebuild flag: set here, consumed by the build kernels, cleared by the tile kernel
+    Vec4<Real> *xw;
+    Vec4<Real> *qse;
+};
+template <typename Real> void launch_nb_prepare(const NbPrepareArgs<Real> &args, cudaStream_t stream);
+
+// Scatter sorted-order accumulators back to atom order (atomically, other potentials may be adding concurrently) and
+// re-zero them (reference k_scatter_accum k_nonbonded.cuh:86).
+void launch_scatter_accum(
+    int K, int Kpad, int D, const unsigned int *perm, u64 *acc_sorted, u64 *out /*[N,D]*/, cudaStream_t stream);
+
+// Snapshot coordinates/box at build time, only if the rebuild flag is set.
+void launch_snapshot_if(
+    const unsigned int *flag, int n_doubles, const double *x, double *x_build, const double *box, double *box_build,
+    cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Neighbour list (reference k_neighborlist.cuh)
+template <typename Real> struct BlockBoundsArgs {
+    int num_blocks;
+    int num_idxs;
+    const unsigned int *idxs; // nullable: idx = base + i
+    int base;
+    const double *coords;     // exactly one of coords / xw is non-null
+    const Vec4<Real> *xw;
+    const double *box;
+    Real *ctr; // [num_blocks,3]
+    Real *ext; // [num_blocks,3]
+    const unsigned int *flag; // nullable: skip all work when *flag == 0
+};
+template <typename Real> void launch_block_bounds(const BlockBoundsArgs<Real> &args, cudaStream_t stream);
+
+template <typename Real> struct BuildTilesArgs {
+    int N;  // sentinel for "no atom" (>= N)
+    int NC; // number of column indices
+    int NR; // number of row indices
+    bool upper_triangular;
+    const unsigned int *col_idxs; // nullable: col_base + i
+    int col_base;
+    const unsigned int *row_idxs; // nullable: row_base + i
+    int row_base;
+    const Real *col_ctr, *col_ext, *row_ctr, *row_ext;
+    const double *coords; // exactly one of coords / xw
+    const Vec4<Real> *xw;
+    const double *box;
+    double cutoff;
+    TileList tiles;
+    const unsigned int *flag; // nullable: skip all work when *flag == 0
+};
+// The tile counter must be reset with launch_reset_tile_count before each build.
+void launch_reset_tile_count(const TileList &tiles, const unsigned int *flag, cudaStream_t stream);
+template <typename Real> void launch_build_tiles(const BuildTilesArgs<Real> &args, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Hilbert curve sort (reference hilbert_sort.cu, k_hilbert.cu)
+void launch_hilbert_lut(unsigned int *lut /*[128^3]*/, cudaStream_t stream);
+void launch_hilbert_keys(
+    int n, const unsigned int *atom_idxs, const double *coords, const double *box, const unsigned int *lut,
+    unsigned int *keys, unsigned int *vals, cudaStream_t stream);
+size_t radix_sort_pairs_temp_bytes(int n);
+void radix_sort_pairs(
+    void *temp, size_t temp_bytes, const unsigned int *keys_in, unsigned int *keys_out, const unsigned int *vals_in,
+    unsigned int *vals_out, int n, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Explicit pair list (reference k_nonbonded_pair_list.cuh:19)
+template <typename Real> struct PairListArgs {
+    int M;
+    const double *x;
+    const double *p;
+    const double *box;
+    const int *pair_idxs; // [M,2]
+    const double *scales; // [M,2] (charge, lj)
+    double beta;
+    double cutoff;
+    bool negated;
+    u64 *du_dx; // [N,3] nullable
+    u64 *du_dp; // [N,4] nullable
+    i128 *u_partials;
+    unsigned int *ticket;
+    i128 *d_u; // nullable
+};
+template <typename Real> void launch_pair_list(const PairListArgs<Real> &args, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bonded terms (reference k_harmonic_bond.cuh, k_harmonic_angle.cuh, k_periodic_torsion.cuh)
+struct BondedArgs {
+    int n_terms;
+    const double *x;
+    const double *p;
+    const int *idxs;
+    u64 *du_dx;
+    u64 *du_dp;
+    i128 *u_partials;
+    unsigned int *ticket;
+    i128 *d_u;
+};
+int bonded_grid(int n_terms);
+template <typename Real> void launch_harmonic_bond(const BondedArgs &args, cudaStream_t stream);
+template <typename Real> void launch_harmonic_angle(const BondedArgs &args, cudaStream_t stream);
+template <typename Real> void launch_periodic_torsion(const BondedArgs &args, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Langevin BAOAB update with in-kernel Philox noise (reference k_integrator.cuh:6-62)
+struct BaoabArgs {
+    int N;
+    float ca;
+    const unsigned int *idxs; // nullable
+    const float *cbs;
+    const float *ccs;
+    const float *noise;       // nullable: externally supplied N x 3 normals (tests); else Philox(seed, step)
+    unsigned long long seed;
+    unsigned long long step;                // noise counter = step + (*step_base if step_base != nullptr)
+    const unsigned long long *step_base;    // device-resident base so CUDA-graph replays draw fresh noise
+    double *x;
+    double *v;
+    u64 *du_dx; // consumed and zeroed
+    float dt;
+};
+void launch_baoab(const BaoabArgs &args, cudaStream_t stream);
+void launch_fill_normal(float *out, int n, unsigned long long seed, unsigned long long step, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small utilities
+void launch_sum_i128(const i128 *in, int n, i128 *out, cudaStream_t stream);
+void launch_iota(unsigned int *out, int n, unsigned int base, cudaStream_t stream);
+
+} // namespace tmb
