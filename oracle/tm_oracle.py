@@ -1,0 +1,489 @@
+"""CPU oracle for the timemachine force-evaluation + integration hot path.
+
+*** TEST INFRASTRUCTURE, NOT PRODUCT CODE. ***  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; nothing under timemachine_b200/ does.
+
+It is a NumPy float64 restatement of the reference's own CPU (JAX) potentials and integrator, with analytic gradients
+(jax.grad is unavailable here: jax is not installed in this image), each function citing the reference lines it
+follows (paths relative to /root/reference):
+
+  nonbonded energy     timemachine/potentials/nonbonded.py:221-339 (`nonbonded`), switch_fn :23-39,
+                       pair form :342-400, block form :82-150; PBC timemachine/potentials/jax_utils.py:37-44,144-181
+  gradients / du_dp    analytic forms of timemachine/cpp/src/kernels/k_nonbonded_common.cuh:72-94,184-246 and
+                       k_nonbonded.cuh:239-264 (which parameter each term feeds)
+  bonded               timemachine/potentials/bonded.py:34-79 (bond), :82-138 (angle), :141-216 (torsion); gradients
+                       as in kernels/k_harmonic_bond.cuh:40-53, k_harmonic_angle.cuh:76-141, k_periodic_torsion.cuh:72-126
+  integrator           timemachine/integrator.py:15-53 (langevin_coefficients), :137-144 (BAOAB step); the
+                       mixed-precision variant restates kernels/k_integrator.cuh:32-46
+  neighbour list       tests/test_nblist.py:28-55 (block bounds), :117-139 (brute-force tile membership)
+  hilbert              timemachine/cpp/src/kernels/k_hilbert.cu:19-47 (binning), hilbert_sort.cu:17-33 (LUT);
+                       the curve itself is checked against the vendored C routine (oracle/_ref/libhilbert_ref.so)
+
+PINNING: the energies of this oracle are checked against outputs of the reference's own Python functions, imported
+from /root/reference with a numpy stand-in for jax.numpy (tests/golden/make_golden.py wrote tests/golden/*.npz; the
+reference has no golden vectors of its own for this path), and its analytic gradients are checked
+against central finite differences of those energies (tests/test_oracle.py).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+from scipy.special import erfc
+
+FIXED_EXPONENT = 1 << 36
+BOLTZ = 0.008314462618  # timemachine/cpp/src/constants.hpp:5 (what the CUDA integrator uses)
+SWITCH_CUTOFF = 1.2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# geometry
+def delta_r(ri, rj, box=None):
+    """jax_utils.py:37-44"""
+    diff = ri - rj
+    if box is not None:
+        bd = np.diag(box)
+        diff = diff - bd * np.floor(diff / bd + 0.5)
+    return diff
+
+
+def switch_fn(d):
+    """nonbonded.py:23-39; the 1.2 nm is intentionally hard-coded in the reference"""
+    f = np.cos(0.5 * np.pi * (d / SWITCH_CUTOFF) ** 8) ** 3
+    return np.where(d < SWITCH_CUTOFF, f, 0.0)
+
+
+def d_switch_fn(d):
+    arg = 0.5 * np.pi * (d / SWITCH_CUTOFF) ** 8
+    g = -12.0 * np.pi * d**7 / SWITCH_CUTOFF**8 * np.sin(arg) * np.cos(arg) ** 2
+    return np.where(d < SWITCH_CUTOFF, g, 0.0)
+
+
+def _pair_terms(d, qi, qj, si, sj, ei, ej, beta, q_scale=1.0, lj_scale=1.0):
+    """Energy and derivatives of one pair at 4-D distance d (arrays broadcast).
+
+    Returns dict with u, du_dd, and the du/dparam pieces:  dq_i, dq_j, dsig (same for i and j), deps_i, deps_j.
+    """
+    inv_d = 1.0 / d
+    bd = beta * d
+    e = erfc(bd)
+    de = -2.0 * beta / np.sqrt(np.pi) * np.exp(-bd * bd)
+    s = switch_fn(d)
+    ds = d_switch_fn(d)
+    damp = e * s
+    ddamp = e * ds + de * s
+    qij = q_scale * qi * qj
+    u_es = qij * damp * inv_d
+    du_es = qij * (ddamp * inv_d - damp * inv_d * inv_d)
+
+    lj_on = (ei != 0) & (ej != 0)
+    eps_ij = np.where(lj_on, ei * ej, 0.0)
+    sig_ij = si + sj
+    s6 = (sig_ij * inv_d) ** 6
+    s12 = s6 * s6
+    u_lj = lj_scale * 4.0 * eps_ij * (s12 - s6)
+    du_lj = -lj_scale * 24.0 * eps_ij * inv_d * (2.0 * s12 - s6)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dsig = np.where(lj_on, lj_scale * 24.0 * eps_ij * (2.0 * s12 - s6) / sig_ij, 0.0)
+    deps_common = np.where(lj_on, lj_scale * 4.0 * (s12 - s6), 0.0)
+    return {
+        "u": u_es + u_lj,
+        "du_dd": du_es + du_lj,
+        "dq_i": q_scale * qj * damp * inv_d,
+        "dq_j": q_scale * qi * damp * inv_d,
+        "dsig": dsig,
+        "deps_i": deps_common * ej,
+        "deps_j": deps_common * ei,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# nonbonded: rows x cols block with optional pair mask, the building block of every variant
+def _nonbonded_block(x, params, box, rows, cols, beta, cutoff, upper_triangular, q_mask=None, lj_mask=None, chunk=256):
+    """Accumulate u, du_dx[N,3], du_dp[N,4] over pairs (i in rows, j in cols); if upper_triangular only i < j (by atom
+    index) counts. q_mask / lj_mask: optional dense [N,N] multipliers (exclusion rescale masks, nonbonded.py:159-173)."""
+    N = x.shape[0]
+    du_dx = np.zeros((N, 3))
+    du_dp = np.zeros((N, 4))
+    u_total = 0.0
+    rows = np.asarray(rows)
+    cols = np.asarray(cols)
+    xj = x[cols]
+    pj = params[cols]
+    for start in range(0, len(rows), chunk):
+        r = rows[start : start + chunk]
+        xi = x[r]
+        pi = params[r]
+        dxyz = delta_r(xi[:, None, :], xj[None, :, :], box)  # (R, C, 3)
+        dw = pi[:, None, 3] - pj[None, :, 3]
+        d2 = np.sum(dxyz * dxyz, axis=-1) + dw * dw
+        keep = d2 < cutoff * cutoff
+        if upper_triangular:
+            keep &= r[:, None] < cols[None, :]
+        else:
+            keep &= r[:, None] != cols[None, :]
+        d = np.sqrt(np.where(keep, d2, 1.0))
+        qs = 1.0 if q_mask is None else q_mask[np.ix_(r, cols)]
+        ls = 1.0 if lj_mask is None else lj_mask[np.ix_(r, cols)]
+        t = _pair_terms(d, pi[:, None, 0], pj[None, :, 0], pi[:, None, 1], pj[None, :, 1], pi[:, None, 2], pj[None, :, 2], beta, qs, ls)
+        k = keep.astype(np.float64)
+        u_total += float(np.sum(t["u"] * k))
+        pref = t["du_dd"] / d * k  # multiplies the displacement
+        f = pref[:, :, None] * dxyz
+        np.add.at(du_dx, r, f.sum(axis=1))
+        np.add.at(du_dx, cols, -f.sum(axis=0))
+        gw = pref * dw
+        np.add.at(du_dp[:, 3], r, gw.sum(axis=1))
+        np.add.at(du_dp[:, 3], cols, -gw.sum(axis=0))
+        np.add.at(du_dp[:, 0], r, (t["dq_i"] * k).sum(axis=1))
+        np.add.at(du_dp[:, 0], cols, (t["dq_j"] * k).sum(axis=0))
+        np.add.at(du_dp[:, 1], r, (t["dsig"] * k).sum(axis=1))
+        np.add.at(du_dp[:, 1], cols, (t["dsig"] * k).sum(axis=0))
+        np.add.at(du_dp[:, 2], r, (t["deps_i"] * k).sum(axis=1))
+        np.add.at(du_dp[:, 2], cols, (t["deps_j"] * k).sum(axis=0))
+    return u_total, du_dx, du_dp
+
+
+def nonbonded_all_pairs(x, params, box, beta, cutoff, atom_idxs=None):
+    """NonbondedAllPairs (no exclusions): every pair i<j of atom_idxs (potentials.py:126-138 decomposition)."""
+    N = x.shape[0]
+    idxs = np.arange(N) if atom_idxs is None else np.asarray(atom_idxs)
+    return _nonbonded_block(x, params, box, idxs, idxs, beta, cutoff, upper_triangular=True)
+
+
+def nonbonded_interaction_group(x, params, box, row_idxs, col_idxs, beta, cutoff):
+    """rows x cols block, disjoint sets (nonbonded.py:82-150 nonbonded_block)."""
+    return _nonbonded_block(x, params, box, np.asarray(row_idxs), np.asarray(col_idxs), beta, cutoff, upper_triangular=False)
+
+
+def nonbonded_pair_list(x, params, box, pair_idxs, scales, beta, cutoff):
+    """Explicit pairs with (charge, lj) rescale (nonbonded.py:342-400 nonbonded_on_specific_pairs)."""
+    N = x.shape[0]
+    du_dx = np.zeros((N, 3))
+    du_dp = np.zeros((N, 4))
+    pair_idxs = np.asarray(pair_idxs).reshape(-1, 2)
+    scales = np.asarray(scales, dtype=np.float64).reshape(-1, 2)
+    if len(pair_idxs) == 0:
+        return 0.0, du_dx, du_dp
+    i, j = pair_idxs[:, 0], pair_idxs[:, 1]
+    dxyz = delta_r(x[i], x[j], box)
+    dw = params[i, 3] - params[j, 3]
+    d2 = np.sum(dxyz * dxyz, axis=-1) + dw * dw
+    keep = d2 < cutoff * cutoff
+    d = np.sqrt(np.where(keep, d2, 1.0))
+    t = _pair_terms(d, params[i, 0], params[j, 0], params[i, 1], params[j, 1], params[i, 2], params[j, 2], beta, scales[:, 0], scales[:, 1])
+    k = keep.astype(np.float64)
+    u = float(np.sum(t["u"] * k))
+    pref = t["du_dd"] / d * k
+    f = pref[:, None] * dxyz
+    np.add.at(du_dx, i, f)
+    np.add.at(du_dx, j, -f)
+    np.add.at(du_dp[:, 3], i, pref * dw)
+    np.add.at(du_dp[:, 3], j, -pref * dw)
+    np.add.at(du_dp[:, 0], i, t["dq_i"] * k)
+    np.add.at(du_dp[:, 0], j, t["dq_j"] * k)
+    np.add.at(du_dp[:, 1], i, t["dsig"] * k)
+    np.add.at(du_dp[:, 1], j, t["dsig"] * k)
+    np.add.at(du_dp[:, 2], i, t["deps_i"] * k)
+    np.add.at(du_dp[:, 2], j, t["deps_j"] * k)
+    return u, du_dx, du_dp
+
+
+def nonbonded(x, params, box, exclusion_idxs, scale_factors, beta, cutoff, atom_idxs=None):
+    """The monolithic `Nonbonded` potential: all pairs minus scaled exclusions (nonbonded.py:221-339;
+    potentials.py:126-138 shows the GPU decomposition AllPairs + Exclusions that this equals)."""
+    u, dx, dp = nonbonded_all_pairs(x, params, box, beta, cutoff, atom_idxs)
+    exclusion_idxs = np.asarray(exclusion_idxs).reshape(-1, 2)
+    scale_factors = np.asarray(scale_factors, dtype=np.float64).reshape(-1, 2)
+    if atom_idxs is not None and len(exclusion_idxs):
+        s = set(int(a) for a in atom_idxs)
+        keep = np.array([int(i) in s and int(j) in s for i, j in exclusion_idxs], dtype=bool)
+        exclusion_idxs, scale_factors = exclusion_idxs[keep], scale_factors[keep]
+    ue, dxe, dpe = nonbonded_pair_list(x, params, box, exclusion_idxs, scale_factors, beta, cutoff)
+    return u - ue, dx - dxe, dp - dpe
+
+
+def nonbonded_energy_dense(x, params, box, exclusion_idxs, scale_factors, beta, cutoff):
+    """Literal dense restatement of nonbonded.py:221-339 (energy only) - used to cross-check the blocked version and
+    as the closest analogue of the reference's JAX CPU path for timing."""
+    N = x.shape[0]
+    q_mask = np.ones((N, N))
+    lj_mask = np.ones((N, N))
+    for (i, j), (qs, ls) in zip(np.asarray(exclusion_idxs).reshape(-1, 2), np.asarray(scale_factors).reshape(-1, 2)):
+        q_mask[i, j] = q_mask[j, i] = 1 - qs
+        lj_mask[i, j] = lj_mask[j, i] = 1 - ls
+    q, sig, eps, w = params.T
+    d_ijk = delta_r(x[:, None], x[None, :], box)
+    d2 = np.sum(d_ijk**2, axis=2) + (w[:, None] - w[None, :]) ** 2
+    np.fill_diagonal(d2, 0.0)
+    dij = np.sqrt(d2)
+    eye = np.eye(N, dtype=bool)
+    eps_ij = eps[:, None] * eps[None, :]
+    sig_ij = sig[:, None] + sig[None, :]
+    keep = (~eye) & (eps_ij != 0) & (dij < cutoff)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = np.where(eye, 0.0, 1.0 / np.where(eye, 1.0, dij))
+        s6 = (np.where(keep, sig_ij, 0.0) * inv) ** 6
+        e_lj = np.where(keep, 4 * eps_ij * (s6 - 1.0) * s6, 0.0)
+        qij = np.where(eye, 0.0, q[:, None] * q[None, :])
+        e_q = np.where(eye | (dij >= cutoff), 0.0, qij * erfc(beta * dij) * inv * switch_fn(dij))
+    return float(np.sum((e_lj * lj_mask + e_q * q_mask) / 2))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bonded
+def harmonic_bond(x, params, bond_idxs):
+    """bonded.py:34-79; returns (u, du_dx, du_dp[B,2])"""
+    N = x.shape[0]
+    du_dx = np.zeros((N, 3))
+    bond_idxs = np.asarray(bond_idxs).reshape(-1, 2)
+    params = np.asarray(params, dtype=np.float64).reshape(-1, 2)
+    if len(bond_idxs) == 0:
+        return 0.0, du_dx, np.zeros_like(params)
+    i, j = bond_idxs[:, 0], bond_idxs[:, 1]
+    dx = x[i] - x[j]
+    r = np.sqrt(np.sum(dx * dx, axis=-1))
+    kb, b0 = params[:, 0], params[:, 1]
+    db = r - b0
+    u = float(np.sum(kb / 2 * db * db))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        g = np.where((b0 != 0)[:, None], (kb * db / r)[:, None] * dx, kb[:, None] * dx)
+    np.add.at(du_dx, i, g)
+    np.add.at(du_dx, j, -g)
+    du_dp = np.stack([0.5 * db * db, -kb * db], axis=1)
+    return u, du_dx, du_dp
+
+
+def _angle_theta(x, angle_idxs, eps):
+    i, j, k = angle_idxs[:, 0], angle_idxs[:, 1], angle_idxs[:, 2]
+    rji = np.concatenate([x[i] - x[j], eps[:, None]], axis=1)
+    rjk = np.concatenate([x[k] - x[j], eps[:, None]], axis=1)
+    nji = np.linalg.norm(rji, axis=1, keepdims=True)
+    njk = np.linalg.norm(rjk, axis=1, keepdims=True)
+    y = np.linalg.norm(njk * rji - nji * rjk, axis=1)
+    xx = np.linalg.norm(njk * rji + nji * rjk, axis=1)
+    return 2 * np.arctan2(y, xx), rji, rjk, nji[:, 0], njk[:, 0]
+
+
+def harmonic_angle(x, params, angle_idxs):
+    """bonded.py:82-138 (Kahan-stable angle with the eps 4th component); returns (u, du_dx, du_dp[A,3])"""
+    N = x.shape[0]
+    du_dx = np.zeros((N, 3))
+    angle_idxs = np.asarray(angle_idxs).reshape(-1, 3)
+    params = np.asarray(params, dtype=np.float64).reshape(-1, 3)
+    if len(angle_idxs) == 0:
+        return 0.0, du_dx, np.zeros_like(params)
+    ka, a0, eps = params[:, 0], params[:, 1], params[:, 2]
+    theta, a, b, na, nb = _angle_theta(x, angle_idxs, eps)
+    delta = theta - a0
+    u = float(np.sum(ka / 2 * delta * delta))
+    ab = np.sum(a * b, axis=1, keepdims=True)
+    aa = np.sum(a * a, axis=1, keepdims=True)
+    bb = np.sum(b * b, axis=1, keepdims=True)
+    aab = a * ab - b * aa
+    bba = b * ab - a * bb
+    aab_n = np.linalg.norm(aab, axis=1, keepdims=True)
+    bba_n = np.linalg.norm(bba, axis=1, keepdims=True)
+    pref = (ka * delta)[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gi4 = np.where(aab_n == 0, 0.0, pref / na[:, None] * aab / aab_n)
+        gk4 = np.where(bba_n == 0, 0.0, pref / nb[:, None] * bba / bba_n)
+    i, j, k = angle_idxs[:, 0], angle_idxs[:, 1], angle_idxs[:, 2]
+    np.add.at(du_dx, i, gi4[:, :3])
+    np.add.at(du_dx, k, gk4[:, :3])
+    np.add.at(du_dx, j, -gi4[:, :3] - gk4[:, :3])
+    du_dp = np.stack([delta * delta / 2, -delta * ka, gi4[:, 3] + gk4[:, 3]], axis=1)
+    return u, du_dx, du_dp
+
+
+def periodic_torsion(x, params, torsion_idxs):
+    """bonded.py:141-216; returns (u, du_dx, du_dp[T,3])"""
+    N = x.shape[0]
+    du_dx = np.zeros((N, 3))
+    torsion_idxs = np.asarray(torsion_idxs).reshape(-1, 4)
+    params = np.asarray(params, dtype=np.float64).reshape(-1, 3)
+    if len(torsion_idxs) == 0:
+        return 0.0, du_dx, np.zeros_like(params)
+    i, j, k, l = torsion_idxs.T
+    rij = x[j] - x[i]
+    rkj = x[j] - x[k]
+    rkl = x[l] - x[k]
+    n1 = np.cross(rij, rkj)
+    n2 = np.cross(rkj, rkl)
+    rkj_n = np.linalg.norm(rkj, axis=1, keepdims=True)
+    y = np.sum(np.cross(n1, n2) * rkj / rkj_n, axis=1)
+    xx = np.sum(n1 * n2, axis=1)
+    phi = np.arctan2(y, xx)
+    kt, phase, period = params[:, 0], params[:, 1], params[:, 2]
+    arg = period * phi - phase
+    u = float(np.sum(kt * (1 + np.cos(arg))))
+    n1_2 = np.sum(n1 * n1, axis=1, keepdims=True)
+    n2_2 = np.sum(n2 * n2, axis=1, keepdims=True)
+    rkj2 = rkj_n * rkj_n
+    d0 = rkj_n / n1_2 * n1
+    d3 = -rkj_n / n2_2 * n2
+    ij_kj = np.sum(rij * rkj, axis=1, keepdims=True)
+    kl_kj = np.sum(rkl * rkj, axis=1, keepdims=True)
+    d1 = (ij_kj / rkj2 - 1) * d0 - d3 * kl_kj / rkj2
+    d2 = (kl_kj / rkj2 - 1) * d3 - d0 * ij_kj / rkj2
+    pref = (kt * np.sin(arg) * period)[:, None]  # note: du/dphi = -k n sin(n phi - phi0); d* hold -dphi/dx
+    np.add.at(du_dx, i, d0 * pref)
+    np.add.at(du_dx, j, d1 * pref)
+    np.add.at(du_dx, k, d2 * pref)
+    np.add.at(du_dx, l, d3 * pref)
+    du_dp = np.stack([1 + np.cos(arg), kt * np.sin(arg), -kt * np.sin(arg) * phi], axis=1)
+    return u, du_dx, du_dp
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# integrator
+def langevin_coefficients(temperature, dt, friction, masses, boltz=BOLTZ):
+    """integrator.py:15-53"""
+    masses = np.asarray(masses, dtype=np.float64)
+    kT = boltz * temperature
+    ca = np.exp(-friction * dt)
+    cb = dt / masses
+    cc = np.sqrt(1 - np.exp(-2 * friction * dt)) * np.sqrt(kT / masses)
+    return ca, cb, cc
+
+
+def baoab_step(x, v, force, ca, cb, cc, dt, noise):
+    """integrator.py:137-144 (_step), float64 throughout"""
+    v_mid = v + cb[:, None] * force
+    new_v = ca * v_mid + cc[:, None] * noise
+    new_x = x + 0.5 * dt * (v_mid + new_v)
+    return new_x, new_v
+
+
+def float_to_fixed(v):
+    """k_fixed_point.cuh:10-24 is round-half-even of v * 2^36 (SURVEY.md §8c sub-oracle 3)"""
+    return np.rint(np.asarray(v, dtype=np.float64) * FIXED_EXPONENT).astype(np.int64).view(np.uint64)
+
+
+def fixed_to_float(v):
+    return np.asarray(v, dtype=np.uint64).view(np.int64).astype(np.float64) / FIXED_EXPONENT
+
+
+def baoab_step_mixed(x, v, du_dx_fixed, masses, temperature, dt, friction, noise_f32):
+    """Bit-level restatement of k_integrator.cuh:32-46 + langevin_integrator.cu:17-30: f32 coefficients/force, f64 state.
+    du_dx_fixed: uint64[N,3]."""
+    dt32 = np.float32(dt)
+    ca = np.float32(np.exp(-friction * dt))
+    kT = BOLTZ * temperature
+    adj = np.sqrt(1 - np.exp(-2 * friction * dt))
+    masses = np.asarray(masses, dtype=np.float64)
+    cbs = (np.float64(dt32) / masses).astype(np.float32)
+    ccs = (adj * np.sqrt(kT / masses)).astype(np.float32)
+    f = -(np.asarray(du_dx_fixed, dtype=np.uint64).view(np.int64).astype(np.float32) / np.float32(FIXED_EXPONENT))
+    cbf = (cbs[:, None] * f).astype(np.float32)
+    v_mid = (v + cbf.astype(np.float64)).astype(np.float32)
+    v_new = (ca * v_mid).astype(np.float32) + (ccs[:, None] * np.asarray(noise_f32, dtype=np.float32)).astype(np.float32)
+    v_new = v_new.astype(np.float32)
+    half_dt = np.float32(np.float32(0.5) * dt32)
+    x_new = x + np.float64(half_dt) * (v_mid.astype(np.float64) + v_new.astype(np.float64))
+    return x_new, v_new.astype(np.float64)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# neighbour list
+def reference_block_bounds(coords, box, block_size=32):
+    """tests/test_nblist.py:28-55"""
+    coords = np.array(coords, dtype=np.float64, copy=True)
+    N = coords.shape[0]
+    nb = (N + block_size - 1) // block_size
+    bd = np.diagonal(box)
+    ctrs, exts = [], []
+    for b in range(nb):
+        blk = coords[b * block_size : min((b + 1) * block_size, N)]
+        lo = blk[0].copy()
+        hi = blk[0].copy()
+        for c in blk[1:]:
+            center = 0.5 * (hi + lo)
+            c = c - bd * np.floor((c - center) / bd + 0.5)
+            lo = np.minimum(lo, c)
+            hi = np.maximum(hi, c)
+        ctrs.append((hi + lo) / 2)
+        exts.append((hi - lo) / 2)
+    return np.array(ctrs), np.array(exts)
+
+
+def reference_ixn_list(coords, box, cutoff, block_size=32, row_idxs=None):
+    """Brute-force canonical tile membership (tests/test_nblist.py:117-139, row-subset form :142-177).
+    Returns (list of sorted j-lists per row block, min |d - cutoff| over all tested pairs)."""
+    coords = np.asarray(coords, dtype=np.float64)
+    N = coords.shape[0]
+    out = []
+    margin = np.inf
+    if row_idxs is None:
+        rows = np.arange(N)
+        cols = np.arange(N)
+        tri = True
+    else:
+        rows = np.asarray(row_idxs)
+        cols = np.setdiff1d(np.arange(N), rows)
+        tri = False
+    nb = (len(rows) + block_size - 1) // block_size
+    for b in range(nb):
+        r = rows[b * block_size : (b + 1) * block_size]
+        d = np.linalg.norm(delta_r(coords[r][:, None, :], coords[cols][None, :, :], box), axis=-1)
+        if tri:
+            d[:, : b * block_size] = np.inf
+        margin = min(margin, float(np.min(np.abs(d - cutoff))))
+        hit = np.any(d < cutoff, axis=0)
+        out.append(sorted(cols[hit].tolist()))
+    return out, margin
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# hilbert
+def hilbert3d_index(c0, c1, c2, nbits=8):
+    """Vectorised Butz/Moore index; exhaustively compared with the vendored C routine in tests/test_hilbert.py."""
+    c0 = np.asarray(c0, dtype=np.uint64)
+    c1 = np.asarray(c1, dtype=np.uint64)
+    c2 = np.asarray(c2, dtype=np.uint64)
+    index = np.zeros_like(c0)
+    rot = np.zeros_like(c0)
+    flip = np.zeros_like(c0)
+    above = np.zeros_like(c0)
+    one = np.uint64(1)
+    for level in range(nbits - 1, -1, -1):
+        lv = np.uint64(level)
+        raw = (((c2 >> lv) & one) << np.uint64(2)) | (((c1 >> lv) & one) << one) | ((c0 >> lv) & one)
+        digit = (raw ^ above) ^ flip
+        digit = ((digit >> rot) | (digit << (np.uint64(3) - rot))) & np.uint64(7)
+        index = (index << np.uint64(3)) | digit
+        above = raw
+        flip = one << rot
+        low = digit & (~digit + one) & np.uint64(3)
+        rot = rot + one + np.where(low == 1, 1, np.where(low == 2, 2, 0)).astype(np.uint64)
+        rot = rot % np.uint64(3)
+    total = 3 * nbits
+    every_third = 0
+    for b in range(0, total, 3):
+        every_third |= 1 << b
+    index ^= np.uint64(every_third >> 1)
+    d = 1
+    while d < total:
+        index ^= index >> np.uint64(d)
+        d *= 2
+    return index
+
+
+def hilbert_keys(coords, box, atom_idxs=None, grid=128):
+    """k_hilbert.cu:19-47: home-box image with floor, bin = (unsigned)(x * min(1/b) * 127), key = curve index"""
+    coords = np.asarray(coords, dtype=np.float64)
+    if atom_idxs is not None:
+        coords = coords[np.asarray(atom_idxs)]
+    bd = np.diagonal(box).astype(np.float64)
+    inv = 1.0 / bd
+    inv_bin_width = np.min(inv) * (grid - 1.0)
+    x = coords - bd * np.floor(coords * inv)
+    bins = (x * inv_bin_width).astype(np.uint32)
+    return hilbert3d_index(bins[:, 0], bins[:, 1], bins[:, 2]).astype(np.uint32)
+
+
+def hilbert_perm(coords, box, atom_idxs=None):
+    """hilbert_sort.cu:51-81: stable sort of (key, atom) pairs"""
+    keys = hilbert_keys(coords, box, atom_idxs)
+    order = np.argsort(keys, kind="stable")
+    idxs = np.arange(len(coords)) if atom_idxs is None else np.asarray(atom_idxs)
+    return idxs[order].astype(np.uint32)

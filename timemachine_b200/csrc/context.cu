@@ -10,7 +10,7 @@
 
 namespace tmb {
 
-constexpr double BOLTZ = 0.0083144621; // kJ/mol/K, reference timemachine/cpp/src/constants.hpp / constants.py:8
+constexpr double BOLTZ = 0.008314462618; // kJ/mol/K, reference timemachine/cpp/src/constants.hpp:5
 
 __global__ void k_set_u64(unsigned long long *p, unsigned long long v) { *p = v; }
 

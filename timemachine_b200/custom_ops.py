@@ -1,0 +1,811 @@
+"""Drop-in for the hot-path subset of `timemachine.lib.custom_ops` (reference: timemachine/cpp/src/wrap_kernels.cpp,
+API listing timemachine/lib/custom_ops.pyi), backed by the sm_100a CUDA library libtmb200.so through its C ABI.
+
+Same class names, constructor argument order, method names, return shapes, fixed-point -> float conversion and error
+strings as the reference module, so the reference's own Python wrappers
+(`timemachine.potentials.Potential.to_gpu`, `timemachine.lib.LangevinIntegrator.impl`, `custom_ops.Context`) can run on
+top of it unchanged:
+
+    import sys, timemachine_b200.custom_ops as ops
+    sys.modules["timemachine.lib.custom_ops"] = ops        # before importing timemachine.potentials
+
+There is no CPU fallback: importing this module without the built CUDA library raises ImportError.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import F32, F64, I128
+
+_L = _lib.load()
+
+FIXED_EXPONENT = int(_L.tmb_fixed_exponent())  # wrap_kernels.cpp:2311
+_LLONG_MAX = (1 << 63) - 1
+_LLONG_MIN = -(1 << 63)
+
+
+class InvalidHardware(Exception):
+    """Raised when the CUDA device/driver is unusable (reference exceptions.hpp, wrap_kernels.cpp:2144)."""
+
+
+def _check(status: int) -> None:
+    if status == _lib.TMB_OK:
+        return
+    msg = (_L.tmb_last_error() or b"").decode("utf-8", "replace")
+    if status == _lib.TMB_INVALID_HARDWARE:
+        raise InvalidHardware(msg)
+    raise RuntimeError(msg)
+
+
+def cuda_device_reset() -> None:
+    _check(_L.tmb_cuda_device_reset())
+
+
+def kernel_launch_count() -> int:
+    """Kernels launched by libtmb200 so far (bench.py reports the delta over the timed region)."""
+    return int(_L.tmb_kernel_launch_count())
+
+
+# ---- marshalling helpers -------------------------------------------------------------------------------------------
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _u32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _ptr(a: Optional[np.ndarray], ctype):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _verify_coords(coords: np.ndarray) -> None:
+    if coords.ndim != 2:
+        raise RuntimeError("coords dimensions must be 2")
+    if coords.shape[-1] != 3:
+        raise RuntimeError("coords must have a shape that is 3 dimensional")
+
+
+def _verify_coords_and_box(coords: np.ndarray, box: np.ndarray) -> None:
+    """wrap_kernels.cpp:51-78"""
+    _verify_coords(coords)
+    if box.ndim != 2 or box.shape[0] != 3 or box.shape[1] != 3:
+        raise RuntimeError("box must be 3x3")
+    flat = box.reshape(-1)
+    for i in range(9):
+        if i in (0, 4, 8):
+            if flat[i] <= 0.0:
+                raise RuntimeError("box must have positive values along diagonal")
+        elif flat[i] != 0.0:
+            raise RuntimeError("box must be ortholinear")
+
+
+def _fixed_to_float(fixed: np.ndarray) -> np.ndarray:
+    """FIXED_TO_FLOAT<double>: (double)(int64)v / 2^36 (fixed_point.hpp:17-19)"""
+    return fixed.view(np.int64).astype(np.float64) / float(FIXED_EXPONENT)
+
+
+def _energy_to_float(u: I128) -> float:
+    """convert_energy_to_fp (wrap_kernels.cpp:83-89): NaN when the int128 sum left the int64 range."""
+    v = (int(u.hi) << 64) | int(u.lo)
+    if v >= _LLONG_MAX or v <= _LLONG_MIN:
+        return float("nan")
+    return float(np.float64(v) / np.float64(FIXED_EXPONENT))
+
+
+def _energies_to_float(us) -> np.ndarray:
+    return np.array([_energy_to_float(u) for u in us], dtype=np.float64)
+
+
+# ---- Potential -----------------------------------------------------------------------------------------------------
+class Potential:
+    """Base class of every potential (wrap_kernels.cpp:729-1131). Holds a tmb_potential handle."""
+
+    _handle: Optional[C.c_void_p] = None
+
+    def __init__(self, *args, **kwargs):
+        raise TypeError("Potential has no constructor; use one of the concrete potentials")
+
+    def _adopt(self, handle: C.c_void_p) -> None:
+        self._handle = handle
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and _L is not None:
+            try:
+                _L.tmb_potential_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    # -- single evaluation ------------------------------------------------------------------------------------------
+    def execute(self, coords, params, box, compute_du_dx=True, compute_du_dp=True, compute_u=True):
+        coords = _f64(coords)
+        params = _f64(params)
+        box = _f64(box)
+        _verify_coords_and_box(coords, box)
+        N = coords.shape[0]
+        P = params.size
+        du_dx = np.empty((N, 3), dtype=np.uint64) if compute_du_dx else None
+        du_dp = np.empty(P, dtype=np.uint64) if compute_du_dp else None
+        u = I128() if compute_u else None
+        _check(
+            _L.tmb_potential_execute(
+                self._handle, N, P, _ptr(coords, C.c_double), _ptr(params, C.c_double), _ptr(box, C.c_double),
+                _ptr(du_dx, C.c_uint64), _ptr(du_dp, C.c_uint64), C.byref(u) if compute_u else None,
+            )
+        )
+        out_dx = _fixed_to_float(du_dx) if compute_du_dx else None
+        out_dp = None
+        if compute_du_dp:
+            out_dp = np.empty(params.shape, dtype=np.float64)
+            if P > 0:
+                _check(_L.tmb_potential_du_dp_fixed_to_float(self._handle, N, P, _ptr(du_dp, C.c_uint64), _ptr(out_dp, C.c_double)))
+        out_u = _energy_to_float(u) if compute_u else None
+        return out_dx, out_dp, out_u
+
+    def execute_du_dx(self, coords, params, box):
+        return self.execute(coords, params, box, True, False, False)[0]
+
+    # -- dense batch: every coords x every params --------------------------------------------------------------------
+    def execute_batch(self, coords, params, boxes, compute_du_dx, compute_du_dp, compute_u):
+        coords = _f64(coords)
+        params = _f64(params)
+        boxes = _f64(boxes)
+        if coords.ndim != 3 or boxes.ndim != 3:
+            raise RuntimeError("coords and boxes must have 3 dimensions")
+        if coords.shape[0] != boxes.shape[0]:
+            raise RuntimeError("number of batches of coords and boxes don't match")
+        if params.ndim < 2:
+            raise RuntimeError("parameters must have at least 2 dimensions")
+        CB, N, D = coords.shape
+        PB = params.shape[0]
+        P = params.size // PB if PB else 0
+        total = CB * PB
+        du_dx = np.empty((total, N, D), dtype=np.uint64) if compute_du_dx else None
+        du_dp = np.empty((total, P), dtype=np.uint64) if compute_du_dp else None
+        u = (I128 * total)() if compute_u else None
+        _check(
+            _L.tmb_potential_execute_batch(
+                self._handle, CB, N, PB, P, _ptr(coords, C.c_double), _ptr(params, C.c_double), _ptr(boxes, C.c_double),
+                _ptr(du_dx, C.c_uint64), _ptr(du_dp, C.c_uint64), u,
+            )
+        )
+        out_dx = _fixed_to_float(du_dx).reshape(CB, PB, N, D) if compute_du_dx else None
+        out_dp = None
+        if compute_du_dp:
+            out_dp = np.empty((CB, PB) + tuple(params.shape[1:]), dtype=np.float64)
+            flat = out_dp.reshape(total, P)
+            for i in range(total):
+                if P > 0:
+                    _check(_L.tmb_potential_du_dp_fixed_to_float(
+                        self._handle, N, P, _ptr(du_dp[i], C.c_uint64), flat[i].ctypes.data_as(C.POINTER(C.c_double))))
+        out_u = _energies_to_float(u).reshape(CB, PB) if compute_u else None
+        return out_dx, out_dp, out_u
+
+    # -- sparse batch: explicit (coords_idx, params_idx) pairs ------------------------------------------------------------
+    def execute_batch_sparse(
+        self, coords, params, boxes, coords_batch_idxs, params_batch_idxs, compute_du_dx, compute_du_dp, compute_u
+    ):
+        coords = _f64(coords)
+        params = _f64(params)
+        boxes = _f64(boxes)
+        cidx = _u32(coords_batch_idxs)
+        pidx = _u32(params_batch_idxs)
+        if coords.ndim != 3 or boxes.ndim != 3:
+            raise RuntimeError("coords and boxes must have 3 dimensions")
+        if coords.shape[0] != boxes.shape[0]:
+            raise RuntimeError("number of coord arrays and boxes don't match")
+        if params.ndim < 2:
+            raise RuntimeError("parameters must have at least 2 dimensions")
+        if cidx.ndim != 1 or pidx.ndim != 1:
+            raise RuntimeError("coords_batch_idxs and params_batch_idxs must be one-dimensional arrays")
+        if cidx.size != pidx.size:
+            raise RuntimeError("coords_batch_idxs and params_batch_idxs must have the same length")
+        if cidx.size and cidx.max() >= coords.shape[0]:
+            raise RuntimeError("coords_batch_idxs contains an index that is out of bounds")
+        if pidx.size and pidx.max() >= params.shape[0]:
+            raise RuntimeError("params_batch_idxs contains an index that is out of bounds")
+        CS, N, D = coords.shape
+        PS = params.shape[0]
+        P = params.size // PS if PS else 0
+        B = cidx.size
+        du_dx = np.empty((B, N, D), dtype=np.uint64) if compute_du_dx else None
+        du_dp = np.empty((B, P), dtype=np.uint64) if compute_du_dp else None
+        u = (I128 * B)() if compute_u else None
+        _check(
+            _L.tmb_potential_execute_batch_sparse(
+                self._handle, CS, N, PS, P, B, _ptr(cidx, C.c_uint32), _ptr(pidx, C.c_uint32), _ptr(coords, C.c_double),
+                _ptr(params, C.c_double), _ptr(boxes, C.c_double), _ptr(du_dx, C.c_uint64), _ptr(du_dp, C.c_uint64), u,
+            )
+        )
+        out_dx = _fixed_to_float(du_dx) if compute_du_dx else None
+        out_dp = None
+        if compute_du_dp:
+            out_dp = np.empty((B,) + tuple(params.shape[1:]), dtype=np.float64)
+            flat = out_dp.reshape(B, P)
+            for i in range(B):
+                if P > 0:
+                    _check(_L.tmb_potential_du_dp_fixed_to_float(
+                        self._handle, N, P, _ptr(du_dp[i], C.c_uint64), flat[i].ctypes.data_as(C.POINTER(C.c_double))))
+        out_u = _energies_to_float(u) if compute_u else None
+        return out_dx, out_dp, out_u
+
+    # -- device-pointer entry (no reference Python equivalent; Potential::execute_device, potential.hpp:87-96) ---------
+    def execute_device(self, N, P, d_coords, d_params, d_box, d_du_dx=0, d_du_dp=0, d_u=0, stream=0) -> None:
+        """Raw CUDA pointers (ints). Accumulates into du_dx/du_dp, overwrites u, enqueues on `stream`, no sync."""
+        _check(
+            _L.tmb_potential_execute_device(
+                self._handle, N, P, C.c_void_p(d_coords), C.c_void_p(d_params or None), C.c_void_p(d_box),
+                C.c_void_p(d_du_dx or None), C.c_void_p(d_du_dp or None), C.c_void_p(d_u or None), C.c_void_p(stream or None),
+            )
+        )
+
+
+def _new_handle() -> C.c_void_p:
+    return C.c_void_p()
+
+
+def _make_bonded(name: str, create_fn, precision: int):
+    def __init__(self, idxs):
+        idxs = _i32(idxs)
+        h = _new_handle()
+        _check(create_fn(precision, _ptr(idxs, C.c_int32), idxs.size, C.byref(h)))
+        self._adopt(h)
+
+    return type(name, (Potential,), {"__init__": __init__, "__doc__": f"{name}(idxs) - see include/tmb200.h"})
+
+
+HarmonicBond_f32 = _make_bonded("HarmonicBond_f32", _L.tmb_harmonic_bond_create, F32)
+HarmonicBond_f64 = _make_bonded("HarmonicBond_f64", _L.tmb_harmonic_bond_create, F64)
+HarmonicAngle_f32 = _make_bonded("HarmonicAngle_f32", _L.tmb_harmonic_angle_create, F32)
+HarmonicAngle_f64 = _make_bonded("HarmonicAngle_f64", _L.tmb_harmonic_angle_create, F64)
+PeriodicTorsion_f32 = _make_bonded("PeriodicTorsion_f32", _L.tmb_periodic_torsion_create, F32)
+PeriodicTorsion_f64 = _make_bonded("PeriodicTorsion_f64", _L.tmb_periodic_torsion_create, F64)
+
+
+class _NonbondedAllPairs(Potential):
+    _precision = F32
+
+    def __init__(self, num_atoms, beta, cutoff, atom_idxs_i=None, disable_hilbert_sort=False, nblist_padding=0.1):
+        h = _new_handle()
+        if atom_idxs_i is None:
+            idxs, n = None, -1
+        else:
+            idxs = _i32(atom_idxs_i)
+            n = idxs.size
+        _check(
+            _L.tmb_nonbonded_all_pairs_create(
+                self._precision, int(num_atoms), float(beta), float(cutoff), _ptr(idxs, C.c_int32), n,
+                int(bool(disable_hilbert_sort)), float(nblist_padding), C.byref(h),
+            )
+        )
+        self._adopt(h)
+
+    def set_atom_idxs(self, atom_idxs) -> None:
+        idxs = _i32(atom_idxs)
+        _check(_L.tmb_nonbonded_all_pairs_set_atom_idxs(self._handle, _ptr(idxs, C.c_int32), idxs.size))
+
+    def get_num_atom_idxs(self) -> int:
+        n = C.c_int()
+        _check(_L.tmb_nonbonded_all_pairs_get_num_atom_idxs(self._handle, C.byref(n)))
+        return n.value
+
+    def get_atom_idxs(self) -> list:
+        out = np.empty(self.get_num_atom_idxs(), dtype=np.int32)
+        _check(_L.tmb_nonbonded_all_pairs_get_atom_idxs(self._handle, _ptr(out, C.c_int32)))
+        return out.tolist()
+
+    def get_tile_count(self) -> int:
+        n = C.c_uint()
+        _check(_L.tmb_nonbonded_num_tiles(self._handle, C.byref(n)))
+        return n.value
+
+
+class NonbondedAllPairs_f32(_NonbondedAllPairs):
+    _precision = F32
+
+
+class NonbondedAllPairs_f64(_NonbondedAllPairs):
+    _precision = F64
+
+
+class _NonbondedInteractionGroup(Potential):
+    _precision = F32
+
+    def __init__(
+        self, num_atoms, row_atom_idxs_i, beta, cutoff, col_atom_idxs_i=None, disable_hilbert_sort=False, nblist_padding=0.1
+    ):
+        rows = _i32(row_atom_idxs_i)
+        if col_atom_idxs_i is None:
+            cols, nc = None, -1
+        else:
+            cols = _i32(col_atom_idxs_i)
+            nc = cols.size
+        h = _new_handle()
+        _check(
+            _L.tmb_nonbonded_interaction_group_create(
+                self._precision, int(num_atoms), _ptr(rows, C.c_int32), rows.size, float(beta), float(cutoff),
+                _ptr(cols, C.c_int32), nc, int(bool(disable_hilbert_sort)), float(nblist_padding), C.byref(h),
+            )
+        )
+        self._adopt(h)
+
+    def set_atom_idxs(self, row_atom_idxs, col_atom_idxs) -> None:
+        rows = _i32(row_atom_idxs)
+        cols = _i32(col_atom_idxs)
+        _check(
+            _L.tmb_nonbonded_interaction_group_set_atom_idxs(
+                self._handle, _ptr(rows, C.c_int32), rows.size, _ptr(cols, C.c_int32), cols.size
+            )
+        )
+
+    def get_tile_count(self) -> int:
+        n = C.c_uint()
+        _check(_L.tmb_nonbonded_num_tiles(self._handle, C.byref(n)))
+        return n.value
+
+
+class NonbondedInteractionGroup_f32(_NonbondedInteractionGroup):
+    _precision = F32
+
+
+class NonbondedInteractionGroup_f64(_NonbondedInteractionGroup):
+    _precision = F64
+
+
+class _NonbondedPairList(Potential):
+    _precision = F32
+    _negated = False
+
+    def __init__(self, pair_idxs_i, scales_i, beta, cutoff):
+        pairs = _i32(pair_idxs_i)
+        scales = _f64(scales_i)
+        h = _new_handle()
+        _check(
+            _L.tmb_nonbonded_pair_list_create(
+                self._precision, int(self._negated), _ptr(pairs, C.c_int32), pairs.size, _ptr(scales, C.c_double),
+                scales.size, float(beta), float(cutoff), C.byref(h),
+            )
+        )
+        self._adopt(h)
+
+
+class NonbondedPairList_f32(_NonbondedPairList):
+    _precision, _negated = F32, False
+
+
+class NonbondedPairList_f64(_NonbondedPairList):
+    _precision, _negated = F64, False
+
+
+class NonbondedExclusions_f32(_NonbondedPairList):
+    _precision, _negated = F32, True
+
+
+class NonbondedExclusions_f64(_NonbondedPairList):
+    _precision, _negated = F64, True
+
+
+def _handle_array(objs: Sequence) -> C.Array:
+    arr = (C.c_void_p * len(objs))()
+    for i, o in enumerate(objs):
+        arr[i] = o._handle
+    return arr
+
+
+class SummedPotential(Potential):
+    def __init__(self, potentials, params_sizes, parallel=True):
+        self._potentials = list(potentials)  # keeps the children alive, like the shared_ptrs in the reference
+        sizes = _i32(params_sizes)
+        h = _new_handle()
+        _check(
+            _L.tmb_summed_potential_create(
+                _handle_array(self._potentials), len(self._potentials), _ptr(sizes, C.c_int32), sizes.size,
+                int(bool(parallel)), C.byref(h),
+            )
+        )
+        self._adopt(h)
+
+    def get_potentials(self):
+        return list(self._potentials)
+
+
+class FanoutSummedPotential(Potential):
+    def __init__(self, potentials, parallel=True):
+        self._potentials = list(potentials)
+        h = _new_handle()
+        _check(
+            _L.tmb_fanout_summed_potential_create(
+                _handle_array(self._potentials), len(self._potentials), int(bool(parallel)), C.byref(h)
+            )
+        )
+        self._adopt(h)
+
+    def get_potentials(self):
+        return list(self._potentials)
+
+
+# ---- BoundPotential ------------------------------------------------------------------------------------------------
+class BoundPotential:
+    """wrap_kernels.cpp:1133-1309"""
+
+    def __init__(self, potential: Potential, params):
+        params = _f64(params)
+        self._potential = potential
+        self._handle = None
+        h = _new_handle()
+        _check(_L.tmb_bound_potential_create(potential._handle, _ptr(params, C.c_double), params.size, C.byref(h)))
+        self._handle = h
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _L.tmb_bound_potential_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def get_potential(self) -> Potential:
+        return self._potential
+
+    def set_params(self, params) -> None:
+        params = _f64(params)
+        _check(_L.tmb_bound_potential_set_params(self._handle, _ptr(params, C.c_double), params.size))
+
+    def size(self) -> int:
+        n = C.c_int()
+        _check(_L.tmb_bound_potential_size(self._handle, C.byref(n)))
+        return n.value
+
+    def execute(self, coords, box, compute_du_dx=True, compute_u=True):
+        coords = _f64(coords)
+        box = _f64(box)
+        _verify_coords_and_box(coords, box)
+        N = coords.shape[0]
+        du_dx = np.empty((N, 3), dtype=np.uint64) if compute_du_dx else None
+        u = I128() if compute_u else None
+        _check(
+            _L.tmb_bound_potential_execute(
+                self._handle, N, _ptr(coords, C.c_double), _ptr(box, C.c_double), _ptr(du_dx, C.c_uint64),
+                C.byref(u) if compute_u else None,
+            )
+        )
+        return (_fixed_to_float(du_dx) if compute_du_dx else None, _energy_to_float(u) if compute_u else None)
+
+    def execute_batch(self, coords, boxes, compute_du_dx, compute_u):
+        coords = _f64(coords)
+        boxes = _f64(boxes)
+        if coords.ndim != 3 and boxes.ndim != 3:
+            raise RuntimeError("coords and boxes must have 3 dimensions")
+        if coords.shape[0] != boxes.shape[0]:
+            raise RuntimeError("number of batches of coords and boxes don't match")
+        CB, N, D = coords.shape
+        du_dx = np.empty((CB, N, D), dtype=np.uint64) if compute_du_dx else None
+        u = (I128 * CB)() if compute_u else None
+        _check(
+            _L.tmb_bound_potential_execute_batch(
+                self._handle, CB, N, _ptr(coords, C.c_double), _ptr(boxes, C.c_double), _ptr(du_dx, C.c_uint64), u
+            )
+        )
+        return (_fixed_to_float(du_dx) if compute_du_dx else None, _energies_to_float(u) if compute_u else None)
+
+    def execute_fixed(self, coords, box) -> np.ndarray:
+        coords = _f64(coords)
+        box = _f64(box)
+        _verify_coords_and_box(coords, box)
+        u = I128()
+        _check(
+            _L.tmb_bound_potential_execute(
+                self._handle, coords.shape[0], _ptr(coords, C.c_double), _ptr(box, C.c_double), None, C.byref(u)
+            )
+        )
+        v = (int(u.hi) << 64) | int(u.lo)
+        if v >= _LLONG_MAX or v <= _LLONG_MIN:
+            v = _LLONG_MAX
+        return np.array([v & ((1 << 64) - 1)], dtype=np.uint64)
+
+    # device-pointer helpers for replica exchange drivers (BoundPotential::set_params_device, bound_potential.cu:139)
+    def set_params_device(self, d_params: int, n_params: int, stream: int = 0) -> None:
+        _check(_L.tmb_bound_potential_set_params_device(self._handle, C.c_void_p(d_params), n_params, C.c_void_p(stream or None)))
+
+    def execute_device(self, N, d_coords, d_box, d_du_dx=0, d_u=0, stream=0) -> None:
+        _check(
+            _L.tmb_bound_potential_execute_device(
+                self._handle, N, C.c_void_p(d_coords), C.c_void_p(d_box), C.c_void_p(d_du_dx or None),
+                C.c_void_p(d_u or None), C.c_void_p(stream or None),
+            )
+        )
+
+
+# ---- integrators / context -----------------------------------------------------------------------------------------
+class Integrator:
+    def __init__(self, *args, **kwargs):
+        raise TypeError("Integrator has no constructor")
+
+
+class LangevinIntegrator(Integrator):
+    """LangevinIntegrator(masses, temperature, dt, friction, seed) - f32 like the reference (wrap_kernels.cpp:698-715)"""
+
+    def __init__(self, masses, temperature, dt, friction, seed):
+        masses = _f64(masses)
+        self._handle = None
+        h = _new_handle()
+        _check(
+            _L.tmb_langevin_integrator_create(
+                _ptr(masses, C.c_double), masses.size, float(temperature), float(dt), float(friction), int(seed), C.byref(h)
+            )
+        )
+        self._handle = h
+        self._n = masses.size
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _L.tmb_langevin_integrator_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def set_noise(self, noise) -> None:
+        """Test hook: use these N x 3 normals on every step (None: back to the in-kernel Philox stream)."""
+        if noise is None:
+            _check(_L.tmb_langevin_integrator_set_noise(self._handle, None))
+            return
+        noise = np.ascontiguousarray(noise, dtype=np.float32)
+        if noise.shape != (self._n, 3):
+            raise RuntimeError("noise must have shape (N, 3)")
+        _check(_L.tmb_langevin_integrator_set_noise(self._handle, _ptr(noise, C.c_float)))
+
+
+class Context:
+    """Context(x0, v0, box, integrator, bps, movers=None) (wrap_kernels.cpp:296-689).  Movers (barostat, exchange
+    moves) are outside this hot path: passing any raises."""
+
+    def __init__(self, x0, v0, box, integrator, bps, movers=None):
+        x0 = _f64(x0)
+        v0 = _f64(v0)
+        box = _f64(box)
+        _verify_coords_and_box(x0, box)
+        if v0.ndim != 2 or x0.shape[0] != v0.shape[0]:
+            raise RuntimeError("v0 N != x0 N")
+        if x0.shape[1] != v0.shape[1]:
+            raise RuntimeError("v0 D != x0 D")
+        if movers:
+            raise RuntimeError("movers are not part of the timemachine_b200 hot path (see DESIGN.md, out of scope)")
+        if not isinstance(integrator, LangevinIntegrator):
+            raise RuntimeError("integrator must be LangevinIntegrator.")
+        self._integrator = integrator
+        self._bps = list(bps)
+        self._n = x0.shape[0]
+        self._handle = None
+        h = _new_handle()
+        _check(
+            _L.tmb_context_create(
+                _ptr(x0, C.c_double), _ptr(v0, C.c_double), _ptr(box, C.c_double), self._n, integrator._handle,
+                _handle_array(self._bps), len(self._bps), C.byref(h),
+            )
+        )
+        self._handle = h
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _L.tmb_context_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def step(self) -> None:
+        _check(_L.tmb_context_step(self._handle))
+
+    def initialize(self) -> None:  # no-op for Langevin (langevin_integrator.cu:90-97)
+        pass
+
+    def finalize(self) -> None:
+        pass
+
+    def multiple_steps(self, n_steps: int, store_x_interval: int = 0):
+        if store_x_interval < 0:
+            raise RuntimeError("store_x_interval must be greater than or equal to zero")
+        n_steps = int(n_steps)
+        x_interval = n_steps if store_x_interval == 0 else int(store_x_interval)
+        n_samples = n_steps // x_interval if x_interval > 0 else 0
+        xs = np.empty((n_samples, self._n, 3), dtype=np.float64)
+        boxes = np.empty((n_samples, 3, 3), dtype=np.float64)
+        _check(_L.tmb_context_multiple_steps(self._handle, n_steps, n_samples, _ptr(xs, C.c_double), _ptr(boxes, C.c_double)))
+        return xs, boxes
+
+    def set_x_t(self, coords) -> None:
+        coords = _f64(coords)
+        if coords.shape != (self._n, 3):
+            raise RuntimeError("number of new coords disagree with current coords")
+        _check(_L.tmb_context_set_x_t(self._handle, _ptr(coords, C.c_double)))
+
+    def set_v_t(self, velocities) -> None:
+        velocities = _f64(velocities)
+        if velocities.shape != (self._n, 3):
+            raise RuntimeError("number of new velocities disagree with current coords")
+        _check(_L.tmb_context_set_v_t(self._handle, _ptr(velocities, C.c_double)))
+
+    def set_box(self, box) -> None:
+        box = _f64(box)
+        if box.shape != (3, 3):
+            raise RuntimeError("box must be 3x3")
+        _check(_L.tmb_context_set_box(self._handle, _ptr(box, C.c_double)))
+
+    def get_x_t(self) -> np.ndarray:
+        out = np.empty((self._n, 3), dtype=np.float64)
+        _check(_L.tmb_context_get_x_t(self._handle, _ptr(out, C.c_double)))
+        return out
+
+    def get_v_t(self) -> np.ndarray:
+        out = np.empty((self._n, 3), dtype=np.float64)
+        _check(_L.tmb_context_get_v_t(self._handle, _ptr(out, C.c_double)))
+        return out
+
+    def get_box(self) -> np.ndarray:
+        out = np.empty((3, 3), dtype=np.float64)
+        _check(_L.tmb_context_get_box(self._handle, _ptr(out, C.c_double)))
+        return out
+
+    def get_integrator(self):
+        return self._integrator
+
+    def get_potentials(self):
+        return list(self._bps)
+
+    def get_movers(self):
+        return []
+
+    def get_barostat(self):
+        return None
+
+    # extensions used by bench.py / the replica driver
+    def set_stream(self, stream: int) -> None:
+        _check(_L.tmb_context_set_stream(self._handle, C.c_void_p(stream or None)))
+
+    def set_use_graphs(self, on: bool) -> None:
+        _check(_L.tmb_context_set_use_graphs(self._handle, int(bool(on))))
+
+    def device_state(self):
+        """(d_x, d_v, d_box) raw device pointers of the context's state."""
+        dx, dv, db = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(_L.tmb_context_device_state(self._handle, C.byref(dx), C.byref(dv), C.byref(db)))
+        return dx.value, dv.value, db.value
+
+
+# ---- neighbour list / Hilbert sort ------------------------------------------------------------------------------------
+class _Neighborlist:
+    _precision = F32
+
+    def __init__(self, N: int):
+        self._handle = None
+        h = _new_handle()
+        _check(_L.tmb_neighborlist_create(self._precision, int(N), C.byref(h)))
+        self._handle = h
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _L.tmb_neighborlist_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def get_nblist(self, coords, box, cutoff):
+        coords = _f64(coords)
+        box = _f64(box)
+        _verify_coords_and_box(coords, box)
+        nrows, nent = C.c_int(), C.c_int()
+        _check(
+            _L.tmb_neighborlist_build(
+                self._handle, coords.shape[0], _ptr(coords, C.c_double), _ptr(box, C.c_double), float(cutoff),
+                C.byref(nrows), C.byref(nent),
+            )
+        )
+        offsets = np.empty(nrows.value + 1, dtype=np.int32)
+        atoms = np.empty(max(nent.value, 1), dtype=np.int32)
+        _check(_L.tmb_neighborlist_fetch(self._handle, _ptr(offsets, C.c_int32), _ptr(atoms, C.c_int32)))
+        return [atoms[offsets[r] : offsets[r + 1]].tolist() for r in range(nrows.value)]
+
+    def compute_block_bounds(self, coords, box, block_size):
+        if block_size != 32:
+            raise RuntimeError("Block size must be 32.")
+        coords = _f64(coords)
+        box = _f64(box)
+        _verify_coords_and_box(coords, box)
+        N = coords.shape[0]
+        B = (N + block_size - 1) // block_size
+        ctrs = np.empty((B, 3), dtype=np.float64)
+        exts = np.empty((B, 3), dtype=np.float64)
+        _check(
+            _L.tmb_neighborlist_compute_block_bounds(
+                self._handle, N, _ptr(coords, C.c_double), _ptr(box, C.c_double), _ptr(ctrs, C.c_double), _ptr(exts, C.c_double)
+            )
+        )
+        return ctrs, exts
+
+    def set_row_idxs(self, idxs) -> None:
+        idxs = _u32(idxs)
+        _check(_L.tmb_neighborlist_set_row_idxs(self._handle, _ptr(idxs, C.c_uint32), idxs.size))
+
+    def reset_row_idxs(self) -> None:
+        _check(_L.tmb_neighborlist_reset_row_idxs(self._handle))
+
+    def resize(self, size: int) -> None:
+        _check(_L.tmb_neighborlist_resize(self._handle, int(size)))
+
+    def get_tile_ixn_count(self) -> int:
+        n = C.c_uint()
+        _check(_L.tmb_neighborlist_get_tile_ixn_count(self._handle, C.byref(n)))
+        return n.value
+
+    def get_max_ixn_count(self) -> int:
+        n = C.c_int()
+        _check(_L.tmb_neighborlist_get_max_ixn_count(self._handle, C.byref(n)))
+        return n.value
+
+    def get_num_row_idxs(self) -> int:
+        n = C.c_int()
+        _check(_L.tmb_neighborlist_get_num_row_idxs(self._handle, C.byref(n)))
+        return n.value
+
+
+class Neighborlist_f32(_Neighborlist):
+    _precision = F32
+
+
+class Neighborlist_f64(_Neighborlist):
+    _precision = F64
+
+
+class HilbertSort:
+    def __init__(self, size: int):
+        self._handle = None
+        h = _new_handle()
+        _check(_L.tmb_hilbert_sort_create(int(size), C.byref(h)))
+        self._handle = h
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _L.tmb_hilbert_sort_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def sort(self, coords, box) -> np.ndarray:
+        coords = _f64(coords)
+        box = _f64(box)
+        _verify_coords_and_box(coords, box)
+        perm = np.empty(coords.shape[0], dtype=np.uint32)
+        _check(
+            _L.tmb_hilbert_sort_sort(
+                self._handle, coords.shape[0], _ptr(coords, C.c_double), _ptr(box, C.c_double), _ptr(perm, C.c_uint32)
+            )
+        )
+        return perm
+
+
+def fill_normal(n_atoms: int, seed: int, step: int) -> np.ndarray:
+    """N x 3 standard normals from the integrator's Philox stream (test utility)."""
+    out = np.empty((n_atoms, 3), dtype=np.float32)
+    _check(_L.tmb_fill_normal(_ptr(out, C.c_float), int(n_atoms), int(seed), int(step)))
+    return out
