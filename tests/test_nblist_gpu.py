@@ -1,0 +1,147 @@
+"""GPU: neighbour list parity (reference tests/test_nblist.py): block bounds vs the NumPy restatement, tile membership
+in canonical form (per row block, sorted set of column atoms) vs brute force, determinism, row-subset lists, argument
+validation messages."""
+
+import numpy as np
+import pytest
+
+from oracle import tm_oracle as O
+from tests.common import load_reference_ops, water_box
+
+pytestmark = pytest.mark.gpu
+
+
+def ops():
+    from timemachine_b200 import custom_ops
+
+    return custom_ops
+
+
+def nblist_cls(precision):
+    return ops().Neighborlist_f32 if precision == np.float32 else ops().Neighborlist_f64
+
+
+def test_empty_neighborlist():
+    with pytest.raises(RuntimeError, match="Neighborlist N must be at least 1"):
+        ops().Neighborlist_f32(0)
+
+
+@pytest.mark.parametrize("precision,atol,rtol", [(np.float32, 1e-6, 1e-6), (np.float64, 1e-7, 1e-7)])
+@pytest.mark.parametrize("size", [12, 128, 156, 298])
+def test_block_bounds(precision, atol, rtol, size):
+    np.random.seed(2020)
+    coords = np.random.randn(size, 3)
+    box = np.eye(3) * (np.random.rand(3) + 1)
+    ref_ctrs, ref_exts = O.reference_block_bounds(coords, box, 32)
+    ctrs, exts = nblist_cls(precision)(size).compute_block_bounds(coords, box, 32)
+    np.testing.assert_allclose(ref_ctrs, ctrs, atol=atol, rtol=rtol)
+    np.testing.assert_allclose(ref_exts, exts, atol=atol, rtol=rtol)
+    with pytest.raises(RuntimeError, match="Block size must be 32."):
+        nblist_cls(precision)(size).compute_block_bounds(coords, box, 16)
+
+
+def canonical(ixn_list):
+    return [sorted(set(row)) for row in ixn_list]
+
+
+@pytest.mark.parametrize("precision", [np.float32, np.float64])
+@pytest.mark.parametrize("n_waters,cutoff", [(11, 0.9), (300, 1.0), (999, 1.2), (999, 0.6)])
+def test_neighborlist_membership_bit_exact(precision, n_waters, cutoff):
+    sys = water_box(n_waters, seed=n_waters)
+    # round to f32 so that both precisions see the same positions (tests/test_nblist.py:109-114 does the same)
+    x = sys["x"].astype(np.float32).astype(np.float64)
+    box = sys["box"]
+    ref, margin = O.reference_ixn_list(x, box, cutoff)
+    if precision == np.float32:
+        # membership of a pair within float rounding of the cutoff is implementation-defined in f32;
+        # assert the input has no such pair so equality is meaningful
+        assert margin > 2e-5, margin
+    nb = nblist_cls(precision)(len(x))
+    got = nb.get_nblist(x, box, cutoff)
+    assert len(got) == len(ref)
+    for b, (r, g) in enumerate(zip(ref, canonical(got))):
+        assert r == g, f"row block {b}"
+    # no duplicates, determinism (tests/test_nblist.py:258-265)
+    for row in got:
+        assert len(row) == len(set(row))
+    again = nb.get_nblist(x, box, cutoff)
+    assert canonical(again) == canonical(got)
+    assert nb.get_tile_ixn_count() >= sum((len(r) + 31) // 32 for r in ref) > 0
+    assert nb.get_tile_ixn_count() * 32 <= nb.get_max_ixn_count() + 32 * len(ref)
+
+
+@pytest.mark.parametrize("precision", [np.float32, np.float64])
+def test_neighborlist_wrapped_coordinates(precision, rng):
+    """Atoms scattered over several periodic images must give the same canonical list as their home-box images."""
+    sys = water_box(400, seed=8)
+    x = sys["x"].astype(np.float32).astype(np.float64)
+    box = sys["box"]
+    L = box[0, 0]
+    shift = rng.integers(-3, 4, x.shape) * L
+    xs = (x + shift).astype(np.float32).astype(np.float64)
+    ref, margin = O.reference_ixn_list(xs, box, 1.0)
+    if precision == np.float32:
+        if margin <= 1e-4:  # f32 positions far from the origin lose absolute precision
+            pytest.skip("borderline pair in f32")
+    got = nblist_cls(precision)(len(x)).get_nblist(xs, box, 1.0)
+    assert canonical(got) == ref
+
+
+@pytest.mark.parametrize("precision", [np.float32, np.float64])
+def test_neighborlist_row_idxs(precision, rng):
+    """Row-subset lists (tests/test_nblist.py:189-234): rows = chosen atoms, columns = the complement."""
+    sys = water_box(300, seed=4)
+    x = sys["x"].astype(np.float32).astype(np.float64)
+    box = sys["box"]
+    n = len(x)
+    nb = nblist_cls(precision)(n)
+    rows = rng.choice(n, 50, replace=False).astype(np.uint32)
+    nb.set_row_idxs(rows)
+    assert nb.get_num_row_idxs() == 50
+    ref, margin = O.reference_ixn_list(x, box, 1.1, row_idxs=rows)
+    if precision == np.float32:
+        assert margin > 2e-5
+    got = nb.get_nblist(x, box, 1.1)
+    assert canonical(got) == ref
+    nb.reset_row_idxs()
+    assert nb.get_num_row_idxs() == n
+    ref_all, _ = O.reference_ixn_list(x, box, 1.1)
+    assert canonical(nb.get_nblist(x, box, 1.1)) == ref_all
+
+
+def test_neighborlist_validation():
+    nb = ops().Neighborlist_f32(10)
+    with pytest.raises(RuntimeError, match="idxs can't be empty"):
+        nb.set_row_idxs(np.array([], dtype=np.uint32))
+    with pytest.raises(RuntimeError, match="atom indices must be unique"):
+        nb.set_row_idxs(np.array([1, 1], dtype=np.uint32))
+    with pytest.raises(RuntimeError, match="number of idxs must be less than N"):
+        nb.set_row_idxs(np.arange(10, dtype=np.uint32))
+    with pytest.raises(RuntimeError, match="indices values must be less than N"):
+        nb.set_row_idxs(np.array([11], dtype=np.uint32))
+    with pytest.raises(RuntimeError, match="size is must be at least 1"):
+        nb.resize(0)
+    with pytest.raises(RuntimeError, match="size is greater than max size: 11 > 10"):
+        nb.resize(11)
+    with pytest.raises(RuntimeError, match="N != N_"):
+        nb.get_nblist(np.zeros((5, 3)), np.eye(3) * 3, 1.0)
+    nb.resize(5)
+    assert nb.get_nblist(np.zeros((5, 3)) + np.arange(5)[:, None] * 0.1, np.eye(3) * 3, 1.0) == [[0, 1, 2, 3, 4]]
+
+
+@pytest.mark.parametrize("precision", [np.float32, np.float64])
+def test_neighborlist_matches_reference_custom_ops(precision):
+    ref = load_reference_ops()
+    if ref is None:
+        pytest.skip("oracle/_ref/custom_ops*.so not built")
+    sys = water_box(999, seed=12)
+    x = sys["x"].astype(np.float32).astype(np.float64)
+    box = sys["box"]
+    suffix = "f32" if precision == np.float32 else "f64"
+    ref_list = getattr(ref, f"Neighborlist_{suffix}")(len(x)).get_nblist(x, box, 1.3)
+    got = nblist_cls(precision)(len(x)).get_nblist(x, box, 1.3)
+    assert canonical(got) == canonical(ref_list)
+    rc, re_ = getattr(ref, f"Neighborlist_{suffix}")(len(x)).compute_block_bounds(x, box, 32)
+    c, e = nblist_cls(precision)(len(x)).compute_block_bounds(x, box, 32)
+    np.testing.assert_allclose(c, rc, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(e, re_, rtol=0, atol=1e-6)

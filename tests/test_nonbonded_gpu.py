@@ -115,6 +115,10 @@ def test_all_pairs_large(precision):
     x, params = round_to_f32(x), round_to_f32(params)
     ref_u, ref_dx, ref_dp = O.nonbonded_all_pairs(x, params, box, BETA, CUTOFF)
     dx, dp, u = impl.execute(x, params, box)
+    # f32 vs the f64 oracle: per-atom sums of ~400 partially cancelling terms of relative accuracy ~1e-6 each; the
+    # tight f32 bound (1e-5) is the one against the reference's own f32 kernels, test_against_reference_custom_ops
+    if precision == np.float32:
+        rtol *= 5
     np.testing.assert_allclose(u, ref_u, rtol=rtol, atol=atol * 10)
     assert_forces_close(ref_dx, dx, rtol)
     assert_forces_close(ref_dp, dp, rtol * 10, what="du_dp")
