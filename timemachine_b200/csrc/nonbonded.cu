@@ -76,6 +76,31 @@ template <typename Real> void NonbondedTiled<Real>::du_dp_fixed_to_float(int N, 
 
 template <typename Real> unsigned int NonbondedTiled<Real>::num_tiles() { return nblist_.num_tile_ixns(); }
 
+template <typename Real> void NonbondedTiled<Real>::set_kernel_timing(bool on) {
+    constexpr size_t CAPACITY = 4096;
+    if (on && timing_events_.empty()) {
+        timing_events_.resize(CAPACITY);
+        for (auto &p : timing_events_) {
+            TMB_CUDA(cudaEventCreate(&p.first));
+            TMB_CUDA(cudaEventCreate(&p.second));
+        }
+    }
+    timing_ = on;
+    timing_used_ = 0;
+}
+
+template <typename Real> std::vector<float> NonbondedTiled<Real>::drain_kernel_times() {
+    std::vector<float> out;
+    for (size_t i = 0; i < timing_used_; i++) {
+        TMB_CUDA(cudaEventSynchronize(timing_events_[i].second));
+        float ms = 0.f;
+        TMB_CUDA(cudaEventElapsedTime(&ms, timing_events_[i].first, timing_events_[i].second));
+        out.push_back(ms);
+    }
+    timing_used_ = 0;
+    return out;
+}
+
 template <typename Real>
 void NonbondedTiled<Real>::run(
     int N, const double *d_x, const double *d_p, const double *d_box, u64 *d_du_dx, u64 *d_du_dp, i128 *d_u,
@@ -127,7 +152,15 @@ void NonbondedTiled<Real>::run(
     ta.d_u = d_u;
     ta.rebuild_flag = d_flags_.data;
     ta.tile_capacity = tl.capacity;
+    const bool timed = timing_ && timing_used_ < timing_events_.size();
+    if (timed) {
+        TMB_CUDA(cudaEventRecord(timing_events_[timing_used_].first, stream));
+    }
     launch_nb_tiles<Real>(ta, d_u != nullptr, d_du_dx != nullptr, d_du_dp != nullptr, stream);
+    if (timed) {
+        TMB_CUDA(cudaEventRecord(timing_events_[timing_used_].second, stream));
+        timing_used_++;
+    }
 
     if (d_du_dx) {
         launch_scatter_accum(K_, Kpad(), 3, d_perm_.data, d_acc_dx_.data, d_du_dx, stream);

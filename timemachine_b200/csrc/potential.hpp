@@ -232,9 +232,15 @@ public:
     NonbondedTiled(int N, double beta, double cutoff, bool disable_hilbert, double nblist_padding, int steps_per_sort);
     void du_dp_fixed_to_float(int N, int P, const u64 *du_dp, double *out) const override;
     int capturable_steps() const override {
+        if (timing_) {
+            return 0; // per-launch events are recorded eagerly
+        }
         const long long r = steps_since_last_sort_ % steps_per_sort_;
         return r == 0 ? 0 : static_cast<int>(steps_per_sort_ - r);
     }
+    // Measurement hook for bench.py: bracket every tile-kernel launch with CUDA events on its launch stream.
+    void set_kernel_timing(bool on);
+    std::vector<float> drain_kernel_times(); // milliseconds per launch since the last drain (synchronises)
     void advance(int n) override { steps_since_last_sort_ += n; }
     double get_cutoff() const { return cutoff_; }
     double get_nblist_padding() const { return nblist_padding_; }
@@ -249,6 +255,9 @@ protected:
     const int steps_per_sort_;
     long long steps_since_last_sort_ = 0;
     bool force_rebuild_ = true;
+    bool timing_ = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events_;
+    size_t timing_used_ = 0;
 
     DeviceBuffer<unsigned int> d_perm_;
     DeviceBuffer<Vec4<Real>> d_xw_, d_qse_;

@@ -275,7 +275,25 @@ PeriodicTorsion_f32 = _make_bonded("PeriodicTorsion_f32", _L.tmb_periodic_torsio
 PeriodicTorsion_f64 = _make_bonded("PeriodicTorsion_f64", _L.tmb_periodic_torsion_create, F64)
 
 
-class _NonbondedAllPairs(Potential):
+class _TiledExtras:
+    """Introspection / measurement hooks of the tile-list potentials (not part of the reference API)."""
+
+    def get_tile_count(self) -> int:
+        n = C.c_uint()
+        _check(_L.tmb_nonbonded_num_tiles(self._handle, C.byref(n)))
+        return n.value
+
+    def set_kernel_timing(self, on: bool) -> None:
+        _check(_L.tmb_nonbonded_set_kernel_timing(self._handle, int(bool(on))))
+
+    def drain_kernel_times(self) -> np.ndarray:
+        out = np.empty(4096, dtype=np.float32)
+        n = C.c_int()
+        _check(_L.tmb_nonbonded_drain_kernel_times(self._handle, _ptr(out, C.c_float), out.size, C.byref(n)))
+        return out[: n.value].copy()
+
+
+class _NonbondedAllPairs(Potential, _TiledExtras):
     _precision = F32
 
     def __init__(self, num_atoms, beta, cutoff, atom_idxs_i=None, disable_hilbert_sort=False, nblist_padding=0.1):
@@ -321,7 +339,7 @@ class NonbondedAllPairs_f64(_NonbondedAllPairs):
     _precision = F64
 
 
-class _NonbondedInteractionGroup(Potential):
+class _NonbondedInteractionGroup(Potential, _TiledExtras):
     _precision = F32
 
     def __init__(
