@@ -213,6 +213,19 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+class stdout_to_stderr:
+    """The reference's C++ prints warnings with std::cout (context.cu:124-126); keep them off our one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_force_step(OC, O, s, x, v, params, coeffs, rng):
     """One force evaluation + BAOAB step with the CPU oracle (C/OpenMP port), all host threads."""
     N = s["N"]
@@ -466,18 +479,19 @@ def main():
 
                 ref = load_reference_ops()
                 if ref is not None:
-                    rimpl = make_reference_potential(ref, s)
-                    rbp = ref.BoundPotential(rimpl, flats[my_state])
-                    rintg = ref.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 1234)
-                    rctx = ref.Context(x_eq, v_eq, s["box"], rintg, [rbp])
-                    rctx.multiple_steps(args.md_steps, args.md_steps + 1)
-                    torch.cuda.synchronize(dev)
-                    t0 = time.perf_counter()
-                    reps = 3
-                    for _ in range(reps):
+                    with stdout_to_stderr():
+                        rimpl = make_reference_potential(ref, s)
+                        rbp = ref.BoundPotential(rimpl, flats[my_state])
+                        rintg = ref.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 1234)
+                        rctx = ref.Context(x_eq, v_eq, s["box"], rintg, [rbp])
                         rctx.multiple_steps(args.md_steps, args.md_steps + 1)
-                    torch.cuda.synchronize(dev)
-                    rs = (time.perf_counter() - t0) / (reps * args.md_steps)
+                        torch.cuda.synchronize(dev)
+                        t0 = time.perf_counter()
+                        reps = 3
+                        for _ in range(reps):
+                            rctx.multiple_steps(args.md_steps, args.md_steps + 1)
+                        torch.cuda.synchronize(dev)
+                        rs = (time.perf_counter() - t0) / (reps * args.md_steps)
                     ref_gpu = {"value": 86400.0 / rs * DT * 1e-3, "unit": "ns/day", "us_per_md_step": rs * 1e6,
                                "what": "UNMODIFIED reference custom_ops (oracle/_ref, nvcc sm_100a) Context.multiple_steps on the same system, same GPU"}
             except Exception as e:  # the reference is a baseline, never a dependency

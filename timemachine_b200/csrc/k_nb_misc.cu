@@ -16,8 +16,11 @@ constexpr int MISC_THREADS = 128;
 template <typename Real> __global__ void __launch_bounds__(MISC_THREADS) k_nb_prepare(const NbPrepareArgs<Real> a) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int *my_flag = a.flag;
-    if (k == 0 && a.force_rebuild) {
-        *my_flag = 1;
+    if (k == 0) {
+        *a.tile_cursor = 0;
+        if (a.force_rebuild) {
+            *my_flag = 1;
+        }
     }
     if (k < 9) {
         if (a.box[k] != a.box_build[k]) {

@@ -18,6 +18,7 @@ namespace tmb {
 
 constexpr int NB_THREADS = 256;
 constexpr int NB_WARPS = NB_THREADS / WARP;
+constexpr unsigned int NB_CHUNK = 4; // tiles claimed per atomicAdd
 
 template <typename Real, bool WITH_DP> struct LaneAtom {
     Real x, y, z, w;
@@ -177,9 +178,8 @@ __global__ void __launch_bounds__(NB_THREADS) k_nb_tiles(const NbTileArgs<Real> 
         *a.rebuild_flag = 0;
     }
     const unsigned int T = min(*a.tile_count, a.tile_capacity);
-    const unsigned int per_warp = (T + total_warps - 1) / total_warps;
-    const unsigned int t_begin = min(T, gwarp * per_warp);
-    const unsigned int t_end = min(T, t_begin + per_warp);
+    (void)total_warps;
+    (void)gwarp;
 
     i128 energy = 0;
     LaneAtom<Real, P> ai;
@@ -187,7 +187,20 @@ __global__ void __launch_bounds__(NB_THREADS) k_nb_tiles(const NbTileArgs<Real> 
     int i_slot = 0;
     bool i_valid = false;
 
-    for (unsigned int t = t_begin; t < t_end; t++) {
+    // Dynamic scheduling: warps claim chunks of consecutive tiles from a device counter (reset by k_nb_prepare).  Tile
+    // cost varies with fill by ~3x, a static split left ~25 % of the warp-slots idle in the tail (profiles/, round 1).
+    // Consecutive tiles mostly share their row block, so the row atoms still stay in registers across a chunk.
+    for (;;) {
+    unsigned int chunk_begin = 0;
+    if (lane == 0) {
+        chunk_begin = atomicAdd(a.tile_cursor, NB_CHUNK);
+    }
+    chunk_begin = __shfl_sync(0xffffffffu, chunk_begin, 0);
+    if (chunk_begin >= T) {
+        break;
+    }
+    const unsigned int chunk_end = min(T, chunk_begin + NB_CHUNK);
+    for (unsigned int t = chunk_begin; t < chunk_end; t++) {
         const int row = a.tile_rows[t];
         if (row != cur_row) {
             if (cur_row >= 0) {
@@ -211,6 +224,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_nb_tiles(const NbTileArgs<Real> 
             tile_rounds<Real, true, U, X, P>(box, cutoff2, beta, triangular, a.K, i_valid, i_slot, ai, j_slot, aj, energy);
         }
         flush_lane_atom<Real, X, P>(aj, j_slot, j_valid, a.Kpad, a.acc_dx, a.acc_dp);
+    }
     }
     if (cur_row >= 0) {
         flush_lane_atom<Real, X, P>(ai, i_slot, i_valid, a.Kpad, a.acc_dx, a.acc_dp);

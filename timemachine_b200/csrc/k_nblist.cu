@@ -12,6 +12,8 @@
 //  * the whole build is skipped on the device when the rebuild flag is clear (no host round trip).
 #include "kernels.hpp"
 
+#include <algorithm>
+
 namespace tmb {
 
 constexpr int BB_THREADS = 128;
@@ -52,10 +54,26 @@ template <typename Real> __global__ void __launch_bounds__(BB_THREADS) k_block_b
     const Real inv_by = 1 / by;
     const Real inv_bz = 1 / bz;
 
+    if (blockIdx.x == 0 && threadIdx.x < 9) {
+        if (threadIdx.x == 0 && a.reset_count != nullptr) {
+            *a.reset_count = 0;
+            *a.reset_overflow = 0;
+        }
+        if (a.box_build != nullptr) {
+            a.box_build[threadIdx.x] = a.box[threadIdx.x];
+        }
+    }
     Real px = 0, py = 0, pz = 0;
     if (valid) {
         const unsigned int atom = a.idxs != nullptr ? a.idxs[i] : static_cast<unsigned int>(a.base + i);
         load_pos<Real>(a.coords, a.xw, atom, px, py, pz);
+        if (a.x_build != nullptr) {
+            // remember where this atom was when the list was built (reference nonbonded_all_pairs.cu:241-242)
+            const size_t src = static_cast<size_t>(a.perm[atom]) * 3;
+            a.x_build[src + 0] = a.x_src[src + 0];
+            a.x_build[src + 1] = a.x_src[src + 1];
+            a.x_build[src + 2] = a.x_src[src + 2];
+        }
     }
     // lane 0 of a block is always a real atom
     Real min_x = __shfl_sync(0xffffffffu, px, 0), max_x = min_x;
@@ -250,7 +268,9 @@ template <typename Real, bool TRI> __global__ void __launch_bounds__(BT_THREADS)
     const int num_chunks = (num_col_blocks + WARP - 1) / WARP;
     const int first_chunk = TRI ? row_block / WARP : 0;
 
-    for (int chunk = first_chunk + warp; chunk < num_chunks; chunk += BT_WARPS) {
+    // gridDim.y > 1 (few row blocks, e.g. a ligand against the whole environment): the column chunks are dealt over
+    // several CTAs per row block; each CTA then closes its own partial tile
+    for (int chunk = first_chunk + blockIdx.y * BT_WARPS + warp; chunk < num_chunks; chunk += BT_WARPS * gridDim.y) {
         const int col_block_base = chunk * WARP;
         const int my_col_block = col_block_base + lane;
         bool include = (my_col_block < num_col_blocks) && (!TRI || my_col_block >= row_block);
@@ -369,7 +389,10 @@ template <typename Real> void launch_build_tiles(const BuildTilesArgs<Real> &arg
     if (args.upper_triangular) {
         TMB_LAUNCH((k_build_tiles<Real, true>), row_blocks, BT_THREADS, 0, stream, args);
     } else {
-        TMB_LAUNCH((k_build_tiles<Real, false>), row_blocks, BT_THREADS, 0, stream, args);
+        const int num_chunks = ceil_div(ceil_div(args.NC, TILE), WARP);
+        int ny = ceil_div(2 * sm_count(), row_blocks);
+        ny = std::max(1, std::min(ny, ceil_div(num_chunks, BT_WARPS)));
+        TMB_LAUNCH((k_build_tiles<Real, false>), dim3(row_blocks, ny), BT_THREADS, 0, stream, args);
     }
 }
 template void launch_build_tiles<float>(const BuildTilesArgs<float> &, cudaStream_t);

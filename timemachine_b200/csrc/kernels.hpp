@@ -29,6 +29,7 @@ template <typename Real> struct NbTileArgs {
     i128 *d_u; // overwritten
     unsigned int *rebuild_flag; // cleared by this kernel (the build, if any, ran before it in stream order)
     unsigned int tile_capacity;
+    unsigned int *tile_cursor;  // dynamic tile scheduling counter, zeroed by k_nb_prepare of the same evaluation
 };
 template <typename Real> int nb_tiles_max_grid();
 template <typename Real>
@@ -47,6 +48,7 @@ template <typename Real> struct NbPrepareArgs {
     double padding;
     int force_rebuild;        // host-known (after a sort / set_atom_idxs)
     unsigned int *flag;       // [1] rebuild flag: set here, consumed by the build kernels, cleared by the tile kernel
+    unsigned int *tile_cursor; // [1] zeroed here for the tile kernel's dynamic scheduler
     Vec4<Real> *xw;
     Vec4<Real> *qse;
 };
@@ -75,6 +77,13 @@ template <typename Real> struct BlockBoundsArgs {
     Real *ctr; // [num_blocks,3]
     Real *ext; // [num_blocks,3]
     const unsigned int *flag; // nullable: skip all work when *flag == 0
+    // Fused bookkeeping of a (re)build, all optional:
+    unsigned int *reset_count;    // tile counter and
+    unsigned int *reset_overflow; //   overflow flag to clear before the tile build
+    const unsigned int *perm;     // snapshot: x_build[perm[slot]] = x_src[perm[slot]] for every slot this launch covers
+    const double *x_src;
+    double *x_build;
+    double *box_build; // box_build = box
 };
 template <typename Real> void launch_block_bounds(const BlockBoundsArgs<Real> &args, cudaStream_t stream);
 

@@ -167,7 +167,7 @@ template <typename Real> int Neighborlist<Real>::max_ixn_count() const {
 template <typename Real>
 void Neighborlist<Real>::build_device(
     const double *d_coords, const Vec4<Real> *d_xw, const double *d_box, double cutoff, const unsigned int *flag,
-    cudaStream_t stream) {
+    cudaStream_t stream, const Snapshot *snap) {
     BlockBoundsArgs<Real> ba;
     ba.num_blocks = num_col_blocks();
     ba.num_idxs = NC_;
@@ -179,6 +179,14 @@ void Neighborlist<Real>::build_device(
     ba.ctr = d_col_ctr_.data;
     ba.ext = d_col_ext_.data;
     ba.flag = flag;
+    // the first bounds launch also clears the tile counter and snapshots the build-time state
+    ba.reset_count = tiles_.count;
+    ba.reset_overflow = tiles_.overflow;
+    const bool can_snapshot = snap != nullptr && contiguous_;
+    ba.perm = can_snapshot ? snap->perm : nullptr;
+    ba.x_src = can_snapshot ? snap->x_src : nullptr;
+    ba.x_build = can_snapshot ? snap->x_build : nullptr;
+    ba.box_build = can_snapshot ? snap->box_build : nullptr;
     launch_block_bounds<Real>(ba, stream);
     const bool tri = upper_triangular();
     if (!tri) {
@@ -188,9 +196,11 @@ void Neighborlist<Real>::build_device(
         ba.base = row_base_;
         ba.ctr = d_row_ctr_.data;
         ba.ext = d_row_ext_.data;
+        ba.reset_count = nullptr;
+        ba.reset_overflow = nullptr;
+        ba.box_build = nullptr;
         launch_block_bounds<Real>(ba, stream);
     }
-    launch_reset_tile_count(tiles_, flag, stream);
 
     BuildTilesArgs<Real> ta;
     ta.N = N_;
@@ -268,6 +278,12 @@ void Neighborlist<Real>::compute_block_bounds_host(
     ba.ctr = d_col_ctr_.data;
     ba.ext = d_col_ext_.data;
     ba.flag = nullptr;
+    ba.reset_count = nullptr;
+    ba.reset_overflow = nullptr;
+    ba.perm = nullptr;
+    ba.x_src = nullptr;
+    ba.x_build = nullptr;
+    ba.box_build = nullptr;
     launch_block_bounds<Real>(ba, stream);
     TMB_CUDA(cudaStreamSynchronize(stream));
     const size_t n = static_cast<size_t>(num_col_blocks()) * 3;

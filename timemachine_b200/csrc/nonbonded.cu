@@ -124,13 +124,15 @@ void NonbondedTiled<Real>::run(
     pa.padding = nblist_padding_;
     pa.force_rebuild = force;
     pa.flag = d_flags_.data;
+    pa.tile_cursor = d_flags_.data + 1;
     pa.xw = d_xw_.data;
     pa.qse = d_qse_.data;
     launch_nb_prepare<Real>(pa, stream);
 
     const unsigned int *flag = d_flags_.data;
-    nblist_.build_device(nullptr, d_xw_.data, d_box, cutoff_ + nblist_padding_, flag, stream);
-    launch_snapshot_if(flag, N * 3, d_x, d_x_build_.data, d_box, d_box_build_.data, stream);
+    typename Neighborlist<Real>::Snapshot snap{d_perm_.data, d_x, d_x_build_.data, d_box_build_.data};
+    nblist_.build_device(nullptr, d_xw_.data, d_box, cutoff_ + nblist_padding_, flag, stream, &snap);
+    (void)N;
 
     const TileList &tl = nblist_.tiles();
     NbTileArgs<Real> ta;
@@ -152,6 +154,7 @@ void NonbondedTiled<Real>::run(
     ta.d_u = d_u;
     ta.rebuild_flag = d_flags_.data;
     ta.tile_capacity = tl.capacity;
+    ta.tile_cursor = d_flags_.data + 1;
     const bool timed = timing_ && timing_used_ < timing_events_.size();
     if (timed) {
         TMB_CUDA(cudaEventRecord(timing_events_[timing_used_].first, stream));

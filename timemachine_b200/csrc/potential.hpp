@@ -205,8 +205,14 @@ public:
 
     // Enqueue bounds + tile build.  Exactly one of d_coords / d_xw is given; `flag` (nullable) gates all work on
     // the device.
+    struct Snapshot { // where to record "coordinates/box at build time" (fused into the bounds kernel)
+        const unsigned int *perm;
+        const double *x_src;
+        double *x_build;
+        double *box_build;
+    };
     void build_device(const double *d_coords, const Vec4<Real> *d_xw, const double *d_box, double cutoff,
-                      const unsigned int *flag, cudaStream_t stream);
+                      const unsigned int *flag, cudaStream_t stream, const Snapshot *snap = nullptr);
 
     const TileList &tiles() const { return tiles_; }
     bool upper_triangular() const { return NR_ == N_ && NC_ == N_; }
