@@ -14,6 +14,10 @@
 #include "nb_math.cuh"
 #include "reduce.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+
 namespace tmb {
 
 constexpr int NB_THREADS = 256;
@@ -250,10 +254,24 @@ template <typename Real> static int nb_tiles_grid_impl() {
     return cached;
 }
 
+static bool use_ring_for_f32() {
+    static const bool ring = [] {
+        const char *e = std::getenv("TMB_NB_RING");
+        return e != nullptr && e[0] == '1';
+    }();
+    return ring;
+}
+
 template <typename Real> int nb_tiles_max_grid() { return nb_tiles_grid_impl<Real>(); }
+template <> int nb_tiles_max_grid<float>() { return std::max(nb_tiles_grid_impl<float>(), nb_tiles_cq_max_grid()); }
 
 template <typename Real>
 void launch_nb_tiles(const NbTileArgs<Real> &args, bool with_u, bool with_dx, bool with_dp, cudaStream_t stream) {
+    if (std::is_same<Real, float>::value && !use_ring_for_f32()) {
+        // f32 (the MD path): compaction-queue kernel; the ring kernel below stays as the f64 path and as an A/B reference
+        launch_nb_tiles_cq(reinterpret_cast<const NbTileArgs<float> &>(args), with_u, with_dx, with_dp, stream);
+        return;
+    }
     const int grid = nb_tiles_grid_impl<Real>();
     const int sel = (with_u ? 4 : 0) | (with_dx ? 2 : 0) | (with_dp ? 1 : 0);
     switch (sel) {
@@ -284,7 +302,6 @@ void launch_nb_tiles(const NbTileArgs<Real> &args, bool with_u, bool with_dx, bo
     }
 }
 
-template int nb_tiles_max_grid<float>();
 template int nb_tiles_max_grid<double>();
 template void launch_nb_tiles<float>(const NbTileArgs<float> &, bool, bool, bool, cudaStream_t);
 template void launch_nb_tiles<double>(const NbTileArgs<double> &, bool, bool, bool, cudaStream_t);

@@ -31,6 +31,9 @@ template <typename Real> struct NbTileArgs {
     unsigned int tile_capacity;
     unsigned int *tile_cursor;  // dynamic tile scheduling counter, zeroed by k_nb_prepare of the same evaluation
 };
+// f32 "compaction queue" formulation (k_nb_tiles_cq.cu); launch_nb_tiles<float> uses it unless TMB_NB_RING=1
+int nb_tiles_cq_max_grid();
+void launch_nb_tiles_cq(const NbTileArgs<float> &args, bool with_u, bool with_dx, bool with_dp, cudaStream_t stream);
 template <typename Real> int nb_tiles_max_grid();
 template <typename Real>
 void launch_nb_tiles(const NbTileArgs<Real> &args, bool with_u, bool with_dx, bool with_dp, cudaStream_t stream);
