@@ -343,3 +343,42 @@ def test_against_reference_custom_ops(precision, rtol, n):
         assert np.array_equal(dx, rdx), f"{np.count_nonzero(dx != rdx)} of {dx.size} force components differ"
         assert np.array_equal(dp, rdp), f"{np.count_nonzero(dp != rdp)} of {dp.size} du_dp components differ"
         assert u == ru
+
+
+def test_compaction_queue_kernel_equals_ring_kernel_bitwise(tmp_path):
+    """The f32 production kernel (k_nb_tiles_cq.cu) and the ring formulation (k_nb_tiles.cu, selected with
+    TMB_NB_RING=1 in a fresh process) evaluate the same pair terms; only the integer summation order differs."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    script = tmp_path / "dump.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {str(root)!r})\n"
+        "from tests.common import random_nonbonded_system, round_to_f32\n"
+        "from timemachine_b200 import potentials as P\n"
+        "out = {}\n"
+        "for n, pat in ((33, 'zero'), (700, 'some'), (3080, 'some')):\n"
+        "    x, p, box = random_nonbonded_system(n, seed=n + 3, w_pattern=pat)\n"
+        "    x, p = round_to_f32(x), round_to_f32(p)\n"
+        "    impl = P.NonbondedAllPairs(n, 2.0, 1.2).to_gpu(np.float32).unbound_impl\n"
+        "    dx, dp, u = impl.execute(x, p, box)\n"
+        "    out[f'dx{n}'], out[f'dp{n}'], out[f'u{n}'] = dx, dp, u\n"
+        "    rows = np.arange(0, n, 9).astype(np.int32)\n"
+        "    g = P.NonbondedInteractionGroup(n, rows, 2.0, 1.2).to_gpu(np.float32).unbound_impl\n"
+        "    gdx, gdp, gu = g.execute(x, p, box)\n"
+        "    out[f'gdx{n}'], out[f'gdp{n}'], out[f'gu{n}'] = gdx, gdp, gu\n"
+        "np.savez(sys.argv[1], **out)\n"
+    )
+    results = {}
+    for mode in ("0", "1"):
+        env = dict(os.environ, TMB_NB_RING=mode)
+        path = tmp_path / f"out{mode}.npz"
+        subprocess.check_call([sys.executable, str(script), str(path)], env=env)
+        results[mode] = dict(np.load(path))
+    assert set(results["0"]) == set(results["1"])
+    for k in results["0"]:
+        np.testing.assert_array_equal(results["0"][k], results["1"][k], err_msg=k)
