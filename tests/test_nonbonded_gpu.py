@@ -340,7 +340,9 @@ def test_against_reference_custom_ops(precision, rtol, n):
     if precision == np.float32:
         # stronger than the stated tolerance: the per-pair rounding sequence is the reference's (nb_math.cuh), every
         # term is rounded to fixed point before it is summed, so forces, du/dp and energy are BIT-identical
-        assert np.array_equal(dx, rdx), f"{np.count_nonzero(dx != rdx)} of {dx.size} force components differ"
+        bad = np.argwhere(dx != rdx)
+        detail = [(tuple(ix), int(round(dx[tuple(ix)] * 2**36)), int(round(rdx[tuple(ix)] * 2**36))) for ix in bad[:6]]
+        assert len(bad) == 0, f"{len(bad)} of {dx.size} force components differ (index, ours, reference in fixed point): {detail}"
         assert np.array_equal(dp, rdp), f"{np.count_nonzero(dp != rdp)} of {dp.size} du_dp components differ"
         assert u == ru
 
