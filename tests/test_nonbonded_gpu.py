@@ -313,6 +313,28 @@ def test_decomposition_is_bitwise_consistent(precision, rng):
 
 
 # ---- against the reference's own kernels (when oracle/_ref was built) ------------------------------------------------------
+@pytest.mark.parametrize("precision", [np.float64, np.float32])
+@pytest.mark.parametrize("dist", [0.16, 0.13, 0.11])
+def test_large_pair_terms(precision, dist):
+    """Pair forces of 1e5..1e8 kJ/mol/nm (close contacts, still inside the 64-bit fixed-point range) exceed the two
+    27-bit limbs of the f32 tile kernel's shared accumulators and must take its direct global path (k_nb_tiles_cq.cu)."""
+    n = 200
+    x, params, box = random_nonbonded_system(n, seed=17, w_pattern="zero")
+    for a, b in ((0, 1), (50, 150), (77, 78)):
+        x[b] = x[a] + np.array([dist, 0.0, 0.0])
+        params[[a, b], 1] = 0.15
+        params[[a, b], 2] = 1.0
+    x, params = round_to_f32(x), round_to_f32(params)
+    impl = pots().NonbondedAllPairs(n, BETA, CUTOFF).to_gpu(precision).unbound_impl
+    dx, dp, u = impl.execute(x, params, box)
+    ou, odx, odp = O.nonbonded_all_pairs(x, params, box, BETA, CUTOFF)
+    assert np.abs(odx).max() > 2.0**17
+    rtol = 1e-9 if precision == np.float64 else 5e-4
+    assert_forces_close(odx, dx, rtol)
+    assert_forces_close(odp, dp, rtol * 10, what="du_dp")
+    np.testing.assert_allclose(u, ou, rtol=rtol)
+
+
 @pytest.mark.parametrize("precision,rtol", [(np.float32, 1e-5), (np.float64, 1e-9)])
 @pytest.mark.parametrize("n", [231, 3080])
 def test_against_reference_custom_ops(precision, rtol, n):
@@ -340,11 +362,21 @@ def test_against_reference_custom_ops(precision, rtol, n):
     if precision == np.float32:
         # stronger than the stated tolerance: the per-pair rounding sequence is the reference's (nb_math.cuh), every
         # term is rounded to fixed point before it is summed, so forces, du/dp and energy are BIT-identical
-        bad = np.argwhere(dx != rdx)
+        # ... for every component whose pair terms fit the 64-bit fixed-point range.  A clashing pair of the random
+        # system (|force| >= 2^27 kJ/mol/nm) overflows it: the reference's float->fixed conversion wraps, ours
+        # saturates (fixed_point.cuh), both are garbage by contract (reference FIXED_TO_FLOAT overflow note,
+        # fixed_point.hpp:11-17), so components at a quarter of full scale or beyond are not compared.
+        in_range = (np.abs(dx) < 2.0**26) & (np.abs(rdx) < 2.0**26)
+        assert in_range.mean() > 0.99
+        bad = np.argwhere((dx != rdx) & in_range)
         detail = [(tuple(ix), int(round(dx[tuple(ix)] * 2**36)), int(round(rdx[tuple(ix)] * 2**36))) for ix in bad[:6]]
         assert len(bad) == 0, f"{len(bad)} of {dx.size} force components differ (index, ours, reference in fixed point): {detail}"
-        assert np.array_equal(dp, rdp), f"{np.count_nonzero(dp != rdp)} of {dp.size} du_dp components differ"
-        assert u == ru
+        dp_full_scale = 2.0 ** np.array([27, 26, 25, 27])  # 2^63 / 2^(36, 37, 38, 36)
+        dp_in_range = (np.abs(dp) < dp_full_scale / 2) & (np.abs(rdp) < dp_full_scale / 2) & in_range.all(axis=1)[:, None]
+        assert dp_in_range.mean() > 0.99
+        assert not np.any((dp != rdp) & dp_in_range), f"{np.count_nonzero((dp != rdp) & dp_in_range)} of {dp.size} du_dp components differ"
+        if in_range.all():
+            assert u == ru
 
 
 def test_compaction_queue_kernel_equals_ring_kernel_bitwise(tmp_path):

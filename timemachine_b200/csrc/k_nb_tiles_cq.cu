@@ -6,13 +6,16 @@
 // (tile fill measured on the Hilbert-sorted list; ncu: 17.4 of 32 threads active per instruction, the
 // kernel is issue-bound).  Here a tile is processed in two decoupled phases:
 //   A. 32 cheap rounds: minimum-image distance of lane i against column (i + r) % 32, read from shared memory; hits are
-//      appended (ballot + prefix popcount) to a per-warp ring queue {dx, dy, dz, d2, dw, i|j} in shared memory;
+//      appended (ballot + prefix popcount) to a per-warp ring queue {dx, dy, dz, i|j} (+ dw) in shared memory with one
+//      16-byte store;
 //   B. whenever 32 hits are queued, one fully populated warp evaluates them: parameters are fetched from the per-warp
-//      shared copy of the 64 atoms, the force is converted to fixed point, split into three 22-bit limbs and added with
-//      native 32-bit shared-memory atomics (no-return ATOMS.ADD: 1.0-1.8 SM-cycles per warp instruction on B200,
-//      profiles/microbench_r1.txt; a 64-bit shared atomicAdd is a CAS loop at 9-16 cycles) to the row atom's and the
-//      column atom's accumulators.  Limb sums of <= 32 terms cannot overflow 32 bits; they are folded back into 64-bit
-//      registers / global reductions once per tile (the column side is negated there: fixed(-v) == -fixed(v)).
+//      shared copy of the 64 atoms, the force is converted to fixed point, split into a 27-bit low limb and a signed
+//      high limb and added with native 32-bit shared-memory atomics (no-return ATOMS.ADD: 1.0-1.8 SM-cycles per warp
+//      instruction on B200, profiles/microbench_r1.txt; a 64-bit shared atomicAdd is a CAS loop at 9-16 cycles) to the
+//      row atom's and the column atom's accumulators.  Two limbs hold any term with |v| < 2^53 (|force| < 1.3e5
+//      kJ/mol/nm per pair) and sums of <= 32 such terms cannot overflow; the rare larger term (clashing atoms) goes
+//      straight to the global 64-bit accumulator.  Limb sums are folded back into 64-bit registers / global
+//      reductions once per tile (the column side is negated there: fixed(-v) == -fixed(v)).
 // The expensive instructions therefore run at ~90 % lane utilisation instead of ~34 %, and the XU-pipe work (MUFU,
 // F2I) drops by the same factor.  Accumulation order changes, results do not (integer sums).
 //
@@ -27,88 +30,137 @@ namespace tmb {
 
 constexpr int CQ_THREADS = 256;
 constexpr int CQ_WARPS = CQ_THREADS / WARP;
-constexpr unsigned int CQ_CHUNK = 4; // tiles claimed per atomicAdd on the tile cursor
-constexpr int CQ_QUEUE = 64;         // ring capacity (a round appends <= 32, a batch removes 32)
-constexpr int LIMB_BITS = 22;
+// Scheduling: every warp first takes CQ_STATIC consecutive tiles (runs of equal row block stay together), the rest of
+// the list is handed out one tile at a time from the device cursor.  A warp only processes ~6 tiles per launch at the
+// 30k-atom benchmark size, so coarser dynamic chunks leave a long tail (ncu r1: 41 % of warp slots active on average).
+constexpr unsigned int CQ_STATIC = 4;
+constexpr int CQ_QUEUE = 64; // ring capacity (a round appends <= 32, a batch removes 32)
+constexpr int LIMB_BITS = 27;
 constexpr unsigned int LIMB_MASK = (1u << LIMB_BITS) - 1u;
 
 // Per-warp shared memory, as offsets (in 4-byte words) into one flat array.
 // atoms: [0,32) row block, [32,64) column atoms
 constexpr int S_X = 0, S_Y = 64, S_Z = 128, S_W = 192, S_Q = 256, S_SIG = 320, S_EPS = 384;
 constexpr int S_JSLOT = 448;                // int[32]
-constexpr int S_ACCX = 480;                 // int[3 comps][3 limbs][64 atoms]: rows [0,32) get +, columns [32,64) get + (negated at fold)
-constexpr int S_QDX = S_ACCX + 9 * 64;      // queue
-constexpr int S_QDY = S_QDX + CQ_QUEUE;
-constexpr int S_QDZ = S_QDY + CQ_QUEUE;
-constexpr int S_QD2 = S_QDZ + CQ_QUEUE;
-constexpr int S_QDW = S_QD2 + CQ_QUEUE;
-constexpr int S_QIDX = S_QDW + CQ_QUEUE;    // int[64]: i | j << 5
-constexpr int S_ACCP = S_QIDX + CQ_QUEUE;   // int[4 params][3 limbs][64 atoms] (du/dp variants only)
-constexpr int S_WORDS_X = S_ACCP;
-constexpr int S_WORDS_P = S_ACCP + 12 * 64;
+constexpr int S_ACCX = 480;                 // int[3 comps][2 limbs][64 atoms]: rows [0,32) get +, columns [32,64) get + (negated at fold)
+constexpr int S_Q4 = S_ACCX + 6 * 64;       // queue: float4 {dx, dy, dz, bits(i | j << 5)} (16-byte aligned: 864 words)
+constexpr int S_QDW = S_Q4 + 4 * CQ_QUEUE;  // queue: dw (alchemical tiles only)
+constexpr int S_ACCP = S_QDW + CQ_QUEUE;    // int[4 params][2 limbs][64 atoms] (du/dp variants only)
+constexpr int S_WORDS_X = S_ACCP;           // 1184 words = 4736 B per warp
+constexpr int S_WORDS_P = S_ACCP + 8 * 64;  // 1696 words = 6784 B per warp
+static_assert(S_Q4 % 4 == 0 && S_WORDS_X % 4 == 0 && S_WORDS_P % 4 == 0, "float4 queue alignment");
 
-__device__ __forceinline__ void limbs_add(int *acc /*[3][64]*/, int atom, u64 v) {
-    const unsigned int lo = static_cast<unsigned int>(v) & LIMB_MASK;
-    const unsigned int mid = static_cast<unsigned int>(v >> LIMB_BITS) & LIMB_MASK;
-    const int hi = static_cast<int>(static_cast<i64>(v) >> (2 * LIMB_BITS));
-    atomicAdd(acc + 0 * 64 + atom, static_cast<int>(lo));
-    atomicAdd(acc + 1 * 64 + atom, static_cast<int>(mid));
-    atomicAdd(acc + 2 * 64 + atom, hi);
+// |v| < 2^53 as a signed 64-bit number (tested on the high word only)
+__device__ __forceinline__ bool limb_small(u64 v) {
+    const int hi32 = static_cast<int>(v >> 32);
+    return static_cast<unsigned int>(hi32 + (1 << 21)) < (1u << 22);
 }
-// fold the three signed limb sums of `atom` into a 64-bit value and clear them
+__device__ __forceinline__ void limb_add(int *acc /*[2][64]*/, int atom, u64 v) {
+    atomicAdd(acc + atom, static_cast<int>(static_cast<unsigned int>(v) & LIMB_MASK));
+    atomicAdd(acc + 64 + atom, static_cast<int>(static_cast<i64>(v) >> LIMB_BITS));
+}
+// fold the two limb sums of `atom` into a 64-bit value and clear them
 __device__ __forceinline__ u64 limbs_take(int *acc, int atom) {
-    const i64 lo = acc[0 * 64 + atom];
-    const i64 mid = acc[1 * 64 + atom];
-    const i64 hi = acc[2 * 64 + atom];
-    acc[0 * 64 + atom] = 0;
-    acc[1 * 64 + atom] = 0;
-    acc[2 * 64 + atom] = 0;
-    return static_cast<u64>(lo) + (static_cast<u64>(mid) << LIMB_BITS) + (static_cast<u64>(hi) << (2 * LIMB_BITS));
+    const unsigned int lo = static_cast<unsigned int>(acc[atom]);
+    const i64 hi = acc[64 + atom];
+    acc[atom] = 0;
+    acc[64 + atom] = 0;
+    return static_cast<u64>(lo) + (static_cast<u64>(hi) << LIMB_BITS);
 }
+
+// Where the rare term too large for the limb accumulators goes (the global sorted-order accumulators).
+struct CqSink {
+    u64 *acc_dx;
+    u64 *acc_dp;
+    int Kpad;
+    int row_base; // sorted slot of row atom 0 of the current tile
+};
 
 // Phase B: evaluate `count` (<= 32) queued pairs, one per lane.
 template <bool ALCH, bool U, bool X, bool P>
-__device__ __forceinline__ void cq_process(float *S, const int head, const int count, const float beta, i128 &energy) {
+__device__ __forceinline__ void cq_process(
+    float *S, const int head, const int count, const float beta, const CqSink &sink, i128 &energy) {
     const int lane = threadIdx.x & 31;
     int *SI = reinterpret_cast<int *>(S);
     __syncwarp();
     if (lane < count) {
         const int k = (head + lane) & (CQ_QUEUE - 1);
-        const float dx = S[S_QDX + k], dy = S[S_QDY + k], dz = S[S_QDZ + k], d2 = S[S_QD2 + k];
-        const int idx = SI[S_QIDX + k];
+        const float4 item = reinterpret_cast<const float4 *>(S + S_Q4)[k];
+        const float dx = item.x, dy = item.y, dz = item.z;
+        const int idx = __float_as_int(item.w);
         const int i = idx & 31;
         const int j = 32 + (idx >> 5);
+        // same expression as phase A: the queue does not carry d2
+        float d2 = dist2_3d(dx, dy, dz);
+        float dw = 0.0f;
+        if (ALCH) {
+            dw = S[S_QDW + k];
+            d2 = fma_(dw, dw, d2);
+        }
         const float qi = S[S_Q + i], qj = S[S_Q + j];
         const float ei = S[S_EPS + i], ej = S[S_EPS + j];
         const PairTerms<float> t = pair_terms<float, U>(1.0f, 1.0f, qi, qj, S[S_SIG + i], S[S_SIG + j], ei, ej, d2, beta);
+        const int gi = sink.row_base + i;
+        const int gj = SI[S_JSLOT + j - 32];
         if (X) {
             const u64 fx = to_fixed_force(t.prefactor * dx);
             const u64 fy = to_fixed_force(t.prefactor * dy);
             const u64 fz = to_fixed_force(t.prefactor * dz);
             int *acc = SI + S_ACCX;
-            limbs_add(acc + 0 * 192, i, fx);
-            limbs_add(acc + 1 * 192, i, fy);
-            limbs_add(acc + 2 * 192, i, fz);
-            // the column atom receives the exact negation; it is accumulated positively and negated once at the fold
-            limbs_add(acc + 0 * 192, j, fx);
-            limbs_add(acc + 1 * 192, j, fy);
-            limbs_add(acc + 2 * 192, j, fz);
+            if (limb_small(fx) && limb_small(fy) && limb_small(fz)) {
+                limb_add(acc + 0 * 128, i, fx);
+                limb_add(acc + 1 * 128, i, fy);
+                limb_add(acc + 2 * 128, i, fz);
+                // the column atom receives the exact negation; it is accumulated positively and negated once at the fold
+                limb_add(acc + 0 * 128, j, fx);
+                limb_add(acc + 1 * 128, j, fy);
+                limb_add(acc + 2 * 128, j, fz);
+            } else {
+                // clashing atoms: too large for two limbs, add to the global accumulators directly
+                atomicAdd(sink.acc_dx + 0 * sink.Kpad + gi, fx);
+                atomicAdd(sink.acc_dx + 1 * sink.Kpad + gi, fy);
+                atomicAdd(sink.acc_dx + 2 * sink.Kpad + gi, fz);
+                atomicAdd(sink.acc_dx + 0 * sink.Kpad + gj, 0ull - fx);
+                atomicAdd(sink.acc_dx + 1 * sink.Kpad + gj, 0ull - fy);
+                atomicAdd(sink.acc_dx + 2 * sink.Kpad + gj, 0ull - fz);
+            }
         }
         if (P) {
             int *acc = SI + S_ACCP;
-            limbs_add(acc + P_CHARGE * 192, i, to_fixed<FIXED_EXPONENT_DU_DCHARGE>(qj * t.inv_d * t.damping));
-            limbs_add(acc + P_CHARGE * 192, j, to_fixed<FIXED_EXPONENT_DU_DCHARGE>(qi * t.inv_d * t.damping));
+            const u64 pqi = to_fixed<FIXED_EXPONENT_DU_DCHARGE>(qj * t.inv_d * t.damping);
+            const u64 pqj = to_fixed<FIXED_EXPONENT_DU_DCHARGE>(qi * t.inv_d * t.damping);
+            u64 psig = 0, pei = 0, pej = 0, pw = 0;
             if (t.lj) {
-                const u64 fs = to_fixed<FIXED_EXPONENT_DU_DSIG>(t.sig_grad);
-                limbs_add(acc + P_SIG * 192, i, fs);
-                limbs_add(acc + P_SIG * 192, j, fs);
-                limbs_add(acc + P_EPS * 192, i, to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ej));
-                limbs_add(acc + P_EPS * 192, j, to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ei));
+                psig = to_fixed<FIXED_EXPONENT_DU_DSIG>(t.sig_grad);
+                pei = to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ej);
+                pej = to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ei);
             }
             if (ALCH) {
-                const u64 fw = to_fixed<FIXED_EXPONENT_DU_DW>(t.prefactor * S[S_QDW + k]);
-                limbs_add(acc + P_W * 192, i, fw);
-                limbs_add(acc + P_W * 192, j, 0ull - fw); // dw is antisymmetric
+                pw = to_fixed<FIXED_EXPONENT_DU_DW>(t.prefactor * dw); // antisymmetric: the column atom gets -pw
+            }
+            if (limb_small(pqi) && limb_small(pqj) && limb_small(psig) && limb_small(pei) && limb_small(pej) &&
+                limb_small(pw)) {
+                limb_add(acc + P_CHARGE * 128, i, pqi);
+                limb_add(acc + P_CHARGE * 128, j, pqj);
+                if (t.lj) {
+                    limb_add(acc + P_SIG * 128, i, psig);
+                    limb_add(acc + P_SIG * 128, j, psig);
+                    limb_add(acc + P_EPS * 128, i, pei);
+                    limb_add(acc + P_EPS * 128, j, pej);
+                }
+                if (ALCH) {
+                    limb_add(acc + P_W * 128, i, pw);
+                    limb_add(acc + P_W * 128, j, 0ull - pw);
+                }
+            } else {
+                atomicAdd(sink.acc_dp + P_CHARGE * sink.Kpad + gi, pqi);
+                atomicAdd(sink.acc_dp + P_CHARGE * sink.Kpad + gj, pqj);
+                atomicAdd(sink.acc_dp + P_SIG * sink.Kpad + gi, psig);
+                atomicAdd(sink.acc_dp + P_SIG * sink.Kpad + gj, psig);
+                atomicAdd(sink.acc_dp + P_EPS * sink.Kpad + gi, pei);
+                atomicAdd(sink.acc_dp + P_EPS * sink.Kpad + gj, pej);
+                atomicAdd(sink.acc_dp + P_W * sink.Kpad + gi, pw);
+                atomicAdd(sink.acc_dp + P_W * sink.Kpad + gj, 0ull - pw);
             }
         }
         if (U) {
@@ -122,7 +174,7 @@ __device__ __forceinline__ void cq_process(float *S, const int head, const int c
 template <bool ALCH, bool DIAG, bool U, bool X, bool P>
 __device__ __forceinline__ void cq_tile(
     float *S, const float bx, const float by, const float bz, const float inv_bx, const float inv_by, const float inv_bz,
-    const float cutoff2, const float beta, const int i_slot, i128 &energy) {
+    const float cutoff2, const float beta, const int i_slot, const CqSink &sink, i128 &energy) {
     const int lane = threadIdx.x & 31;
     const unsigned int lt_mask = (1u << lane) - 1u;
     int *SI = reinterpret_cast<int *>(S);
@@ -154,25 +206,21 @@ __device__ __forceinline__ void cq_tile(
         const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
         if (hit) {
             const int k = (head + count + __popc(ballot & lt_mask)) & (CQ_QUEUE - 1);
-            S[S_QDX + k] = dx;
-            S[S_QDY + k] = dy;
-            S[S_QDZ + k] = dz;
-            S[S_QD2 + k] = d2;
+            reinterpret_cast<float4 *>(S + S_Q4)[k] = make_float4(dx, dy, dz, __int_as_float(lane | (jp << 5)));
             if (ALCH) {
                 S[S_QDW + k] = dw;
             }
-            SI[S_QIDX + k] = lane | (jp << 5);
         }
         count += __popc(ballot);
         if (count >= WARP) {
-            cq_process<ALCH, U, X, P>(S, head, WARP, beta, energy);
+            cq_process<ALCH, U, X, P>(S, head, WARP, beta, sink, energy);
             head = (head + WARP) & (CQ_QUEUE - 1);
             count -= WARP;
         }
         jp = (jp + 1) & 31;
     }
     if (count > 0) {
-        cq_process<ALCH, U, X, P>(S, head, count, beta, energy);
+        cq_process<ALCH, U, X, P>(S, head, count, beta, sink, energy);
     }
 }
 
@@ -197,12 +245,12 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
         *a.rebuild_flag = 0;
     }
     // clear this warp's limb accumulators
-    for (int c = 0; c < 9; c++) {
+    for (int c = 0; c < 6; c++) {
         SI[S_ACCX + c * 64 + lane] = 0;
         SI[S_ACCX + c * 64 + 32 + lane] = 0;
     }
     if (P) {
-        for (int c = 0; c < 12; c++) {
+        for (int c = 0; c < 8; c++) {
             SI[S_ACCP + c * 64 + lane] = 0;
             SI[S_ACCP + c * 64 + 32 + lane] = 0;
         }
@@ -234,21 +282,30 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
         gpi[0] = gpi[1] = gpi[2] = gpi[3] = 0;
     };
 
-    for (;;) {
-        unsigned int chunk_begin = 0;
-        if (lane == 0) {
-            chunk_begin = atomicAdd(a.tile_cursor, CQ_CHUNK);
+    const unsigned int static_end = min(T, static_cast<unsigned int>(gridDim.x) * CQ_WARPS * CQ_STATIC);
+    CqSink sink = {a.acc_dx, a.acc_dp, a.Kpad, 0};
+    for (bool first = true;; first = false) {
+        unsigned int chunk_begin, chunk_end;
+        if (first) {
+            chunk_begin = min(static_end, (blockIdx.x * CQ_WARPS + warp) * CQ_STATIC);
+            chunk_end = min(static_end, chunk_begin + CQ_STATIC);
+        } else {
+            unsigned int next = 0;
+            if (lane == 0) {
+                next = atomicAdd(a.tile_cursor, 1u);
+            }
+            chunk_begin = static_end + __shfl_sync(0xffffffffu, next, 0);
+            if (chunk_begin >= T) {
+                break;
+            }
+            chunk_end = chunk_begin + 1;
         }
-        chunk_begin = __shfl_sync(0xffffffffu, chunk_begin, 0);
-        if (chunk_begin >= T) {
-            break;
-        }
-        const unsigned int chunk_end = min(T, chunk_begin + CQ_CHUNK);
         for (unsigned int t = chunk_begin; t < chunk_end; t++) {
             const int row = a.tile_rows[t];
             if (row != cur_row) {
                 flush_row();
                 cur_row = row;
+                sink.row_base = row * TILE;
                 i_slot = row * TILE + lane;
                 i_valid = i_slot < a.NR;
                 Vec4<float> c = {nan, nan, nan, 0.f}, p = {0.f, 0.f, 0.f, 0.f};
@@ -288,22 +345,22 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
             __syncwarp();
             if (vanilla) {
                 if (diag) {
-                    cq_tile<false, true, U, X, P>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, energy);
+                    cq_tile<false, true, U, X, P>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, sink, energy);
                 } else {
-                    cq_tile<false, false, U, X, P>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, energy);
+                    cq_tile<false, false, U, X, P>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, sink, energy);
                 }
             } else {
                 if (diag) {
-                    cq_tile<true, true, U, X, P>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, energy);
+                    cq_tile<true, true, U, X, P>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, sink, energy);
                 } else {
-                    cq_tile<true, false, U, X, P>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, energy);
+                    cq_tile<true, false, U, X, P>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, sink, energy);
                 }
             }
             // fold this tile's limb sums: row atoms into registers, column atoms (negated) to the sorted accumulators
             if (X) {
                 for (int c = 0; c < 3; c++) {
-                    gi[c] += limbs_take(SI + S_ACCX + c * 192, lane);
-                    const u64 gj = 0ull - limbs_take(SI + S_ACCX + c * 192, 32 + lane);
+                    gi[c] += limbs_take(SI + S_ACCX + c * 128, lane);
+                    const u64 gj = 0ull - limbs_take(SI + S_ACCX + c * 128, 32 + lane);
                     if (j_valid && gj != 0) {
                         atomicAdd(a.acc_dx + c * a.Kpad + j_slot, gj);
                     }
@@ -311,8 +368,8 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
             }
             if (P) {
                 for (int c = 0; c < 4; c++) {
-                    gpi[c] += limbs_take(SI + S_ACCP + c * 192, lane);
-                    const u64 gj = limbs_take(SI + S_ACCP + c * 192, 32 + lane);
+                    gpi[c] += limbs_take(SI + S_ACCP + c * 128, lane);
+                    const u64 gj = limbs_take(SI + S_ACCP + c * 128, 32 + lane);
                     if (j_valid && gj != 0) {
                         atomicAdd(a.acc_dp + c * a.Kpad + j_slot, gj);
                     }
