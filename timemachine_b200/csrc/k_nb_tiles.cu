@@ -262,6 +262,15 @@ static bool use_ring_for_f32() {
     return ring;
 }
 
+int nb_tiles_reserved_ctas() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char *env = std::getenv("TMB_NB_RESERVE");
+        cached = env != nullptr ? std::max(0, std::atoi(env)) : 16;
+    }
+    return cached;
+}
+
 template <typename Real> int nb_tiles_max_grid() { return nb_tiles_grid_impl<Real>(); }
 template <> int nb_tiles_max_grid<float>() { return std::max(nb_tiles_grid_impl<float>(), nb_tiles_cq_max_grid()); }
 
@@ -272,7 +281,10 @@ void launch_nb_tiles(const NbTileArgs<Real> &args, bool with_u, bool with_dx, bo
         launch_nb_tiles_cq(reinterpret_cast<const NbTileArgs<float> &>(args), with_u, with_dx, with_dp, stream);
         return;
     }
-    const int grid = nb_tiles_grid_impl<Real>();
+    int grid = nb_tiles_grid_impl<Real>();
+    if (args.grid_ctas > 0) {
+        grid = std::min(grid, args.grid_ctas);
+    }
     const int sel = (with_u ? 4 : 0) | (with_dx ? 2 : 0) | (with_dp ? 1 : 0);
     switch (sel) {
     case 0:

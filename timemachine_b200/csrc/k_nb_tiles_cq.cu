@@ -21,6 +21,8 @@
 //
 // Invalid atoms (padding of the last block / of a partial tile) are given NaN coordinates in the shared copy: every
 // comparison d2 < cutoff2 is then false, so no validity logic is needed in the inner loop.
+#include <algorithm>
+
 #include "fixed_point.cuh"
 #include "kernels.hpp"
 #include "nb_math.cuh"
@@ -30,10 +32,9 @@ namespace tmb {
 
 constexpr int CQ_THREADS = 256;
 constexpr int CQ_WARPS = CQ_THREADS / WARP;
-// Scheduling: every warp first takes CQ_STATIC consecutive tiles (runs of equal row block stay together), the rest of
-// the list is handed out one tile at a time from the device cursor.  A warp only processes ~6 tiles per launch at the
-// 30k-atom benchmark size, so coarser dynamic chunks leave a long tail (ncu r1: 41 % of warp slots active on average).
-constexpr unsigned int CQ_STATIC = 4;
+// Scheduling: every warp first takes args.static_tiles consecutive tiles (runs of equal row block stay together), the
+// rest of the list is handed out one tile at a time from the device cursor.  A warp only processes ~6 tiles per launch
+// at the 30k-atom benchmark size, so coarser dynamic chunks leave a long tail (ncu r1: 41 % of warp slots active).
 constexpr int CQ_QUEUE = 64; // ring capacity (a round appends <= 32, a batch removes 32)
 constexpr int LIMB_BITS = 27;
 constexpr unsigned int LIMB_MASK = (1u << LIMB_BITS) - 1u;
@@ -282,13 +283,15 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
         gpi[0] = gpi[1] = gpi[2] = gpi[3] = 0;
     };
 
-    const unsigned int static_end = min(T, static_cast<unsigned int>(gridDim.x) * CQ_WARPS * CQ_STATIC);
+    const unsigned int total_warps = gridDim.x * CQ_WARPS;
+    const unsigned int n_static = min(a.static_tiles, T / total_warps);
+    const unsigned int static_end = n_static * total_warps;
     CqSink sink = {a.acc_dx, a.acc_dp, a.Kpad, 0};
     for (bool first = true;; first = false) {
         unsigned int chunk_begin, chunk_end;
         if (first) {
-            chunk_begin = min(static_end, (blockIdx.x * CQ_WARPS + warp) * CQ_STATIC);
-            chunk_end = min(static_end, chunk_begin + CQ_STATIC);
+            chunk_begin = (blockIdx.x * CQ_WARPS + warp) * n_static;
+            chunk_end = chunk_begin + n_static;
         } else {
             unsigned int next = 0;
             if (lane == 0) {
@@ -409,7 +412,10 @@ int nb_tiles_cq_max_grid() {
 }
 
 void launch_nb_tiles_cq(const NbTileArgs<float> &args, bool with_u, bool with_dx, bool with_dp, cudaStream_t stream) {
-    const int grid = nb_tiles_cq_max_grid();
+    int grid = nb_tiles_cq_max_grid();
+    if (args.grid_ctas > 0) {
+        grid = std::min(grid, args.grid_ctas);
+    }
     const int sel = (with_u ? 4 : 0) | (with_dx ? 2 : 0) | (with_dp ? 1 : 0);
     switch (sel) {
     case 0:

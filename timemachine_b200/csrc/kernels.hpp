@@ -30,7 +30,12 @@ template <typename Real> struct NbTileArgs {
     unsigned int *rebuild_flag; // cleared by this kernel (the build, if any, ran before it in stream order)
     unsigned int tile_capacity;
     unsigned int *tile_cursor;  // dynamic tile scheduling counter, zeroed by k_nb_prepare of the same evaluation
+    int grid_ctas = 0;              // persistent grid size; 0 = every CTA slot of the device
+    unsigned int static_tiles = 0;  // tiles each warp takes up front (clamped to tile_count / warps); the rest is dynamic
 };
+// CTA slots a machine-filling tile launch leaves free so that a small concurrent tile launch (the ligand-environment
+// interaction group next to the environment all-pairs term) is not serialised behind it; TMB_NB_RESERVE overrides.
+int nb_tiles_reserved_ctas();
 // f32 "compaction queue" formulation (k_nb_tiles_cq.cu); launch_nb_tiles<float> uses it unless TMB_NB_RING=1
 int nb_tiles_cq_max_grid();
 void launch_nb_tiles_cq(const NbTileArgs<float> &args, bool with_u, bool with_dx, bool with_dp, cudaStream_t stream);

@@ -155,6 +155,26 @@ void NonbondedTiled<Real>::run(
     ta.rebuild_flag = d_flags_.data;
     ta.tile_capacity = tl.capacity;
     ta.tile_cursor = d_flags_.data + 1;
+    {
+        // Persistent-grid policy.  A launch that can fill the machine leaves a few CTA slots free (the tile kernel
+        // otherwise owns every register of every SM and a concurrent small tile launch - the ligand-environment
+        // interaction group next to the environment all-pairs term - would only start when it ends); a small launch
+        // is sized from the upper bound of its tile count and scheduled dynamically, since its CTAs may become
+        // resident one after another.
+        const long row_blocks = ceil_div(NR_, TILE);
+        const long col_blocks = ceil_div(NR_ == K_ ? K_ : K_ - NR_, TILE);
+        const long max_tiles = NR_ == K_ ? row_blocks * (row_blocks + 1) / 2 : row_blocks * col_blocks;
+        const int full = nb_tiles_max_grid<Real>();
+        const int warps_per_cta = 8;
+        const int roomy = std::max(1, full - (full > 4 * nb_tiles_reserved_ctas() ? nb_tiles_reserved_ctas() : 0));
+        if (max_tiles >= 2L * full * warps_per_cta) {
+            ta.grid_ctas = roomy;
+            ta.static_tiles = 4;
+        } else {
+            ta.grid_ctas = static_cast<int>(std::min<long>(roomy, std::max<long>(1, ceil_div(max_tiles, 2L * warps_per_cta))));
+            ta.static_tiles = 0;
+        }
+    }
     const bool timed = timing_ && timing_used_ < timing_events_.size();
     if (timed) {
         TMB_CUDA(cudaEventRecord(timing_events_[timing_used_].first, stream));
