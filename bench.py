@@ -384,6 +384,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches_before = ops.kernel_launch_count()
+    rebuilds_before = all_pairs_impl.get_num_rebuilds()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     wall0 = time.perf_counter()
@@ -397,6 +398,7 @@ def main():
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     gpu_launches = ops.kernel_launch_count() - launches_before
+    nblist_rebuilds = all_pairs_impl.get_num_rebuilds() - rebuilds_before
     total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
     t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -455,7 +457,7 @@ def main():
         achieved = algo_bytes / t_kernel / 1e9
         pair_slots = 1024.0 * T
         roofline = {
-            "kernel": "k_nb_tiles<float,U=0,X=1,P=0> (NonbondedAllPairs, env-env)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "kernel": "k_nb_tiles_cq<U=0,X=1,P=0> (NonbondedAllPairs, env-env)", "bound": "hbm", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_us": t_kernel * 1e6,
             "launches_timed": int(len(times_ms)), "tiles": int(T), "algorithmic_bytes": algo_bytes,
             "pair_slots_per_s": pair_slots / t_kernel,
@@ -503,7 +505,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(workload, l2="256 MiB buffer rewritten between timed steps; MD state itself is carried step to step",
                                                 timing="CUDA events on the MD stream per bench step, summed; max over ranks"),
-            "clocks": clocks, "gpu_launches": int(gpu_launches), "wall_s": wall,
+            "clocks": clocks, "gpu_launches": int(gpu_launches), "nblist_rebuilds": int(nblist_rebuilds), "md_steps_timed": int(args.md_steps * args.steps), "wall_s": wall,
             "e2e": {"value": e2e_ns_day, "unit": "ns/day", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": ref_gpu,
             "us_per_md_step": total_ms * 1e3 / (args.md_steps * args.steps),

@@ -110,6 +110,9 @@ int tmb_potential_execute_device(
     uint64_t *d_du_dx, uint64_t *d_du_dp, tmb_i128 *d_u, void *cuda_stream);
 /* number of 32x32 interaction tiles in the cached neighbour list of a NonbondedAllPairs / InteractionGroup */
 int tmb_nonbonded_num_tiles(tmb_potential pot, unsigned int *out);
+/* neighbour-list (re)builds since construction; the rebuild decision itself never leaves the device
+ * (reference: host-side flag read every step, nonbonded_all_pairs.cu:217-235) */
+int tmb_nonbonded_num_rebuilds(tmb_potential pot, unsigned int *out);
 /* measurement hooks (bench.py roofline): bracket each tile-kernel launch with CUDA events on its launch stream;
  * drain returns the per-launch durations in ms recorded since the previous drain (at most `capacity`). */
 int tmb_nonbonded_set_kernel_timing(tmb_potential pot, int on);

@@ -336,6 +336,18 @@ int tmb_nonbonded_num_tiles(tmb_potential pot, unsigned int *out) {
     });
 }
 
+int tmb_nonbonded_num_rebuilds(tmb_potential pot, unsigned int *out) {
+    return guarded([&] {
+        if (auto a = std::dynamic_pointer_cast<NonbondedTiled<float>>(as_pot(pot))) {
+            *out = a->num_rebuilds();
+        } else if (auto b = std::dynamic_pointer_cast<NonbondedTiled<double>>(as_pot(pot))) {
+            *out = b->num_rebuilds();
+        } else {
+            throw std::runtime_error("not a tile-list nonbonded potential");
+        }
+    });
+}
+
 int tmb_nonbonded_set_kernel_timing(tmb_potential pot, int on) {
     return guarded([&] {
         if (auto a = std::dynamic_pointer_cast<NonbondedTiled<float>>(as_pot(pot))) {

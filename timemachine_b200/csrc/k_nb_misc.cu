@@ -1,4 +1,5 @@
-// Gather/cast + device-side rebuild decision, scatter-accumulate, build-time snapshot and small utilities.
+// Gather/cast + device-side rebuild decision, build-time snapshot and small utilities.
+#include "block_bounds.cuh"
 #include "fixed_point.cuh"
 #include "kernels.hpp"
 #include "reduce.cuh"
@@ -15,48 +16,67 @@ constexpr int MISC_THREADS = 128;
 // runs after the (conditional) build in stream order, clears it.
 template <typename Real> __global__ void __launch_bounds__(MISC_THREADS) k_nb_prepare(const NbPrepareArgs<Real> a) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int *my_flag = a.flag;
+    bool rebuild = false;
     if (k == 0) {
         *a.tile_cursor = 0;
-        if (a.force_rebuild) {
-            *my_flag = 1;
-        }
+        rebuild = a.force_rebuild != 0;
     }
     if (k < 9) {
-        if (a.box[k] != a.box_build[k]) {
-            *my_flag = 1;
+        rebuild = rebuild || (a.box[k] != a.box_build[k]);
+    }
+    Vec4<Real> c = {0, 0, 0, 0};
+    if (k < a.K) {
+        const unsigned int atom = a.perm[k];
+        const double x = a.x[atom * 3 + 0];
+        const double y = a.x[atom * 3 + 1];
+        const double z = a.x[atom * 3 + 2];
+        const double *p = a.p + static_cast<size_t>(atom) * P_PER_ATOM;
+
+        Vec4<Real> q;
+        c.x = static_cast<Real>(x);
+        c.y = static_cast<Real>(y);
+        c.z = static_cast<Real>(z);
+        c.w = static_cast<Real>(p[P_W]);
+        q.x = static_cast<Real>(p[P_CHARGE]);
+        q.y = static_cast<Real>(p[P_SIG]);
+        q.z = static_cast<Real>(p[P_EPS]);
+        q.w = static_cast<Real>(0);
+        a.xw[k] = c;
+        a.qse[k] = q;
+
+        const Real ox = static_cast<Real>(a.x_build[atom * 3 + 0]);
+        const Real oy = static_cast<Real>(a.x_build[atom * 3 + 1]);
+        const Real oz = static_cast<Real>(a.x_build[atom * 3 + 2]);
+        const Real dx = ox - c.x;
+        const Real dy = oy - c.y;
+        const Real dz = oz - c.z;
+        const Real d2 = dx * dx + dy * dy + dz * dz;
+        rebuild = rebuild || (static_cast<double>(d2) > 0.25 * a.padding * a.padding);
+    }
+    if (rebuild) {
+        // benign races: every writer stores the same values, and nothing reads them before the kernel ends
+        *a.flag = 1;
+        if (a.reset_count != nullptr) {
+            *a.reset_count = 0;
+            *a.reset_overflow = 0;
         }
     }
-    if (k >= a.K) {
-        return;
-    }
-    const unsigned int atom = a.perm[k];
-    const double x = a.x[atom * 3 + 0];
-    const double y = a.x[atom * 3 + 1];
-    const double z = a.x[atom * 3 + 2];
-    const double *p = a.p + static_cast<size_t>(atom) * P_PER_ATOM;
-
-    Vec4<Real> c, q;
-    c.x = static_cast<Real>(x);
-    c.y = static_cast<Real>(y);
-    c.z = static_cast<Real>(z);
-    c.w = static_cast<Real>(p[P_W]);
-    q.x = static_cast<Real>(p[P_CHARGE]);
-    q.y = static_cast<Real>(p[P_SIG]);
-    q.z = static_cast<Real>(p[P_EPS]);
-    q.w = static_cast<Real>(0);
-    a.xw[k] = c;
-    a.qse[k] = q;
-
-    const Real ox = static_cast<Real>(a.x_build[atom * 3 + 0]);
-    const Real oy = static_cast<Real>(a.x_build[atom * 3 + 1]);
-    const Real oz = static_cast<Real>(a.x_build[atom * 3 + 2]);
-    const Real dx = ox - c.x;
-    const Real dy = oy - c.y;
-    const Real dz = oz - c.z;
-    const Real d2 = dx * dx + dy * dy + dz * dz;
-    if (static_cast<double>(d2) > 0.25 * a.padding * a.padding) {
-        *my_flag = 1; // benign race: every writer stores the same value
+    if (a.ctr != nullptr) {
+        // warp w of the grid holds block w (MISC_THREADS is a multiple of 32, k is lane-contiguous)
+        const int block = k / WARP;
+        if (block * WARP < a.K) {
+            const Real bx = static_cast<Real>(a.box[0]);
+            const Real by = static_cast<Real>(a.box[4]);
+            const Real bz = static_cast<Real>(a.box[8]);
+            Real ctr[3], ext[3];
+            warp_block_bounds<Real>(c.x, c.y, c.z, a.K - block * WARP, bx, by, bz, 1 / bx, 1 / by, 1 / bz, ctr, ext);
+            if ((threadIdx.x & 31) == 0) {
+                for (int d = 0; d < 3; d++) {
+                    a.ctr[block * 3 + d] = ctr[d];
+                    a.ext[block * 3 + d] = ext[d];
+                }
+            }
+        }
     }
 }
 
@@ -66,39 +86,6 @@ template <typename Real> void launch_nb_prepare(const NbPrepareArgs<Real> &args,
 }
 template void launch_nb_prepare<float>(const NbPrepareArgs<float> &, cudaStream_t);
 template void launch_nb_prepare<double>(const NbPrepareArgs<double> &, cudaStream_t);
-
-// out[perm[k], d] += acc[d][k]; acc[d][k] = 0
-template <int D>
-__global__ void __launch_bounds__(MISC_THREADS)
-    k_scatter_accum(const int K, const int Kpad, const unsigned int *__restrict__ perm, u64 *__restrict__ acc, u64 *__restrict__ out) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) {
-        return;
-    }
-    const unsigned int atom = perm[k];
-#pragma unroll
-    for (int d = 0; d < D; d++) {
-        const u64 v = acc[d * Kpad + k];
-        if (v != 0) {
-            atomicAdd(out + static_cast<size_t>(atom) * D + d, v);
-            acc[d * Kpad + k] = 0;
-        }
-    }
-}
-
-void launch_scatter_accum(
-    int K, int Kpad, int D, const unsigned int *perm, u64 *acc_sorted, u64 *out, cudaStream_t stream) {
-    if (K <= 0) {
-        return;
-    }
-    if (D == 3) {
-        TMB_LAUNCH(k_scatter_accum<3>, ceil_div(K, MISC_THREADS), MISC_THREADS, 0, stream, K, Kpad, perm, acc_sorted, out);
-    } else if (D == 4) {
-        TMB_LAUNCH(k_scatter_accum<4>, ceil_div(K, MISC_THREADS), MISC_THREADS, 0, stream, K, Kpad, perm, acc_sorted, out);
-    } else {
-        throw std::runtime_error("scatter_accum: unsupported D");
-    }
-}
 
 __global__ void __launch_bounds__(MISC_THREADS) k_snapshot_if(
     const unsigned int *__restrict__ flag,

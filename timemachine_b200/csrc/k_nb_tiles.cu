@@ -53,20 +53,22 @@ load_lane_atom(LaneAtom<Real, DP> &a, const Vec4<Real> *__restrict__ xw, const V
 
 template <typename Real, bool X, bool P>
 __device__ __forceinline__ void flush_lane_atom(
-    const LaneAtom<Real, P> &a, int slot, bool valid, int Kpad, u64 *__restrict__ acc_dx, u64 *__restrict__ acc_dp) {
+    const LaneAtom<Real, P> &a, int slot, bool valid, const unsigned int *__restrict__ perm, u64 *__restrict__ du_dx,
+    u64 *__restrict__ du_dp) {
     if (!valid) {
         return;
     }
+    const size_t atom = perm[slot];
     if (X) {
-        atomicAdd(acc_dx + 0 * Kpad + slot, a.gx);
-        atomicAdd(acc_dx + 1 * Kpad + slot, a.gy);
-        atomicAdd(acc_dx + 2 * Kpad + slot, a.gz);
+        atomicAdd(du_dx + atom * 3 + 0, a.gx);
+        atomicAdd(du_dx + atom * 3 + 1, a.gy);
+        atomicAdd(du_dx + atom * 3 + 2, a.gz);
     }
     if (P) {
-        atomicAdd(acc_dp + P_CHARGE * Kpad + slot, a.gq);
-        atomicAdd(acc_dp + P_SIG * Kpad + slot, a.gsig);
-        atomicAdd(acc_dp + P_EPS * Kpad + slot, a.geps);
-        atomicAdd(acc_dp + P_W * Kpad + slot, a.gw);
+        atomicAdd(du_dp + atom * P_PER_ATOM + P_CHARGE, a.gq);
+        atomicAdd(du_dp + atom * P_PER_ATOM + P_SIG, a.gsig);
+        atomicAdd(du_dp + atom * P_PER_ATOM + P_EPS, a.geps);
+        atomicAdd(du_dp + atom * P_PER_ATOM + P_W, a.gw);
     }
 }
 
@@ -179,7 +181,10 @@ __global__ void __launch_bounds__(NB_THREADS) k_nb_tiles(const NbTileArgs<Real> 
     const bool triangular = (a.NR == a.K);
 
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        *a.rebuild_flag = 0;
+        if (*a.rebuild_flag != 0) {
+            a.rebuild_flag[2] += 1; // builds since construction (introspection only)
+            *a.rebuild_flag = 0;
+        }
     }
     const unsigned int T = min(*a.tile_count, a.tile_capacity);
     (void)total_warps;
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_nb_tiles(const NbTileArgs<Real> 
         const int row = a.tile_rows[t];
         if (row != cur_row) {
             if (cur_row >= 0) {
-                flush_lane_atom<Real, X, P>(ai, i_slot, i_valid, a.Kpad, a.acc_dx, a.acc_dp);
+                flush_lane_atom<Real, X, P>(ai, i_slot, i_valid, a.perm, a.du_dx, a.du_dp);
             }
             cur_row = row;
             i_slot = row * TILE + lane;
@@ -227,11 +232,11 @@ __global__ void __launch_bounds__(NB_THREADS) k_nb_tiles(const NbTileArgs<Real> 
         } else {
             tile_rounds<Real, true, U, X, P>(box, cutoff2, beta, triangular, a.K, i_valid, i_slot, ai, j_slot, aj, energy);
         }
-        flush_lane_atom<Real, X, P>(aj, j_slot, j_valid, a.Kpad, a.acc_dx, a.acc_dp);
+        flush_lane_atom<Real, X, P>(aj, j_slot, j_valid, a.perm, a.du_dx, a.du_dp);
     }
     }
     if (cur_row >= 0) {
-        flush_lane_atom<Real, X, P>(ai, i_slot, i_valid, a.Kpad, a.acc_dx, a.acc_dp);
+        flush_lane_atom<Real, X, P>(ai, i_slot, i_valid, a.perm, a.du_dx, a.du_dp);
     }
 
     if (U) {

@@ -71,9 +71,9 @@ __device__ __forceinline__ u64 limbs_take(int *acc, int atom) {
 
 // Where the rare term too large for the limb accumulators goes (the global sorted-order accumulators).
 struct CqSink {
-    u64 *acc_dx;
-    u64 *acc_dp;
-    int Kpad;
+    const unsigned int *perm;
+    u64 *du_dx;
+    u64 *du_dp;
     int row_base; // sorted slot of row atom 0 of the current tile
 };
 
@@ -101,8 +101,8 @@ __device__ __forceinline__ void cq_process(
         const float qi = S[S_Q + i], qj = S[S_Q + j];
         const float ei = S[S_EPS + i], ej = S[S_EPS + j];
         const PairTerms<float> t = pair_terms<float, U>(1.0f, 1.0f, qi, qj, S[S_SIG + i], S[S_SIG + j], ei, ej, d2, beta);
-        const int gi = sink.row_base + i;
-        const int gj = SI[S_JSLOT + j - 32];
+        const int si = sink.row_base + i;      // sorted slots, translated to atoms on the (rare) direct path only
+        const int sj = SI[S_JSLOT + j - 32];
         if (X) {
             const u64 fx = to_fixed_force(t.prefactor * dx);
             const u64 fy = to_fixed_force(t.prefactor * dy);
@@ -118,12 +118,14 @@ __device__ __forceinline__ void cq_process(
                 limb_add(acc + 2 * 128, j, fz);
             } else {
                 // clashing atoms: too large for two limbs, add to the global accumulators directly
-                atomicAdd(sink.acc_dx + 0 * sink.Kpad + gi, fx);
-                atomicAdd(sink.acc_dx + 1 * sink.Kpad + gi, fy);
-                atomicAdd(sink.acc_dx + 2 * sink.Kpad + gi, fz);
-                atomicAdd(sink.acc_dx + 0 * sink.Kpad + gj, 0ull - fx);
-                atomicAdd(sink.acc_dx + 1 * sink.Kpad + gj, 0ull - fy);
-                atomicAdd(sink.acc_dx + 2 * sink.Kpad + gj, 0ull - fz);
+                u64 *gi = sink.du_dx + static_cast<size_t>(sink.perm[si]) * 3;
+                u64 *gj = sink.du_dx + static_cast<size_t>(sink.perm[sj]) * 3;
+                atomicAdd(gi + 0, fx);
+                atomicAdd(gi + 1, fy);
+                atomicAdd(gi + 2, fz);
+                atomicAdd(gj + 0, 0ull - fx);
+                atomicAdd(gj + 1, 0ull - fy);
+                atomicAdd(gj + 2, 0ull - fz);
             }
         }
         if (P) {
@@ -154,14 +156,16 @@ __device__ __forceinline__ void cq_process(
                     limb_add(acc + P_W * 128, j, 0ull - pw);
                 }
             } else {
-                atomicAdd(sink.acc_dp + P_CHARGE * sink.Kpad + gi, pqi);
-                atomicAdd(sink.acc_dp + P_CHARGE * sink.Kpad + gj, pqj);
-                atomicAdd(sink.acc_dp + P_SIG * sink.Kpad + gi, psig);
-                atomicAdd(sink.acc_dp + P_SIG * sink.Kpad + gj, psig);
-                atomicAdd(sink.acc_dp + P_EPS * sink.Kpad + gi, pei);
-                atomicAdd(sink.acc_dp + P_EPS * sink.Kpad + gj, pej);
-                atomicAdd(sink.acc_dp + P_W * sink.Kpad + gi, pw);
-                atomicAdd(sink.acc_dp + P_W * sink.Kpad + gj, 0ull - pw);
+                u64 *gi = sink.du_dp + static_cast<size_t>(sink.perm[si]) * P_PER_ATOM;
+                u64 *gj = sink.du_dp + static_cast<size_t>(sink.perm[sj]) * P_PER_ATOM;
+                atomicAdd(gi + P_CHARGE, pqi);
+                atomicAdd(gj + P_CHARGE, pqj);
+                atomicAdd(gi + P_SIG, psig);
+                atomicAdd(gj + P_SIG, psig);
+                atomicAdd(gi + P_EPS, pei);
+                atomicAdd(gj + P_EPS, pej);
+                atomicAdd(gi + P_W, pw);
+                atomicAdd(gj + P_W, 0ull - pw);
             }
         }
         if (U) {
@@ -243,7 +247,10 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
     const float nan = __int_as_float(0x7fc00000);
 
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        *a.rebuild_flag = 0;
+        if (*a.rebuild_flag != 0) {
+            a.rebuild_flag[2] += 1; // builds since construction (introspection only)
+            *a.rebuild_flag = 0;
+        }
     }
     // clear this warp's limb accumulators
     for (int c = 0; c < 6; c++) {
@@ -268,14 +275,15 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
 
     auto flush_row = [&]() {
         if (cur_row >= 0 && i_valid) {
+            const size_t atom = a.perm[i_slot];
             if (X) {
-                atomicAdd(a.acc_dx + 0 * a.Kpad + i_slot, gi[0]);
-                atomicAdd(a.acc_dx + 1 * a.Kpad + i_slot, gi[1]);
-                atomicAdd(a.acc_dx + 2 * a.Kpad + i_slot, gi[2]);
+                atomicAdd(a.du_dx + atom * 3 + 0, gi[0]);
+                atomicAdd(a.du_dx + atom * 3 + 1, gi[1]);
+                atomicAdd(a.du_dx + atom * 3 + 2, gi[2]);
             }
             if (P) {
                 for (int c = 0; c < 4; c++) {
-                    atomicAdd(a.acc_dp + c * a.Kpad + i_slot, gpi[c]);
+                    atomicAdd(a.du_dp + atom * P_PER_ATOM + c, gpi[c]);
                 }
             }
         }
@@ -286,7 +294,7 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
     const unsigned int total_warps = gridDim.x * CQ_WARPS;
     const unsigned int n_static = min(a.static_tiles, T / total_warps);
     const unsigned int static_end = n_static * total_warps;
-    CqSink sink = {a.acc_dx, a.acc_dp, a.Kpad, 0};
+    CqSink sink = {a.perm, a.du_dx, a.du_dp, 0};
     for (bool first = true;; first = false) {
         unsigned int chunk_begin, chunk_end;
         if (first) {
@@ -326,6 +334,7 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
             }
             const int j_slot = static_cast<int>(min(a.tile_cols[t * TILE + lane], static_cast<unsigned int>(a.K)));
             const bool j_valid = j_slot < a.K;
+            const size_t j_atom = j_valid ? a.perm[j_slot] : 0;
             {
                 Vec4<float> c = {nan, nan, nan, 0.f}, p = {0.f, 0.f, 0.f, 0.f};
                 if (j_valid) {
@@ -365,7 +374,7 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
                     gi[c] += limbs_take(SI + S_ACCX + c * 128, lane);
                     const u64 gj = 0ull - limbs_take(SI + S_ACCX + c * 128, 32 + lane);
                     if (j_valid && gj != 0) {
-                        atomicAdd(a.acc_dx + c * a.Kpad + j_slot, gj);
+                        atomicAdd(a.du_dx + j_atom * 3 + c, gj);
                     }
                 }
             }
@@ -374,7 +383,7 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
                     gpi[c] += limbs_take(SI + S_ACCP + c * 128, lane);
                     const u64 gj = limbs_take(SI + S_ACCP + c * 128, 32 + lane);
                     if (j_valid && gj != 0) {
-                        atomicAdd(a.acc_dp + c * a.Kpad + j_slot, gj);
+                        atomicAdd(a.du_dp + j_atom * P_PER_ATOM + c, gj);
                     }
                 }
             }

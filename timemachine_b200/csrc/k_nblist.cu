@@ -10,6 +10,7 @@
 //  * finished tiles are staged in shared memory and published in batches with one atomicAdd per batch, so the list
 //    is made of RUNS of tiles with equal row block - the tile kernel keeps the row atoms in registers across a run;
 //  * the whole build is skipped on the device when the rebuild flag is clear (no host round trip).
+#include "block_bounds.cuh"
 #include "kernels.hpp"
 
 #include <algorithm>
@@ -75,36 +76,13 @@ template <typename Real> __global__ void __launch_bounds__(BB_THREADS) k_block_b
             a.x_build[src + 2] = a.x_src[src + 2];
         }
     }
-    // lane 0 of a block is always a real atom
-    Real min_x = __shfl_sync(0xffffffffu, px, 0), max_x = min_x;
-    Real min_y = __shfl_sync(0xffffffffu, py, 0), max_y = min_y;
-    Real min_z = __shfl_sync(0xffffffffu, pz, 0), max_z = min_z;
-    const Real half = static_cast<Real>(0.5);
-    for (int it = 1; it <= WARP; it++) {
-        const int src = it & 31;
-        const Real qx = __shfl_sync(0xffffffffu, px, src);
-        const Real qy = __shfl_sync(0xffffffffu, py, src);
-        const Real qz = __shfl_sync(0xffffffffu, pz, src);
-        const bool src_valid = (block * TILE + src) < a.num_idxs;
-        if (src_valid) {
-            Real im = qx - bx * nearbyint((qx - half * (max_x + min_x)) * inv_bx);
-            min_x = min(min_x, im);
-            max_x = max(max_x, im);
-            im = qy - by * nearbyint((qy - half * (max_y + min_y)) * inv_by);
-            min_y = min(min_y, im);
-            max_y = max(max_y, im);
-            im = qz - bz * nearbyint((qz - half * (max_z + min_z)) * inv_bz);
-            min_z = min(min_z, im);
-            max_z = max(max_z, im);
-        }
-    }
+    Real ctr[3], ext[3];
+    warp_block_bounds<Real>(px, py, pz, a.num_idxs - block * TILE, bx, by, bz, inv_bx, inv_by, inv_bz, ctr, ext);
     if (lane == 0) {
-        a.ctr[block * 3 + 0] = half * (max_x + min_x);
-        a.ctr[block * 3 + 1] = half * (max_y + min_y);
-        a.ctr[block * 3 + 2] = half * (max_z + min_z);
-        a.ext[block * 3 + 0] = half * (max_x - min_x);
-        a.ext[block * 3 + 1] = half * (max_y - min_y);
-        a.ext[block * 3 + 2] = half * (max_z - min_z);
+        for (int c = 0; c < 3; c++) {
+            a.ctr[block * 3 + c] = ctr[c];
+            a.ext[block * 3 + c] = ext[c];
+        }
     }
 }
 
@@ -203,6 +181,20 @@ template <typename Real, bool TRI> __global__ void __launch_bounds__(BT_THREADS)
     if (a.flag != nullptr && *a.flag == 0) {
         return;
     }
+    if (a.snap_x_build != nullptr) {
+        // remember where every atom was when the list was built (reference nonbonded_all_pairs.cu:241-242)
+        const int n_threads = gridDim.x * gridDim.y * BT_THREADS;
+        const int tid = (blockIdx.y * gridDim.x + blockIdx.x) * BT_THREADS + threadIdx.x;
+        for (int k = tid; k < a.snap_slots; k += n_threads) {
+            const size_t src = static_cast<size_t>(a.snap_perm[k]) * 3;
+            a.snap_x_build[src + 0] = a.snap_x_src[src + 0];
+            a.snap_x_build[src + 1] = a.snap_x_src[src + 1];
+            a.snap_x_build[src + 2] = a.snap_x_src[src + 2];
+        }
+        if (tid < 9) {
+            a.snap_box_build[tid] = a.box[tid];
+        }
+    }
     __shared__ int s_buf[BT_WARPS][2 * TILE];
     __shared__ unsigned int s_stage[BT_WARPS][BT_STAGE * TILE];
     __shared__ int s_left[BT_WARPS];
@@ -268,42 +260,104 @@ template <typename Real, bool TRI> __global__ void __launch_bounds__(BT_THREADS)
     const int num_chunks = (num_col_blocks + WARP - 1) / WARP;
     const int first_chunk = TRI ? row_block / WARP : 0;
 
-    // gridDim.y > 1 (few row blocks, e.g. a ligand against the whole environment): the column chunks are dealt over
-    // several CTAs per row block; each CTA then closes its own partial tile
-    for (int chunk = first_chunk + blockIdx.y * BT_WARPS + warp; chunk < num_chunks; chunk += BT_WARPS * gridDim.y) {
-        const int col_block_base = chunk * WARP;
-        const int my_col_block = col_block_base + lane;
-        bool include = (my_col_block < num_col_blocks) && (!TRI || my_col_block >= row_block);
-        if (include) {
-            Real ddx = row_ctr_x - a.col_ctr[my_col_block * 3 + 0];
-            Real ddy = row_ctr_y - a.col_ctr[my_col_block * 3 + 1];
-            Real ddz = row_ctr_z - a.col_ctr[my_col_block * 3 + 2];
-            ddx -= bx * nearbyint(ddx * inv_bx);
-            ddy -= by * nearbyint(ddy * inv_by);
-            ddz -= bz * nearbyint(ddz * inv_bz);
-            ddx = max(zero, fabs(ddx) - row_ext_x - a.col_ext[my_col_block * 3 + 0]);
-            ddy = max(zero, fabs(ddy) - row_ext_y - a.col_ext[my_col_block * 3 + 1]);
-            ddz = max(zero, fabs(ddz) - row_ext_z - a.col_ext[my_col_block * 3 + 2]);
-            include = (ddx * ddx + ddy * ddy + ddz * ddz) < cutoff2;
+    // Row atoms {x, y, z, |x|^2 / 2} (imaged around the row-block centre when single_box) in shared memory: the
+    // atom-atom test below reads them with broadcast 128-bit loads instead of four shuffles per row atom.
+    __shared__ Vec4<Real> s_row[TILE];
+    if (warp == 0) {
+        s_row[lane] = Vec4<Real>{pos_i_x, pos_i_y, pos_i_z, np_i};
+    }
+    __syncthreads();
+    const Real half_cutoff2 = half * cutoff2;
+
+    // Candidate column blocks are found a window of 32 chunks (32 x 32 blocks) at a time: the warps first run the
+    // box-box test for the window (phase 1, one chunk per warp pass), then the candidates are dealt round-robin to the
+    // warps (phase 2) - spatially sorted atoms put a row block's candidates into very few chunks, and handing whole
+    // chunks to warps left most of them idle.  gridDim.y > 1 (few row blocks, e.g. a ligand against the whole
+    // environment): the chunks are dealt over several CTAs per row block; each CTA closes its own partial tile.
+    __shared__ unsigned int s_flags[WARP];
+    const int n_set = max(0, (num_chunks - first_chunk - static_cast<int>(blockIdx.y) + static_cast<int>(gridDim.y) - 1) /
+                                 static_cast<int>(gridDim.y));
+    auto chunk_of = [&](int i) { return first_chunk + static_cast<int>(blockIdx.y) + i * static_cast<int>(gridDim.y); };
+
+    for (int win = 0; win < n_set; win += WARP) {
+        const int n_win = min(WARP, n_set - win);
+        __syncthreads(); // previous window's flags are no longer needed
+        for (int i = warp; i < n_win; i += BT_WARPS) {
+            const int my_col_block = chunk_of(win + i) * WARP + lane;
+            bool include = (my_col_block < num_col_blocks) && (!TRI || my_col_block >= row_block);
+            if (include) {
+                Real ddx = row_ctr_x - a.col_ctr[my_col_block * 3 + 0];
+                Real ddy = row_ctr_y - a.col_ctr[my_col_block * 3 + 1];
+                Real ddz = row_ctr_z - a.col_ctr[my_col_block * 3 + 2];
+                ddx -= bx * nearbyint(ddx * inv_bx);
+                ddy -= by * nearbyint(ddy * inv_by);
+                ddz -= bz * nearbyint(ddz * inv_bz);
+                ddx = max(zero, fabs(ddx) - row_ext_x - a.col_ext[my_col_block * 3 + 0]);
+                ddy = max(zero, fabs(ddy) - row_ext_y - a.col_ext[my_col_block * 3 + 1]);
+                ddz = max(zero, fabs(ddz) - row_ext_z - a.col_ext[my_col_block * 3 + 2]);
+                include = (ddx * ddx + ddy * ddy + ddz * ddz) < cutoff2;
+            }
+            const unsigned int flags = __ballot_sync(0xffffffffu, include);
+            if (lane == 0) {
+                s_flags[i] = flags;
+            }
         }
-        unsigned int block_flags = __ballot_sync(0xffffffffu, include);
+        __syncthreads();
+        // lane i: candidates in window chunk i and before it (inclusive prefix) - identical in every warp
+        const unsigned int my_flags = lane < n_win ? s_flags[lane] : 0u;
+        int incl = __popc(my_flags);
+        for (int d = 1; d < WARP; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) {
+                incl += up;
+            }
+        }
+        const int n_cand = __shfl_sync(0xffffffffu, incl, WARP - 1);
 
-        while (block_flags != 0) {
-            const int offset = __ffs(block_flags) - 1;
-            block_flags &= block_flags - 1;
-            const int col_block = col_block_base + offset;
+        // candidate number o (in chunk order, then block order) -> column block
+        auto locate = [&](int o) {
+            const int ci = __ffs(__ballot_sync(0xffffffffu, incl > o)) - 1;
+            const unsigned int flags = __shfl_sync(0xffffffffu, my_flags, ci);
+            const int before = __shfl_sync(0xffffffffu, incl - __popc(my_flags), ci);
+            return chunk_of(win + ci) * WARP + static_cast<int>(__fns(flags, 0, o - before + 1));
+        };
+        // column block data {atoms, box} of the next candidate are fetched while the current one is tested
+        struct Cand {
+            unsigned int atom;
+            Real x, y, z, cc_x, cc_y, cc_z, ce_x, ce_y, ce_z;
+        };
+        auto fetch = [&](int col_block) {
+            Cand cd;
             const int cj = col_block * TILE + lane;
-            const unsigned int atom_j =
-                cj < a.NC ? (a.col_idxs != nullptr ? a.col_idxs[cj] : static_cast<unsigned int>(a.col_base + cj))
-                          : static_cast<unsigned int>(N);
+            cd.atom = cj < a.NC ? (a.col_idxs != nullptr ? a.col_idxs[cj] : static_cast<unsigned int>(a.col_base + cj))
+                                : static_cast<unsigned int>(N);
+            cd.x = cd.y = cd.z = 0;
+            if (cd.atom < static_cast<unsigned int>(N)) {
+                load_pos<Real>(a.coords, a.xw, cd.atom, cd.x, cd.y, cd.z);
+            }
+            cd.cc_x = a.col_ctr[col_block * 3 + 0];
+            cd.cc_y = a.col_ctr[col_block * 3 + 1];
+            cd.cc_z = a.col_ctr[col_block * 3 + 2];
+            cd.ce_x = a.col_ext[col_block * 3 + 0];
+            cd.ce_y = a.col_ext[col_block * 3 + 1];
+            cd.ce_z = a.col_ext[col_block * 3 + 2];
+            return cd;
+        };
+        Cand next;
+        next.atom = N;
+        if (warp < n_cand) {
+            next = fetch(locate(warp));
+        }
+        for (int o = warp; o < n_cand; o += BT_WARPS) {
+            const Cand cur = next;
+            if (o + BT_WARPS < n_cand) {
+                next = fetch(locate(o + BT_WARPS));
+            }
+            const unsigned int atom_j = cur.atom;
+            Real pos_j_x = cur.x, pos_j_y = cur.y, pos_j_z = cur.z;
             const bool j_real = atom_j < static_cast<unsigned int>(N);
-
-            const Real cc_x = a.col_ctr[col_block * 3 + 0];
-            const Real cc_y = a.col_ctr[col_block * 3 + 1];
-            const Real cc_z = a.col_ctr[col_block * 3 + 2];
-            const Real ce_x = a.col_ext[col_block * 3 + 0];
-            const Real ce_y = a.col_ext[col_block * 3 + 1];
-            const Real ce_z = a.col_ext[col_block * 3 + 2];
+            const Real cc_x = cur.cc_x, cc_y = cur.cc_y, cc_z = cur.cc_z;
+            const Real ce_x = cur.ce_x, ce_y = cur.ce_y, ce_z = cur.ce_z;
 
             // row atom vs column box (uses the un-imaged row coordinates)
             Real abx = raw_i_x - cc_x;
@@ -316,43 +370,52 @@ template <typename Real, bool TRI> __global__ void __launch_bounds__(BT_THREADS)
             aby = max(zero, fabs(aby) - ce_y);
             abz = max(zero, fabs(abz) - ce_z);
             const bool row_near = atom_i < static_cast<unsigned int>(N) && (abx * abx + aby * aby + abz * abz) < cutoff2;
-            unsigned int row_flags = __ballot_sync(0xffffffffu, row_near);
-
-            Real pos_j_x = 0, pos_j_y = 0, pos_j_z = 0;
-            if (j_real) {
-                load_pos<Real>(a.coords, a.xw, atom_j, pos_j_x, pos_j_y, pos_j_z);
+            const unsigned int row_flags = __ballot_sync(0xffffffffu, row_near);
+            if (row_flags == 0) {
+                continue; // no row atom reaches this column box: nothing of it is listed
             }
-            Real np_j = 0;
+
+            bool interacts = false;
             if (single_box) {
                 pos_j_x -= bx * nearbyint((pos_j_x - row_ctr_x) * inv_bx);
                 pos_j_y -= by * nearbyint((pos_j_y - row_ctr_y) * inv_by);
                 pos_j_z -= bz * nearbyint((pos_j_z - row_ctr_z) * inv_bz);
-                np_j = half * (pos_j_x * pos_j_x + pos_j_y * pos_j_y + pos_j_z * pos_j_z);
-            }
-
-            bool interacts = false;
-            while (row_flags != 0) {
-                const int row_atom = __ffs(row_flags) - 1;
-                row_flags &= row_flags - 1;
-                const Real rx = __shfl_sync(0xffffffffu, pos_i_x, row_atom);
-                const Real ry = __shfl_sync(0xffffffffu, pos_i_y, row_atom);
-                const Real rz = __shfl_sync(0xffffffffu, pos_i_z, row_atom);
-                if (!single_box) {
-                    Real dx = rx - pos_j_x;
-                    Real dy = ry - pos_j_y;
-                    Real dz = rz - pos_j_z;
+                const Real np_j = half * (pos_j_x * pos_j_x + pos_j_y * pos_j_y + pos_j_z * pos_j_z);
+                // four row atoms per step, straight-line; atoms whose row_near bit is clear get an unreachable
+                // threshold, so membership is exactly "some row_near atom within the cutoff" as in the reference
+                for (int base = 0; base < TILE; base += 4) {
+                    const unsigned int bits = (row_flags >> base) & 0xFu;
+                    if (bits == 0) {
+                        continue;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const Vec4<Real> r = s_row[base + u];
+                        const Real half_d2 = r.w + np_j - r.x * pos_j_x - r.y * pos_j_y - r.z * pos_j_z;
+                        const Real limit = ((bits >> u) & 1u) ? half_cutoff2 : static_cast<Real>(-1);
+                        interacts |= half_d2 < limit;
+                    }
+                    // once every column atom is known to interact there is nothing left to learn
+                    if (__all_sync(0xffffffffu, interacts)) {
+                        break;
+                    }
+                }
+            } else {
+                unsigned int todo = row_flags;
+                while (todo != 0) {
+                    const int row_atom = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const Vec4<Real> r = s_row[row_atom];
+                    Real dx = r.x - pos_j_x;
+                    Real dy = r.y - pos_j_y;
+                    Real dz = r.z - pos_j_z;
                     dx -= bx * nearbyint(dx * inv_bx);
                     dy -= by * nearbyint(dy * inv_by);
                     dz -= bz * nearbyint(dz * inv_bz);
                     interacts |= (dx * dx + dy * dy + dz * dz) < cutoff2;
-                } else {
-                    const Real ci = __shfl_sync(0xffffffffu, np_i, row_atom);
-                    const Real half_d2 = ci + np_j - rx * pos_j_x - ry * pos_j_y - rz * pos_j_z;
-                    interacts |= half_d2 < (half * cutoff2);
-                }
-                // once every column atom is known to interact there is nothing left to learn
-                if (__all_sync(0xffffffffu, interacts)) {
-                    break;
+                    if (__all_sync(0xffffffffu, interacts)) {
+                        break;
+                    }
                 }
             }
             w.append(interacts && j_real, static_cast<int>(atom_j));

@@ -13,7 +13,6 @@ namespace tmb {
 template <typename Real> struct NbTileArgs {
     int K;    // gathered atoms (sorted slots); padding column entries are >= K
     int NR;   // row slots are [0, NR); NR == K means all-pairs (upper triangle, i < j)
-    int Kpad; // stride of the SoA accumulators
     const unsigned int *tile_count;
     const int *tile_rows;
     const unsigned int *tile_cols;
@@ -22,12 +21,16 @@ template <typename Real> struct NbTileArgs {
     const double *box;
     double beta;
     double cutoff;
-    u64 *acc_dx; // [3][Kpad] sorted-order fixed-point du/dx accumulators (must be zero on entry)
-    u64 *acc_dp; // [4][Kpad] sorted-order fixed-point du/dp accumulators (must be zero on entry)
+    // Fixed-point outputs in ATOM order, added to atomically (integer sums: order-free).  The kernels translate sorted
+    // slots through perm when they flush a tile, so no scatter pass (reference k_scatter_accum k_nonbonded.cuh:86) runs.
+    const unsigned int *perm; // [K] sorted slot -> atom index
+    u64 *du_dx;               // [N,3] nullable
+    u64 *du_dp;               // [N,4] nullable
     i128 *u_partials;
     unsigned int *ticket;
     i128 *d_u; // overwritten
-    unsigned int *rebuild_flag; // cleared by this kernel (the build, if any, ran before it in stream order)
+    unsigned int *rebuild_flag; // cleared by this kernel (the build, if any, ran before it in stream order);
+                                // rebuild_flag[2] counts the builds
     unsigned int tile_capacity;
     unsigned int *tile_cursor;  // dynamic tile scheduling counter, zeroed by k_nb_prepare of the same evaluation
     int grid_ctas = 0;              // persistent grid size; 0 = every CTA slot of the device
@@ -59,13 +62,15 @@ template <typename Real> struct NbPrepareArgs {
     unsigned int *tile_cursor; // [1] zeroed here for the tile kernel's dynamic scheduler
     Vec4<Real> *xw;
     Vec4<Real> *qse;
+    // Optional fusion of the block-bounds pass (all-pairs layout only: block b == sorted slots [32 b, 32 b + 32)).
+    // Bounds are recomputed every step into ctr/ext (only read by a build); whoever raises the rebuild flag also
+    // clears the tile counter, so a build needs no separate bounds/reset launch.
+    Real *ctr = nullptr; // [ceil(K/32),3]
+    Real *ext = nullptr;
+    unsigned int *reset_count = nullptr;
+    unsigned int *reset_overflow = nullptr;
 };
 template <typename Real> void launch_nb_prepare(const NbPrepareArgs<Real> &args, cudaStream_t stream);
-
-// Scatter sorted-order accumulators back to atom order (atomically, other potentials may be adding concurrently) and
-// re-zero them (reference k_scatter_accum k_nonbonded.cuh:86).
-void launch_scatter_accum(
-    int K, int Kpad, int D, const unsigned int *perm, u64 *acc_sorted, u64 *out /*[N,D]*/, cudaStream_t stream);
 
 // Snapshot coordinates/box at build time, only if the rebuild flag is set.
 void launch_snapshot_if(
@@ -111,6 +116,13 @@ template <typename Real> struct BuildTilesArgs {
     double cutoff;
     TileList tiles;
     const unsigned int *flag; // nullable: skip all work when *flag == 0
+    // Optional "state at build time" snapshot taken by the build itself (when the bounds pass was fused into
+    // k_nb_prepare): x_build[perm[k]] = x_src[perm[k]] for k < snap_slots, box_build = box.
+    const unsigned int *snap_perm = nullptr;
+    const double *snap_x_src = nullptr;
+    double *snap_x_build = nullptr;
+    double *snap_box_build = nullptr;
+    int snap_slots = 0;
 };
 // The tile counter must be reset with launch_reset_tile_count before each build.
 void launch_reset_tile_count(const TileList &tiles, const unsigned int *flag, cudaStream_t stream);

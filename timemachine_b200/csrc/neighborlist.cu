@@ -168,6 +168,11 @@ template <typename Real>
 void Neighborlist<Real>::build_device(
     const double *d_coords, const Vec4<Real> *d_xw, const double *d_box, double cutoff, const unsigned int *flag,
     cudaStream_t stream, const Snapshot *snap) {
+    const bool tri = upper_triangular();
+    const bool fused = snap != nullptr && snap->bounds_done;
+    if (fused && !(tri && contiguous_ && col_base_ == 0)) {
+        throw std::runtime_error("Neighborlist: fused bounds need the all-pairs layout");
+    }
     BlockBoundsArgs<Real> ba;
     ba.num_blocks = num_col_blocks();
     ba.num_idxs = NC_;
@@ -187,8 +192,9 @@ void Neighborlist<Real>::build_device(
     ba.x_src = can_snapshot ? snap->x_src : nullptr;
     ba.x_build = can_snapshot ? snap->x_build : nullptr;
     ba.box_build = can_snapshot ? snap->box_build : nullptr;
-    launch_block_bounds<Real>(ba, stream);
-    const bool tri = upper_triangular();
+    if (!fused) {
+        launch_block_bounds<Real>(ba, stream);
+    }
     if (!tri) {
         ba.num_blocks = num_row_blocks();
         ba.num_idxs = NR_;
@@ -221,6 +227,13 @@ void Neighborlist<Real>::build_device(
     ta.cutoff = cutoff;
     ta.tiles = tiles_;
     ta.flag = flag;
+    if (fused) {
+        ta.snap_perm = snap->perm;
+        ta.snap_x_src = snap->x_src;
+        ta.snap_x_build = snap->x_build;
+        ta.snap_box_build = snap->box_build;
+        ta.snap_slots = snap->slots;
+    }
     launch_build_tiles<Real>(ta, stream);
 }
 

@@ -1,15 +1,15 @@
 // Host orchestration of the nonbonded potentials: Hilbert sort cadence, gather, device-side rebuild decision,
-// tile kernel, scatter.  Reference: nonbonded_all_pairs.cu:21-313, nonbonded_interaction_group.cu:20-386,
+// tile kernel.  Reference: nonbonded_all_pairs.cu:21-313, nonbonded_interaction_group.cu:20-386,
 // nonbonded_pair_list.cu:12-121, nonbonded_common.cpp:45-63.
 //
 // One evaluation enqueues (no host synchronisation anywhere):
 //   [every steps_per_sort-th call: hilbert keys + radix sort -> perm, force rebuild]
 //   k_nb_prepare      gather/cast into packed sorted working set, decide rebuild (device flag)
-//   k_block_bounds    } all three return immediately
-//   k_reset/k_build   } unless the
-//   k_snapshot_if     } flag is set
-//   k_nb_tiles        the hot loop (also clears the rebuild flag)
-//   k_scatter_accum   sorted fixed-point accumulators -> caller's du_dx / du_dp (atomic), re-zeroed in passing
+//   k_block_bounds    } return immediately unless the flag is set (bounds also resets the tile counter and
+//   k_build_tiles     } snapshots the build coordinates)
+//   k_nb_tiles(_cq)   the hot loop: adds straight into the caller's atom-order du_dx / du_dp (slot -> atom through
+//                     perm when a tile is flushed; the reference's separate scatter pass does not exist) and clears
+//                     the rebuild flag
 #include "fixed_point.cuh"
 #include "potential.hpp"
 
@@ -53,13 +53,10 @@ NonbondedTiled<Real>::NonbondedTiled(
     int N, double beta, double cutoff, bool disable_hilbert, double nblist_padding, int steps_per_sort)
     : N_(N), beta_(beta), cutoff_(cutoff), nblist_padding_(nblist_padding), disable_hilbert_(disable_hilbert),
       steps_per_sort_(steps_per_sort), d_perm_(N), d_xw_(round_up(N, TILE)), d_qse_(round_up(N, TILE)),
-      d_acc_dx_(3 * static_cast<size_t>(round_up(N, TILE))), d_acc_dp_(4 * static_cast<size_t>(round_up(N, TILE))),
-      d_x_build_(static_cast<size_t>(N) * 3), d_box_build_(9), d_flags_(2),
+      d_x_build_(static_cast<size_t>(N) * 3), d_box_build_(9), d_flags_(3),
       d_partials_(nb_tiles_max_grid<Real>()), d_ticket_(1), nblist_(N) {
     d_xw_.zero();
     d_qse_.zero();
-    d_acc_dx_.zero();
-    d_acc_dp_.zero();
     d_x_build_.zero(); // nonsensical positions: the first evaluation always rebuilds anyway
     d_box_build_.zero();
     d_flags_.zero();
@@ -75,6 +72,12 @@ template <typename Real> void NonbondedTiled<Real>::du_dp_fixed_to_float(int N, 
 }
 
 template <typename Real> unsigned int NonbondedTiled<Real>::num_tiles() { return nblist_.num_tile_ixns(); }
+template <typename Real> unsigned int NonbondedTiled<Real>::num_rebuilds() {
+    TMB_CUDA(cudaDeviceSynchronize());
+    unsigned int n = 0;
+    TMB_CUDA(cudaMemcpy(&n, d_flags_.data + 2, sizeof(n), cudaMemcpyDeviceToHost));
+    return n;
+}
 
 template <typename Real> void NonbondedTiled<Real>::set_kernel_timing(bool on) {
     constexpr size_t CAPACITY = 4096;
@@ -105,6 +108,11 @@ template <typename Real>
 void NonbondedTiled<Real>::run(
     int N, const double *d_x, const double *d_p, const double *d_box, u64 *d_du_dx, u64 *d_du_dp, i128 *d_u,
     cudaStream_t stream) {
+    if (d_du_dx == nullptr && d_du_dp == nullptr && d_u == nullptr) {
+        // nothing requested: enqueue nothing.  (A prepare/build without the tile kernel that clears the rebuild flag
+        // would leave the flag raised and the next evaluation would append to a stale tile list.)
+        return;
+    }
     int force = force_rebuild_ ? 1 : 0;
     if (needs_sort()) {
         // a new permutation invalidates the tile list (reference nonbonded_all_pairs.cu:153-164)
@@ -127,10 +135,19 @@ void NonbondedTiled<Real>::run(
     pa.tile_cursor = d_flags_.data + 1;
     pa.xw = d_xw_.data;
     pa.qse = d_qse_.data;
+    // all-pairs layout (rows == columns == every gathered slot): block bounds, the counter reset and the build-time
+    // snapshot ride along with the gather and the build, the per-step chain is prepare -> build -> tiles
+    const bool fuse_bounds = (NR_ == K_);
+    if (fuse_bounds) {
+        pa.ctr = nblist_.col_ctr();
+        pa.ext = nblist_.col_ext();
+        pa.reset_count = nblist_.tiles().count;
+        pa.reset_overflow = nblist_.tiles().overflow;
+    }
     launch_nb_prepare<Real>(pa, stream);
 
     const unsigned int *flag = d_flags_.data;
-    typename Neighborlist<Real>::Snapshot snap{d_perm_.data, d_x, d_x_build_.data, d_box_build_.data};
+    typename Neighborlist<Real>::Snapshot snap{d_perm_.data, d_x, d_x_build_.data, d_box_build_.data, fuse_bounds, K_};
     nblist_.build_device(nullptr, d_xw_.data, d_box, cutoff_ + nblist_padding_, flag, stream, &snap);
     (void)N;
 
@@ -138,7 +155,6 @@ void NonbondedTiled<Real>::run(
     NbTileArgs<Real> ta;
     ta.K = K_;
     ta.NR = NR_;
-    ta.Kpad = Kpad();
     ta.tile_count = tl.count;
     ta.tile_rows = tl.rows;
     ta.tile_cols = tl.cols;
@@ -147,8 +163,9 @@ void NonbondedTiled<Real>::run(
     ta.box = d_box;
     ta.beta = beta_;
     ta.cutoff = cutoff_;
-    ta.acc_dx = d_acc_dx_.data;
-    ta.acc_dp = d_acc_dp_.data;
+    ta.perm = d_perm_.data;
+    ta.du_dx = d_du_dx;
+    ta.du_dp = d_du_dp;
     ta.u_partials = d_partials_.data;
     ta.ticket = d_ticket_.data;
     ta.d_u = d_u;
@@ -185,12 +202,6 @@ void NonbondedTiled<Real>::run(
         timing_used_++;
     }
 
-    if (d_du_dx) {
-        launch_scatter_accum(K_, Kpad(), 3, d_perm_.data, d_acc_dx_.data, d_du_dx, stream);
-    }
-    if (d_du_dp) {
-        launch_scatter_accum(K_, Kpad(), P_PER_ATOM, d_perm_.data, d_acc_dp_.data, d_du_dp, stream);
-    }
     steps_since_last_sort_++;
 }
 

@@ -210,7 +210,13 @@ public:
         const double *x_src;
         double *x_build;
         double *box_build;
+        // all-pairs layout only: column-block bounds were already written to col_ctr()/col_ext() and the tile counter
+        // reset by k_nb_prepare; the build kernel takes the snapshot itself and no bounds kernel is launched
+        bool bounds_done = false;
+        int slots = 0;
     };
+    Real *col_ctr() { return d_col_ctr_.data; }
+    Real *col_ext() { return d_col_ext_.data; }
     void build_device(const double *d_coords, const Vec4<Real> *d_xw, const double *d_box, double cutoff,
                       const unsigned int *flag, cudaStream_t stream, const Snapshot *snap = nullptr);
 
@@ -251,6 +257,7 @@ public:
     double get_cutoff() const { return cutoff_; }
     double get_nblist_padding() const { return nblist_padding_; }
     unsigned int num_tiles();
+    unsigned int num_rebuilds(); // neighbour-list builds since construction (device counter; synchronises)
 
 protected:
     const int N_;
@@ -267,7 +274,6 @@ protected:
 
     DeviceBuffer<unsigned int> d_perm_;
     DeviceBuffer<Vec4<Real>> d_xw_, d_qse_;
-    DeviceBuffer<u64> d_acc_dx_, d_acc_dp_;
     DeviceBuffer<double> d_x_build_, d_box_build_;
     DeviceBuffer<unsigned int> d_flags_;
     DeviceBuffer<i128> d_partials_;

@@ -283,6 +283,11 @@ class _TiledExtras:
         _check(_L.tmb_nonbonded_num_tiles(self._handle, C.byref(n)))
         return n.value
 
+    def get_num_rebuilds(self) -> int:
+        n = C.c_uint()
+        _check(_L.tmb_nonbonded_num_rebuilds(self._handle, C.byref(n)))
+        return n.value
+
     def set_kernel_timing(self, on: bool) -> None:
         _check(_L.tmb_nonbonded_set_kernel_timing(self._handle, int(bool(on))))
 
