@@ -455,13 +455,22 @@ def main():
             except Exception:
                 pass
         achieved = algo_bytes / t_kernel / 1e9
+        traffic, traffic_src = None, None
+        traffic_file = ROOT / "profiles" / "r1_nb_tiles_cq_traffic.json"
+        if traffic_file.exists():  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per launch
+            try:
+                tj = json.loads(traffic_file.read_text())
+                traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
+                traffic_src = tj["source"]
+            except Exception:
+                pass
         pair_slots = 1024.0 * T
         roofline = {
             "kernel": "k_nb_tiles_cq<U=0,X=1,P=0> (NonbondedAllPairs, env-env)", "bound": "hbm", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_us": t_kernel * 1e6,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_us": t_kernel * 1e6,
             "launches_timed": int(len(times_ms)), "tiles": int(T), "algorithmic_bytes": algo_bytes,
             "pair_slots_per_s": pair_slots / t_kernel,
-            "note": "the working set (tile list + 32 B/atom) is L2-resident; the kernel is FP32/SFU-issue bound, see DESIGN.md",
+            "note": "the working set (tile list + 32 B/atom) is L2-resident; the kernel is instruction-issue bound (ncu: issue slots 80 % busy, DRAM 45 GB/s), see DESIGN.md and profiles/r1_summary.md",
         }
 
     # ---------------- baselines on rank 0 ----------------------------------------------------------------------------------
