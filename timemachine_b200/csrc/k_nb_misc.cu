@@ -1,4 +1,4 @@
-// Gather/cast + device-side rebuild decision, build-time snapshot and small utilities.
+// Gather/cast + device-side rebuild decision and small utilities.
 #include "block_bounds.cuh"
 #include "fixed_point.cuh"
 #include "kernels.hpp"
@@ -44,12 +44,12 @@ template <typename Real> __global__ void __launch_bounds__(MISC_THREADS) k_nb_pr
         a.xw[k] = c;
         a.qse[k] = q;
 
-        const Real ox = static_cast<Real>(a.x_build[atom * 3 + 0]);
-        const Real oy = static_cast<Real>(a.x_build[atom * 3 + 1]);
-        const Real oz = static_cast<Real>(a.x_build[atom * 3 + 2]);
-        const Real dx = ox - c.x;
-        const Real dy = oy - c.y;
-        const Real dz = oz - c.z;
+        // the snapshot is kept in sorted order, already cast: one coalesced 16-byte load (a new permutation always
+        // forces a rebuild, so slot k holds the same atom as at build time whenever the comparison matters)
+        const Vec4<Real> o = a.xw_build[k];
+        const Real dx = o.x - c.x;
+        const Real dy = o.y - c.y;
+        const Real dz = o.z - c.z;
         const Real d2 = dx * dx + dy * dy + dz * dz;
         rebuild = rebuild || (static_cast<double>(d2) > 0.25 * a.padding * a.padding);
     }
@@ -69,7 +69,7 @@ template <typename Real> __global__ void __launch_bounds__(MISC_THREADS) k_nb_pr
             const Real by = static_cast<Real>(a.box[4]);
             const Real bz = static_cast<Real>(a.box[8]);
             Real ctr[3], ext[3];
-            warp_block_bounds<Real>(c.x, c.y, c.z, a.K - block * WARP, bx, by, bz, 1 / bx, 1 / by, 1 / bz, ctr, ext);
+            warp_block_bounds_anchor<Real>(c.x, c.y, c.z, a.K - block * WARP, bx, by, bz, 1 / bx, 1 / by, 1 / bz, ctr, ext);
             if ((threadIdx.x & 31) == 0) {
                 for (int d = 0; d < 3; d++) {
                     a.ctr[block * 3 + d] = ctr[d];
@@ -86,32 +86,6 @@ template <typename Real> void launch_nb_prepare(const NbPrepareArgs<Real> &args,
 }
 template void launch_nb_prepare<float>(const NbPrepareArgs<float> &, cudaStream_t);
 template void launch_nb_prepare<double>(const NbPrepareArgs<double> &, cudaStream_t);
-
-__global__ void __launch_bounds__(MISC_THREADS) k_snapshot_if(
-    const unsigned int *__restrict__ flag,
-    const int n,
-    const double *__restrict__ x,
-    double *__restrict__ x_build,
-    const double *__restrict__ box,
-    double *__restrict__ box_build) {
-    if (*flag == 0) {
-        return;
-    }
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        x_build[i] = x[i];
-    }
-    if (i < 9) {
-        box_build[i] = box[i];
-    }
-}
-
-void launch_snapshot_if(
-    const unsigned int *flag, int n_doubles, const double *x, double *x_build, const double *box, double *box_build,
-    cudaStream_t stream) {
-    const int n = n_doubles > 9 ? n_doubles : 9;
-    TMB_LAUNCH(k_snapshot_if, ceil_div(n, MISC_THREADS), MISC_THREADS, 0, stream, flag, n_doubles, x, x_build, box, box_build);
-}
 
 // single-CTA int128 sum (used by Summed/Fanout potentials over a handful of child energies)
 __global__ void __launch_bounds__(256) k_sum_i128(const i128 *__restrict__ in, const int n, i128 *__restrict__ out) {

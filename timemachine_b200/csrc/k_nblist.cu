@@ -68,12 +68,9 @@ template <typename Real> __global__ void __launch_bounds__(BB_THREADS) k_block_b
     if (valid) {
         const unsigned int atom = a.idxs != nullptr ? a.idxs[i] : static_cast<unsigned int>(a.base + i);
         load_pos<Real>(a.coords, a.xw, atom, px, py, pz);
-        if (a.x_build != nullptr) {
-            // remember where this atom was when the list was built (reference nonbonded_all_pairs.cu:241-242)
-            const size_t src = static_cast<size_t>(a.perm[atom]) * 3;
-            a.x_build[src + 0] = a.x_src[src + 0];
-            a.x_build[src + 1] = a.x_src[src + 1];
-            a.x_build[src + 2] = a.x_src[src + 2];
+        if (a.xw_build != nullptr) {
+            // remember where this slot's atom was when the list was built (reference nonbonded_all_pairs.cu:241-242)
+            a.xw_build[atom] = a.xw[atom];
         }
     }
     Real ctr[3], ext[3];
@@ -181,15 +178,12 @@ template <typename Real, bool TRI> __global__ void __launch_bounds__(BT_THREADS)
     if (a.flag != nullptr && *a.flag == 0) {
         return;
     }
-    if (a.snap_x_build != nullptr) {
+    if (a.snap_xw_build != nullptr) {
         // remember where every atom was when the list was built (reference nonbonded_all_pairs.cu:241-242)
         const int n_threads = gridDim.x * gridDim.y * BT_THREADS;
         const int tid = (blockIdx.y * gridDim.x + blockIdx.x) * BT_THREADS + threadIdx.x;
         for (int k = tid; k < a.snap_slots; k += n_threads) {
-            const size_t src = static_cast<size_t>(a.snap_perm[k]) * 3;
-            a.snap_x_build[src + 0] = a.snap_x_src[src + 0];
-            a.snap_x_build[src + 1] = a.snap_x_src[src + 1];
-            a.snap_x_build[src + 2] = a.snap_x_src[src + 2];
+            a.snap_xw_build[k] = a.xw[k];
         }
         if (tid < 9) {
             a.snap_box_build[tid] = a.box[tid];

@@ -54,7 +54,7 @@ template <typename Real> struct NbPrepareArgs {
     const double *x;          // [N,3]
     const double *p;          // [N,4]
     const double *box;        // [9]
-    const double *x_build;    // [N,3] coordinates at the last neighbour-list build
+    const Vec4<Real> *xw_build; // [K] sorted-order packed coordinates at the last neighbour-list build
     const double *box_build;  // [9]
     double padding;
     int force_rebuild;        // host-known (after a sort / set_atom_idxs)
@@ -72,11 +72,6 @@ template <typename Real> struct NbPrepareArgs {
 };
 template <typename Real> void launch_nb_prepare(const NbPrepareArgs<Real> &args, cudaStream_t stream);
 
-// Snapshot coordinates/box at build time, only if the rebuild flag is set.
-void launch_snapshot_if(
-    const unsigned int *flag, int n_doubles, const double *x, double *x_build, const double *box, double *box_build,
-    cudaStream_t stream);
-
 // ---------------------------------------------------------------------------------------------------------------
 // Neighbour list (reference k_neighborlist.cuh)
 template <typename Real> struct BlockBoundsArgs {
@@ -93,9 +88,7 @@ template <typename Real> struct BlockBoundsArgs {
     // Fused bookkeeping of a (re)build, all optional:
     unsigned int *reset_count;    // tile counter and
     unsigned int *reset_overflow; //   overflow flag to clear before the tile build
-    const unsigned int *perm;     // snapshot: x_build[perm[slot]] = x_src[perm[slot]] for every slot this launch covers
-    const double *x_src;
-    double *x_build;
+    Vec4<Real> *xw_build;         // snapshot: xw_build[slot] = xw[slot] for every slot this launch covers
     double *box_build; // box_build = box
 };
 template <typename Real> void launch_block_bounds(const BlockBoundsArgs<Real> &args, cudaStream_t stream);
@@ -117,10 +110,8 @@ template <typename Real> struct BuildTilesArgs {
     TileList tiles;
     const unsigned int *flag; // nullable: skip all work when *flag == 0
     // Optional "state at build time" snapshot taken by the build itself (when the bounds pass was fused into
-    // k_nb_prepare): x_build[perm[k]] = x_src[perm[k]] for k < snap_slots, box_build = box.
-    const unsigned int *snap_perm = nullptr;
-    const double *snap_x_src = nullptr;
-    double *snap_x_build = nullptr;
+    // k_nb_prepare): xw_build[k] = xw[k] for k < snap_slots, box_build = box.
+    Vec4<Real> *snap_xw_build = nullptr;
     double *snap_box_build = nullptr;
     int snap_slots = 0;
 };

@@ -187,10 +187,8 @@ void Neighborlist<Real>::build_device(
     // the first bounds launch also clears the tile counter and snapshots the build-time state
     ba.reset_count = tiles_.count;
     ba.reset_overflow = tiles_.overflow;
-    const bool can_snapshot = snap != nullptr && contiguous_;
-    ba.perm = can_snapshot ? snap->perm : nullptr;
-    ba.x_src = can_snapshot ? snap->x_src : nullptr;
-    ba.x_build = can_snapshot ? snap->x_build : nullptr;
+    const bool can_snapshot = snap != nullptr && contiguous_ && d_xw != nullptr;
+    ba.xw_build = can_snapshot ? snap->xw_build : nullptr;
     ba.box_build = can_snapshot ? snap->box_build : nullptr;
     if (!fused) {
         launch_block_bounds<Real>(ba, stream);
@@ -228,9 +226,7 @@ void Neighborlist<Real>::build_device(
     ta.tiles = tiles_;
     ta.flag = flag;
     if (fused) {
-        ta.snap_perm = snap->perm;
-        ta.snap_x_src = snap->x_src;
-        ta.snap_x_build = snap->x_build;
+        ta.snap_xw_build = snap->xw_build;
         ta.snap_box_build = snap->box_build;
         ta.snap_slots = snap->slots;
     }
@@ -293,9 +289,7 @@ void Neighborlist<Real>::compute_block_bounds_host(
     ba.flag = nullptr;
     ba.reset_count = nullptr;
     ba.reset_overflow = nullptr;
-    ba.perm = nullptr;
-    ba.x_src = nullptr;
-    ba.x_build = nullptr;
+    ba.xw_build = nullptr;
     ba.box_build = nullptr;
     launch_block_bounds<Real>(ba, stream);
     TMB_CUDA(cudaStreamSynchronize(stream));

@@ -53,11 +53,11 @@ NonbondedTiled<Real>::NonbondedTiled(
     int N, double beta, double cutoff, bool disable_hilbert, double nblist_padding, int steps_per_sort)
     : N_(N), beta_(beta), cutoff_(cutoff), nblist_padding_(nblist_padding), disable_hilbert_(disable_hilbert),
       steps_per_sort_(steps_per_sort), d_perm_(N), d_xw_(round_up(N, TILE)), d_qse_(round_up(N, TILE)),
-      d_x_build_(static_cast<size_t>(N) * 3), d_box_build_(9), d_flags_(3),
+      d_xw_build_(round_up(N, TILE)), d_box_build_(9), d_flags_(3),
       d_partials_(nb_tiles_max_grid<Real>()), d_ticket_(1), nblist_(N) {
     d_xw_.zero();
     d_qse_.zero();
-    d_x_build_.zero(); // nonsensical positions: the first evaluation always rebuilds anyway
+    d_xw_build_.zero(); // nonsensical positions: the first evaluation always rebuilds anyway
     d_box_build_.zero();
     d_flags_.zero();
     d_ticket_.zero();
@@ -127,7 +127,7 @@ void NonbondedTiled<Real>::run(
     pa.x = d_x;
     pa.p = d_p;
     pa.box = d_box;
-    pa.x_build = d_x_build_.data;
+    pa.xw_build = d_xw_build_.data;
     pa.box_build = d_box_build_.data;
     pa.padding = nblist_padding_;
     pa.force_rebuild = force;
@@ -147,7 +147,7 @@ void NonbondedTiled<Real>::run(
     launch_nb_prepare<Real>(pa, stream);
 
     const unsigned int *flag = d_flags_.data;
-    typename Neighborlist<Real>::Snapshot snap{d_perm_.data, d_x, d_x_build_.data, d_box_build_.data, fuse_bounds, K_};
+    typename Neighborlist<Real>::Snapshot snap{d_xw_build_.data, d_box_build_.data, fuse_bounds, K_};
     nblist_.build_device(nullptr, d_xw_.data, d_box, cutoff_ + nblist_padding_, flag, stream, &snap);
     (void)N;
 

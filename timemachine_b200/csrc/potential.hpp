@@ -206,9 +206,7 @@ public:
     // Enqueue bounds + tile build.  Exactly one of d_coords / d_xw is given; `flag` (nullable) gates all work on
     // the device.
     struct Snapshot { // where to record "coordinates/box at build time" (fused into the bounds kernel)
-        const unsigned int *perm;
-        const double *x_src;
-        double *x_build;
+        Vec4<Real> *xw_build; // sorted-order packed coordinates at build time
         double *box_build;
         // all-pairs layout only: column-block bounds were already written to col_ctr()/col_ext() and the tile counter
         // reset by k_nb_prepare; the build kernel takes the snapshot itself and no bounds kernel is launched
@@ -274,7 +272,8 @@ protected:
 
     DeviceBuffer<unsigned int> d_perm_;
     DeviceBuffer<Vec4<Real>> d_xw_, d_qse_;
-    DeviceBuffer<double> d_x_build_, d_box_build_;
+    DeviceBuffer<Vec4<Real>> d_xw_build_;
+    DeviceBuffer<double> d_box_build_;
     DeviceBuffer<unsigned int> d_flags_;
     DeviceBuffer<i128> d_partials_;
     DeviceBuffer<unsigned int> d_ticket_;
