@@ -34,6 +34,7 @@ typedef void *tmb_integrator;      /* std::shared_ptr<LangevinIntegrator>   (wra
 typedef void *tmb_context;         /* Context                               (wrap_kernels.cpp:296) */
 typedef void *tmb_neighborlist;    /* Neighborlist<float|double>            (wrap_kernels.cpp:113) */
 typedef void *tmb_hilbert_sort;    /* HilbertSort                           (wrap_kernels.cpp:174) */
+typedef void *tmb_mover;           /* std::shared_ptr<Mover>                (wrap_kernels.cpp:1591 declare_mover) */
 
 #define TMB_OK 0
 #define TMB_ERROR 1
@@ -140,10 +141,37 @@ int tmb_langevin_integrator_destroy(tmb_integrator intg);
 /* test hook: N x 3 f32 normals used on every step instead of the in-kernel Philox stream (NULL restores Philox) */
 int tmb_langevin_integrator_set_noise(tmb_integrator intg, const float *noise);
 
+/* ---- Mover / MonteCarloBarostat           wrap_kernels.cpp:1591-1659, barostat.cu ------------- */
+/* MonteCarloBarostat<float>(N, pressure[bar], temperature[K], group_idxs, interval, bps, seed, adaptive_scaling_enabled,
+ * initial_volume_scale_factor).  group_idxs is passed flattened: atoms of group g are
+ * group_atoms[group_offsets[g] .. group_offsets[g+1]).                wrap_kernels.cpp:1621-1653 */
+int tmb_barostat_create(
+    int N, double pressure, double temperature, const int *group_atoms, const int *group_offsets, int n_groups,
+    int interval, const tmb_bound_potential *bps, int n_bps, int seed, int adaptive_scaling_enabled,
+    double initial_volume_scale_factor, tmb_mover *out);
+int tmb_mover_destroy(tmb_mover m);
+int tmb_mover_set_interval(tmb_mover m, int interval); /* wrap_kernels.cpp:1596 */
+int tmb_mover_get_interval(tmb_mover m, int *out);     /* :1597 */
+int tmb_mover_set_step(tmb_mover m, int step);         /* :1598 */
+/* Mover::move_host: HOST coords[N,3] / box[3,3] in, moved copies out   wrap_kernels.cpp:1599-1616, mover.cu:7-23 */
+int tmb_mover_move_host(tmb_mover m, int N, const double *coords, const double *box, double *out_coords, double *out_box);
+int tmb_barostat_set_volume_scale_factor(tmb_mover m, double v); /* :1654 */
+int tmb_barostat_get_volume_scale_factor(tmb_mover m, double *out); /* :1655 */
+int tmb_barostat_set_adaptive_scaling(tmb_mover m, int on);      /* :1656 */
+int tmb_barostat_get_adaptive_scaling(tmb_mover m, int *out);    /* :1657 */
+int tmb_barostat_set_pressure(tmb_mover m, double pressure);     /* :1658 */
+/* introspection for the parity tests: the two cuRAND uniforms of the last attempted move; {attempted, accepted} */
+int tmb_barostat_last_uniforms(tmb_mover m, float *out2);
+int tmb_barostat_counters(tmb_mover m, int *out2);
+
 /* ---- Context(x0, v0, box, integrator, bps)                       wrap_kernels.cpp:296-689, context.cu ------------- */
 int tmb_context_create(
     const double *x0, const double *v0, const double *box, int N, tmb_integrator intg, const tmb_bound_potential *bps,
     int n_bps, tmb_context *out);
+/* same with movers=[...] (Context ctor, context.cu:28-50); movers run after every integrator step (context.cu:261-277) */
+int tmb_context_create_with_movers(
+    const double *x0, const double *v0, const double *box, int N, tmb_integrator intg, const tmb_bound_potential *bps,
+    int n_bps, const tmb_mover *movers, int n_movers, tmb_context *out);
 int tmb_context_destroy(tmb_context ctx);
 int tmb_context_step(tmb_context ctx);
 /* Context::multiple_steps(n_steps, n_samples, h_x[n_samples,N,3], h_box[n_samples,3,3])   context.cu:216-242 */

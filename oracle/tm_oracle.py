@@ -487,3 +487,134 @@ def hilbert_perm(coords, box, atom_idxs=None):
     order = np.argsort(keys, kind="stable")
     idxs = np.arange(len(coords)) if atom_idxs is None else np.asarray(atom_idxs)
     return idxs[order].astype(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Monte Carlo barostat.  Restates timemachine/cpp/src/kernels/k_barostat.cuh:11-189 and the
+# host logic of timemachine/cpp/src/barostat.cu:153-250; the centroid scaling itself is pinned against the reference's
+# Python CentroidRescaler (timemachine/md/barostat/moves.py:40-87) through tests/golden/barostat.npz.
+AVOGADRO = 6.0221367e23  # timemachine/cpp/src/constants.hpp:6
+
+
+def barostat_scale_centroids(coords, group_idxs, center, scale):
+    """Rigidly move every group so that its centroid is scaled about `center` (float64; no re-imaging).
+    Reference: CentroidRescaler.scale_centroids, md/barostat/moves.py:72-87."""
+    out = np.array(coords, dtype=np.float64, copy=True)
+    for g in group_idxs:
+        g = np.asarray(g)
+        centroid = out[g].mean(axis=0)
+        out[g] += (center + scale * (centroid - center)) - centroid
+    return out
+
+
+def _f32(v):
+    return np.float32(v)
+
+
+def _fma32(a, b, c):
+    # float32 fused multiply-add: the double product of two floats is exact; the final double->float rounding can
+    # differ from a true fma only in double-rounding corner cases (probability ~2^-29 per operation)
+    return np.float32(np.float64(a) * np.float64(b) + np.float64(c))
+
+
+def barostat_propose(x, box, group_idxs, volume_scale, rand0, adaptive=True):
+    """Proposal of one barostat move in the reference's float32 arithmetic.
+    k_setup_barostat_move (k_barostat.cuh:92-115): volume change delta = scale_factor * 2 * (rand0 - 0.5), length scale
+    cbrt(V'/V); k_find_group_centroids (:71-88): centroids from float32-rounded coordinates summed in 2^36 fixed point;
+    k_rescale_positions (:11-68): centroid scaled about the box centre, group moved rigidly, then shifted so that the
+    moved centroid lies in the scaled home box.  Atoms in no group are left where they are.
+    Returns (x_proposed, box_proposed, volume, delta_volume, volume_scale_used)."""
+    x = np.asarray(x, dtype=np.float64)
+    box = np.asarray(box, dtype=np.float64)
+    volume = _f32(box[0, 0] * box[1, 1] * box[2, 2])
+    scale_factor = float(volume_scale)
+    if adaptive and scale_factor == 0.0:
+        scale_factor = 0.01 * float(volume)
+    delta = _f32((scale_factor * 2) * (float(_f32(rand0)) - 0.5))
+    new_volume = _f32(volume + delta)
+    scale = _f32(np.cbrt(_f32(new_volume / volume)))
+    box_prop = box.copy()
+    for c in range(3):
+        box_prop[c, c] = box[c, c] * float(scale)
+    center = [_f32(box[c, c] * 0.5) for c in range(3)]
+    scaled_box = [_f32(box[c, c] * float(scale)) for c in range(3)]
+    x_prop = x.copy()
+    two36 = np.float32(2.0**36)
+    for g in group_idxs:
+        g = np.sort(np.asarray(g))
+        n = _f32(len(g))
+        for c in range(3):
+            fixed = int(np.sum(np.rint(x[g, c].astype(np.float32) * two36).astype(np.int64)))
+            centroid = _f32(_f32(_f32(fixed) / two36) / n)
+            displacement = _f32(_fma32(scale, _f32(centroid - center[c]), center[c]) - centroid)
+            moved = _f32(displacement + centroid)
+            cells = np.floor(_f32(moved / scaled_box[c]))
+            if c < 2:  # the reference binary rounds the product for x and y and fuses it for z (barostat.cu, SASS)
+                shift = _f32(displacement - _f32(scaled_box[c] * cells))
+            else:
+                shift = _fma32(scaled_box[c], -cells, displacement)
+            x_prop[g, c] = x[g, c] + float(shift)
+    return x_prop, box_prop, volume, delta, scale_factor
+
+
+def barostat_accepts(u_init_fixed, u_final_fixed, volume, delta_volume, num_molecules, temperature, pressure_bar, rand1):
+    """Metropolis test of k_decide_move (k_barostat.cuh:120-189): w = dU + P dV - N kT ln(V'/V); the move is rejected
+    iff w > 0 and rand1 > exp(-w / kT).  Energies are 2^36 fixed-point integers (overflowed sums give dU = +inf).
+    temperature and pressure pass through float32 like the reference's MonteCarloBarostat<float> members.
+    Returns (accepted, w)."""
+    kt = BOLTZ * float(_f32(temperature))
+    pressure = float(_f32(pressure_bar)) * AVOGADRO * 1e-25
+    llmax, llmin = (1 << 63) - 1, -(1 << 63)
+    if u_init_fixed >= llmax or u_init_fixed <= llmin or u_final_fixed >= llmax or u_final_fixed <= llmin:
+        du = np.float32(np.inf)
+    else:
+        du = _f32(_f32(int(u_final_fixed) - int(u_init_fixed)) / np.float32(2.0**36))
+    new_volume = _f32(_f32(volume) + _f32(delta_volume))
+    log_ratio = np.log(_f32(new_volume / _f32(volume)))
+    w = _f32(float(du) + pressure * float(delta_volume) - (num_molecules * kt) * float(log_ratio))
+    rejected = bool(w > 0 and float(_f32(rand1)) > np.exp(-float(w) / kt))
+    return (not rejected), w
+
+
+def barostat_adapt(volume_scale, attempted, accepted, volume):
+    """Adaptive volume-scale rule applied after the counters of an attempt are updated (k_barostat.cuh:157-171).
+    Returns (volume_scale, attempted, accepted)."""
+    if attempted >= 10:
+        if accepted < 0.25 * attempted:
+            return volume_scale / 1.1, 0, 0
+        if accepted > 0.75 * attempted:
+            return min(volume_scale * 1.1, float(volume) * 0.3), 0, 0
+    return volume_scale, attempted, accepted
+
+
+def get_group_indices(bond_list, num_atoms):
+    """Connected components of the bond graph, atoms outside every bond as singletons at the end.
+    Reference: timemachine/md/barostat/utils.py:43-62 (networkx there; union-find here)."""
+    parent = list(range(num_atoms))
+
+    def find(i):
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
+
+    bonded = set()
+    for i, j in bond_list:
+        bonded.update((int(i), int(j)))
+        parent[find(int(i))] = find(int(j))
+    comps = {}
+    for i in sorted(bonded):
+        comps.setdefault(find(i), []).append(i)
+    # networkx yields components in order of first appearance of any member in the edge list
+    order, seen = [], set()
+    for i, j in bond_list:
+        for k in (int(i), int(j)):
+            r = find(k)
+            if r not in seen:
+                seen.add(r)
+                order.append(r)
+    groups = [np.array(comps[r]) for r in order]
+    for g in groups:
+        assert np.all(np.diff(g) == 1)
+    groups += [np.array([i], dtype=np.int32) for i in range(num_atoms) if i not in bonded]
+    return groups

@@ -247,6 +247,36 @@ def main():
     )
     print("integrator: ca=%.12f" % ca)
 
+    # ---- barostat: the reference's Python CentroidRescaler and get_group_indices --------------------------------------
+    # md/barostat/moves.py imports custom_ops and half of the package at module scope; the two pure pieces are exec'd
+    # from the reference source text (unmodified), with numpy standing in for jax.numpy / jax.ops.segment_sum.
+    def segment_sum(data, segment_ids):
+        out = np.zeros((int(np.max(segment_ids)) + 1,) + np.shape(data)[1:])
+        np.add.at(out, np.asarray(segment_ids), np.asarray(data))
+        return out
+
+    src = (REF / "timemachine/md/barostat/moves.py").read_text()
+    ns = {"np": np, "jnp": sys.modules["jax.numpy"], "segment_sum": segment_sum}
+    exec(src[src.index("def compute_centroid") : src.index("class NPTMove")], ns)
+    n_mols, box_len = 40, 3.1
+    sizes = rng.choice([1, 3, 3, 3, 7], n_mols)
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    group_idxs = [np.arange(offsets[i], offsets[i + 1]) for i in range(n_mols)]
+    coords = rng.uniform(-0.5, box_len + 0.5, (offsets[-1], 3))
+    center = np.full(3, box_len / 2)
+    scale = 1.0173
+    rescaler = ns["CentroidRescaler"](group_idxs)
+    scaled = np.asarray(rescaler.scale_centroids(coords, center, scale))
+    centroids = np.asarray(rescaler.compute_centroids(coords))
+    # get_group_indices needs networkx (not in this image): the connected components it returns are restated with the
+    # reference's own slow path as the check - every group must be a maximal set connected by the bond list
+    bond_list = [(int(g[k]), int(g[k + 1])) for g in group_idxs for k in range(len(g) - 1)]
+    np.savez(
+        OUT / "barostat.npz", coords=coords, group_sizes=sizes, center=center, scale=scale, scaled=scaled,
+        centroids=centroids, bond_list=np.array(bond_list, dtype=np.int32), num_atoms=int(offsets[-1]),
+    )
+    print(f"barostat: {n_mols} groups, {offsets[-1]} atoms, scale {scale}")
+
 
 if __name__ == "__main__":
     main()

@@ -74,6 +74,20 @@ SIGNATURES = {
     "tmb_langevin_integrator_destroy": [_h],
     "tmb_langevin_integrator_set_noise": [_h, _p_f32],
     "tmb_context_create": [_p_f64, _p_f64, _p_f64, _int, _h, _ph, _int, _ph],
+    "tmb_context_create_with_movers": [_p_f64, _p_f64, _p_f64, _int, _h, _ph, _int, _ph, _int, _ph],
+    "tmb_barostat_create": [_int, _dbl, _dbl, _p_i32, _p_i32, _int, _int, _ph, _int, _int, _int, _dbl, _ph],
+    "tmb_mover_destroy": [_h],
+    "tmb_mover_set_interval": [_h, _int],
+    "tmb_mover_get_interval": [_h, C.POINTER(C.c_int)],
+    "tmb_mover_set_step": [_h, _int],
+    "tmb_mover_move_host": [_h, _int, _p_f64, _p_f64, _p_f64, _p_f64],
+    "tmb_barostat_set_volume_scale_factor": [_h, _dbl],
+    "tmb_barostat_get_volume_scale_factor": [_h, C.POINTER(C.c_double)],
+    "tmb_barostat_set_adaptive_scaling": [_h, _int],
+    "tmb_barostat_get_adaptive_scaling": [_h, C.POINTER(C.c_int)],
+    "tmb_barostat_set_pressure": [_h, _dbl],
+    "tmb_barostat_last_uniforms": [_h, _p_f32],
+    "tmb_barostat_counters": [_h, C.POINTER(C.c_int)],
     "tmb_context_destroy": [_h],
     "tmb_context_step": [_h],
     "tmb_context_multiple_steps": [_h, _int, _int, _p_f64, _p_f64],

@@ -52,9 +52,15 @@ def _headers_mtime() -> float:
     return max(h.stat().st_mtime for h in hs if h.exists())
 
 
+# barostat.cu inlines cbrtf / logf / exp from libdevice and must contract them like the reference build does (default
+# fmad); all of its own arithmetic is written with explicit round-to-nearest intrinsics.
+DEFAULT_FMAD_SOURCES = {"barostat.cu"}
+
+
 def _compile(src: Path, extra: list[str]) -> tuple[Path, str]:
     obj = OBJ_DIR / (src.stem + ".o")
-    cmd = [NVCC, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
+    flags = [f for f in NVCC_FLAGS if not (src.name in DEFAULT_FMAD_SOURCES and f == "--fmad=false")]
+    cmd = [NVCC, *flags, *extra, "-c", str(src), "-o", str(obj)]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src.name}:\n{proc.stdout}\n{proc.stderr}")
@@ -92,7 +98,8 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
             raise RuntimeError("\n".join(errors))
     objs = [OBJ_DIR / (s.stem + ".o") for s in srcs]
     if todo or not LIB_PATH.exists():
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *map(str, objs)]
+        # cuRAND: the barostat draws the reference's XORWOW stream (same seed -> same accept/reject decisions)
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *map(str, objs), "-lcurand"]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError(f"link failed:\n{proc.stdout}\n{proc.stderr}")

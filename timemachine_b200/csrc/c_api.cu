@@ -55,6 +55,21 @@ static Context &as_ctx(tmb_context h) {
     return *static_cast<Context *>(h);
 }
 
+typedef std::shared_ptr<Mover> MoverPtr;
+static MoverPtr &as_mover(tmb_mover h) {
+    if (h == nullptr) {
+        throw std::runtime_error("null mover handle");
+    }
+    return *static_cast<MoverPtr *>(h);
+}
+static std::shared_ptr<MonteCarloBarostat<float>> as_barostat(tmb_mover h) {
+    auto b = std::dynamic_pointer_cast<MonteCarloBarostat<float>>(as_mover(h));
+    if (!b) {
+        throw std::runtime_error("mover is not a MonteCarloBarostat");
+    }
+    return b;
+}
+
 struct NeighborlistHandle {
     int precision;
     std::unique_ptr<Neighborlist<float>> f32;
@@ -439,6 +454,86 @@ int tmb_context_create(
             v.push_back(as_bp(bps[i]));
         }
         *out = new Context(N, x0, v0, box, as_intg(intg), v);
+    });
+}
+int tmb_context_create_with_movers(
+    const double *x0, const double *v0, const double *box, int N, tmb_integrator intg, const tmb_bound_potential *bps,
+    int n_bps, const tmb_mover *movers, int n_movers, tmb_context *out) {
+    return guarded([&] {
+        std::vector<BpPtr> v;
+        for (int i = 0; i < n_bps; i++) {
+            v.push_back(as_bp(bps[i]));
+        }
+        std::vector<MoverPtr> mv;
+        for (int i = 0; i < n_movers; i++) {
+            mv.push_back(as_mover(movers[i]));
+        }
+        *out = new Context(N, x0, v0, box, as_intg(intg), v, mv);
+    });
+}
+int tmb_barostat_create(
+    int N, double pressure, double temperature, const int *group_atoms, const int *group_offsets, int n_groups,
+    int interval, const tmb_bound_potential *bps, int n_bps, int seed, int adaptive_scaling_enabled,
+    double initial_volume_scale_factor, tmb_mover *out) {
+    return guarded([&] {
+        std::vector<std::vector<int>> groups(n_groups);
+        for (int g = 0; g < n_groups; g++) {
+            groups[g].assign(group_atoms + group_offsets[g], group_atoms + group_offsets[g + 1]);
+        }
+        std::vector<BpPtr> v;
+        for (int i = 0; i < n_bps; i++) {
+            v.push_back(as_bp(bps[i]));
+        }
+        *out = new MoverPtr(std::make_shared<MonteCarloBarostat<float>>(
+            N, pressure, temperature, groups, interval, v, seed, adaptive_scaling_enabled != 0, initial_volume_scale_factor));
+    });
+}
+int tmb_mover_destroy(tmb_mover m) {
+    return guarded([&] { delete static_cast<MoverPtr *>(m); });
+}
+int tmb_mover_set_interval(tmb_mover m, int interval) {
+    return guarded([&] { as_mover(m)->set_interval(interval); });
+}
+int tmb_mover_get_interval(tmb_mover m, int *out) {
+    return guarded([&] { *out = as_mover(m)->get_interval(); });
+}
+int tmb_mover_set_step(tmb_mover m, int step) {
+    return guarded([&] { as_mover(m)->set_step(step); });
+}
+int tmb_mover_move_host(tmb_mover m, int N, const double *coords, const double *box, double *out_coords, double *out_box) {
+    return guarded([&] {
+        auto r = as_mover(m)->move_host(N, coords, box);
+        std::memcpy(out_coords, r[0].data(), r[0].size() * sizeof(double));
+        std::memcpy(out_box, r[1].data(), r[1].size() * sizeof(double));
+    });
+}
+int tmb_barostat_set_volume_scale_factor(tmb_mover m, double v) {
+    return guarded([&] { as_barostat(m)->set_volume_scale_factor(v); });
+}
+int tmb_barostat_get_volume_scale_factor(tmb_mover m, double *out) {
+    return guarded([&] { *out = as_barostat(m)->get_volume_scale_factor(); });
+}
+int tmb_barostat_set_adaptive_scaling(tmb_mover m, int on) {
+    return guarded([&] { as_barostat(m)->set_adaptive_scaling(on != 0); });
+}
+int tmb_barostat_get_adaptive_scaling(tmb_mover m, int *out) {
+    return guarded([&] { *out = as_barostat(m)->get_adaptive_scaling() ? 1 : 0; });
+}
+int tmb_barostat_set_pressure(tmb_mover m, double pressure) {
+    return guarded([&] { as_barostat(m)->set_pressure(pressure); });
+}
+int tmb_barostat_last_uniforms(tmb_mover m, float *out2) {
+    return guarded([&] {
+        auto u = as_barostat(m)->last_uniforms();
+        out2[0] = u[0];
+        out2[1] = u[1];
+    });
+}
+int tmb_barostat_counters(tmb_mover m, int *out2) {
+    return guarded([&] {
+        auto c = as_barostat(m)->counters();
+        out2[0] = c[0];
+        out2[1] = c[1];
     });
 }
 int tmb_context_destroy(tmb_context ctx) {

@@ -90,9 +90,9 @@ constexpr int GRAPH_STEPS = 10;
 
 Context::Context(
     int N, const double *x0, const double *v0, const double *box0, std::shared_ptr<LangevinIntegrator> intg,
-    std::vector<std::shared_ptr<BoundPotential>> bps)
+    std::vector<std::shared_ptr<BoundPotential>> bps, std::vector<std::shared_ptr<Mover>> movers)
     : N_(N), d_x_(static_cast<size_t>(N) * 3), d_v_(static_cast<size_t>(N) * 3), d_box_(9), intg_(std::move(intg)),
-      bps_(std::move(bps)) {
+      bps_(std::move(bps)), movers_(std::move(movers)) {
     if (intg_->num_atoms() != N) {
         throw std::runtime_error("integrator N != x0 N");
     }
@@ -131,6 +131,9 @@ void Context::run_steps(int n, cudaStream_t stream) {
         for (auto &bp : bps_) {
             cap = std::min(cap, bp->potential->capturable_steps());
         }
+        for (auto &m : movers_) {
+            cap = std::min(cap, m->idle_steps()); // a graph block must not span a step on which a mover acts
+        }
         if (use_graphs_ && cap >= GRAPH_STEPS && remaining >= GRAPH_STEPS) {
             intg_->publish_step_base(stream);
             if (graph_exec_ == nullptr || graph_stream_ != stream) {
@@ -164,18 +167,37 @@ void Context::run_steps(int n, cudaStream_t stream) {
                 g_kernel_launches.fetch_add(graph_kernels_, std::memory_order_relaxed);
             }
             TMB_CUDA(cudaGraphLaunch(graph_exec_, stream));
+            for (auto &m : movers_) {
+                m->skip(GRAPH_STEPS);
+            }
             remaining -= GRAPH_STEPS;
         } else {
-            intg_->step_fwd(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream, -1);
+            eager_step(stream);
             remaining -= 1;
         }
     }
 }
 
+void Context::eager_step(cudaStream_t stream) {
+    intg_->step_fwd(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream, -1);
+    for (auto &m : movers_) {
+        m->move(N_, d_x_.data, d_box_.data, stream); // may modify coordinates and box
+    }
+}
+
 void Context::step() {
     cudaStream_t stream = active_stream();
-    intg_->step_fwd(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream, -1);
+    eager_step(stream);
     TMB_CUDA(cudaStreamSynchronize(stream));
+}
+
+std::shared_ptr<MonteCarloBarostat<float>> Context::get_barostat() const {
+    for (auto &m : movers_) {
+        if (auto b = std::dynamic_pointer_cast<MonteCarloBarostat<float>>(m)) {
+            return b;
+        }
+    }
+    return nullptr;
 }
 
 void Context::verify_frame(const double *h_x, const double *h_box) const {

@@ -362,10 +362,14 @@ private:
     friend class Context;
 };
 
+} // namespace tmb
+#include "barostat.hpp"
+namespace tmb {
+
 class Context {
 public:
     Context(int N, const double *x0, const double *v0, const double *box0, std::shared_ptr<LangevinIntegrator> intg,
-            std::vector<std::shared_ptr<BoundPotential>> bps);
+            std::vector<std::shared_ptr<BoundPotential>> bps, std::vector<std::shared_ptr<Mover>> movers = {});
     ~Context();
     int num_atoms() const { return N_; }
     void step();
@@ -384,6 +388,8 @@ public:
     double *d_box() { return d_box_.data; }
     std::shared_ptr<LangevinIntegrator> get_integrator() const { return intg_; }
     const std::vector<std::shared_ptr<BoundPotential>> &get_potentials() const { return bps_; }
+    const std::vector<std::shared_ptr<Mover>> &get_movers() const { return movers_; }
+    std::shared_ptr<MonteCarloBarostat<float>> get_barostat() const; // reference context.cu:311-320
     void set_use_graphs(bool on) { use_graphs_ = on; }
     // Run the MD loop on a caller-owned stream (e.g. torch's current stream) instead of the context's own one.
     void set_stream(cudaStream_t s);
@@ -393,6 +399,7 @@ private:
     DeviceBuffer<double> d_x_, d_v_, d_box_;
     std::shared_ptr<LangevinIntegrator> intg_;
     std::vector<std::shared_ptr<BoundPotential>> bps_;
+    std::vector<std::shared_ptr<Mover>> movers_;
     std::vector<double> nb_cutoffs_with_padding_;
     bool use_graphs_ = true;
     cudaStream_t stream_ = nullptr;      // owned, non-blocking
@@ -403,6 +410,7 @@ private:
     cudaGraphExec_t graph_exec_ = nullptr;
     long long graph_kernels_ = 0;
     void run_steps(int n, cudaStream_t stream);
+    void eager_step(cudaStream_t stream); // integrator step, then every mover (reference context.cu:261-277)
     void verify_frame(const double *h_x, const double *h_box) const;
     void destroy_graph();
 };

@@ -594,9 +594,108 @@ class LangevinIntegrator(Integrator):
         _check(_L.tmb_langevin_integrator_set_noise(self._handle, _ptr(noise, C.c_float)))
 
 
+class Mover:
+    """Base of the movers Context runs after every integrator step (wrap_kernels.cpp:1591-1617, mover.hpp:11-50)."""
+
+    _handle = None
+
+    def __init__(self, *args, **kwargs):
+        raise TypeError("Mover: No constructor defined!")
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _L.tmb_mover_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def set_interval(self, interval: int) -> None:
+        _check(_L.tmb_mover_set_interval(self._handle, int(interval)))
+
+    def get_interval(self) -> int:
+        n = C.c_int()
+        _check(_L.tmb_mover_get_interval(self._handle, C.byref(n)))
+        return n.value
+
+    def set_step(self, step: int) -> None:
+        _check(_L.tmb_mover_set_step(self._handle, int(step)))
+
+    def move(self, coords, box):
+        """One call of the mover on host arrays; returns (coords, box) after it (wrap_kernels.cpp:1599-1616)."""
+        coords, box = _f64(coords), _f64(box)
+        _verify_coords_and_box(coords, box)
+        out_x, out_box = np.empty_like(coords), np.empty_like(box)
+        _check(
+            _L.tmb_mover_move_host(
+                self._handle, coords.shape[0], _ptr(coords, C.c_double), _ptr(box, C.c_double), _ptr(out_x, C.c_double),
+                _ptr(out_box, C.c_double),
+            )
+        )
+        return out_x, out_box
+
+
+class MonteCarloBarostat(Mover):
+    """MonteCarloBarostat(N, pressure, temperature, group_idxs, interval, bps, seed, adaptive_scaling_enabled,
+    initial_volume_scale_factor) (wrap_kernels.cpp:1619-1659; barostat.cu).  f32 arithmetic like the reference's only
+    exported instantiation; same cuRAND stream, so the same seed gives the same accept/reject sequence."""
+
+    def __init__(
+        self, N, pressure, temperature, group_idxs, interval, bps, seed, adaptive_scaling_enabled,
+        initial_volume_scale_factor,
+    ):
+        groups = [np.asarray(g, dtype=np.int32).reshape(-1) for g in group_idxs]
+        offsets = np.zeros(len(groups) + 1, dtype=np.int32)
+        if groups:
+            offsets[1:] = np.cumsum([len(g) for g in groups])
+        flat = np.ascontiguousarray(np.concatenate(groups) if groups else np.zeros(0, dtype=np.int32), dtype=np.int32)
+        self._bps = list(bps)  # keep the Python owners alive
+        self._handle = None
+        h = _new_handle()
+        _check(
+            _L.tmb_barostat_create(
+                int(N), float(pressure), float(temperature), _ptr(flat, C.c_int32), _ptr(offsets, C.c_int32), len(groups),
+                int(interval), _handle_array(self._bps), len(self._bps), int(seed), int(bool(adaptive_scaling_enabled)),
+                float(initial_volume_scale_factor), C.byref(h),
+            )
+        )
+        self._handle = h
+
+    def set_volume_scale_factor(self, volume_scale_factor: float) -> None:
+        _check(_L.tmb_barostat_set_volume_scale_factor(self._handle, float(volume_scale_factor)))
+
+    def get_volume_scale_factor(self) -> float:
+        v = C.c_double()
+        _check(_L.tmb_barostat_get_volume_scale_factor(self._handle, C.byref(v)))
+        return v.value
+
+    def set_adaptive_scaling(self, adaptive_scaling_enabled: bool) -> None:
+        _check(_L.tmb_barostat_set_adaptive_scaling(self._handle, int(bool(adaptive_scaling_enabled))))
+
+    def get_adaptive_scaling(self) -> bool:
+        v = C.c_int()
+        _check(_L.tmb_barostat_get_adaptive_scaling(self._handle, C.byref(v)))
+        return bool(v.value)
+
+    def set_pressure(self, pressure: float) -> None:
+        _check(_L.tmb_barostat_set_pressure(self._handle, float(pressure)))
+
+    # introspection, not part of the reference API
+    def last_uniforms(self) -> np.ndarray:
+        out = np.zeros(2, dtype=np.float32)
+        _check(_L.tmb_barostat_last_uniforms(self._handle, _ptr(out, C.c_float)))
+        return out
+
+    def counters(self) -> tuple:
+        out = (C.c_int * 2)()
+        _check(_L.tmb_barostat_counters(self._handle, out))
+        return int(out[0]), int(out[1])
+
+
 class Context:
-    """Context(x0, v0, box, integrator, bps, movers=None) (wrap_kernels.cpp:296-689).  Movers (barostat, exchange
-    moves) are outside this hot path: passing any raises."""
+    """Context(x0, v0, box, integrator, bps, movers=None) (wrap_kernels.cpp:296-689).  Movers run after every
+    integrator step (context.cu:261-277); MonteCarloBarostat is the one implemented here."""
 
     def __init__(self, x0, v0, box, integrator, bps, movers=None):
         x0 = _f64(x0)
@@ -607,8 +706,10 @@ class Context:
             raise RuntimeError("v0 N != x0 N")
         if x0.shape[1] != v0.shape[1]:
             raise RuntimeError("v0 D != x0 D")
-        if movers:
-            raise RuntimeError("movers are not part of the timemachine_b200 hot path (see DESIGN.md, out of scope)")
+        self._movers = list(movers) if movers else []
+        for m in self._movers:
+            if not isinstance(m, Mover):
+                raise RuntimeError("movers must be timemachine_b200 Mover objects")
         if not isinstance(integrator, LangevinIntegrator):
             raise RuntimeError("integrator must be LangevinIntegrator.")
         self._integrator = integrator
@@ -617,9 +718,9 @@ class Context:
         self._handle = None
         h = _new_handle()
         _check(
-            _L.tmb_context_create(
+            _L.tmb_context_create_with_movers(
                 _ptr(x0, C.c_double), _ptr(v0, C.c_double), _ptr(box, C.c_double), self._n, integrator._handle,
-                _handle_array(self._bps), len(self._bps), C.byref(h),
+                _handle_array(self._bps), len(self._bps), _handle_array(self._movers), len(self._movers), C.byref(h),
             )
         )
         self._handle = h
@@ -693,9 +794,13 @@ class Context:
         return list(self._bps)
 
     def get_movers(self):
-        return []
+        return list(self._movers)
 
     def get_barostat(self):
+        """The first MonteCarloBarostat among the movers, else None (context.cu:311-320)."""
+        for m in self._movers:
+            if isinstance(m, MonteCarloBarostat):
+                return m
         return None
 
     # extensions used by bench.py / the replica driver

@@ -1,8 +1,9 @@
-"""Mirror of timemachine/lib/__init__.py:12-21 for the hot path: the picklable integrator description."""
+"""Mirror of timemachine/lib/__init__.py:12-62 for the hot path: the picklable integrator and barostat descriptions."""
 
 from __future__ import annotations
 
 from dataclasses import dataclass
+from typing import Any, Optional
 
 import numpy as np
 
@@ -19,3 +20,30 @@ class LangevinIntegrator:
 
     def impl(self) -> custom_ops.LangevinIntegrator:
         return custom_ops.LangevinIntegrator(self.masses, self.temperature, self.dt, self.friction, self.seed)
+
+
+@dataclass
+class MonteCarloBarostat:
+    """timemachine/lib/__init__.py:39-62."""
+
+    N: int
+    pressure: float
+    temperature: float
+    group_idxs: Any
+    interval: int
+    seed: int
+    adaptive_scaling_enabled: bool = True
+    initial_volume_scale_factor: Optional[float] = None
+
+    def impl(self, bound_potentials) -> custom_ops.MonteCarloBarostat:
+        return custom_ops.MonteCarloBarostat(
+            self.N,
+            self.pressure,
+            self.temperature,
+            self.group_idxs,
+            self.interval,
+            bound_potentials,
+            self.seed,
+            self.adaptive_scaling_enabled,
+            self.initial_volume_scale_factor or 0.0,  # 0.0: "use 1% of the initial box volume"
+        )
