@@ -266,6 +266,66 @@ def cpu_arm(args, s, x0, v0, lam):
     return ns_day, dt_s, OC.num_threads(), n
 
 
+BAROSTAT_INTERVAL, PRESSURE_BAR = 25, 1.013
+
+
+def npt_arm(args, s, ops, impl, flat, x_eq, v_eq, dev, torch):
+    """Side measurement, not the headline metric: the same leg under NPT (MonteCarloBarostat every 25 steps, molecules =
+    waters + the ligand) with this repo's barostat, and with the compiled reference's where oracle/_ref is present."""
+    n_env = s["n_env"]
+    groups = [np.arange(i, i + 3, dtype=np.int32) for i in range(0, n_env, 3)] + [s["lig_idx"].astype(np.int32)]
+    reps = 3
+
+    def time_ctx(make):
+        ctx, baro = make()
+        ctx.multiple_steps(args.md_steps, args.md_steps + 1)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.multiple_steps(args.md_steps, args.md_steps + 1)
+        torch.cuda.synchronize(dev)
+        per_step = (time.perf_counter() - t0) / (reps * args.md_steps)
+        box = np.asarray(ctx.get_box())
+        return per_step, float(box[0, 0] * box[1, 1] * box[2, 2]), baro
+
+    def ours():
+        bp = ops.BoundPotential(impl, flat)
+        intg = ops.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 4321)
+        baro = ops.MonteCarloBarostat(s["N"], PRESSURE_BAR, TEMPERATURE, groups, BAROSTAT_INTERVAL, [bp], 99, True, 0.0)
+        return ops.Context(x_eq, v_eq, s["box"], intg, [bp], movers=[baro]), baro
+
+    out = {"barostat_interval": BAROSTAT_INTERVAL, "pressure_bar": PRESSURE_BAR, "unit": "ns/day",
+           "timing": f"wall clock around {reps} x {args.md_steps} steps, synchronised both sides"}
+    try:
+        t, vol, baro = time_ctx(ours)
+        out.update(value=86400.0 / t * DT * 1e-3, us_per_md_step=t * 1e6, final_volume_nm3=vol,
+                   attempted_accepted_since_last_adaptation=list(baro.counters()))
+    except Exception as e:
+        out["error"] = repr(e)[:200]
+        return out
+    if not args.no_ref_gpu:
+        try:
+            from tests.common import load_reference_ops
+
+            ref = load_reference_ops()
+            if ref is not None:
+                with stdout_to_stderr():
+
+                    def theirs():
+                        rbp = ref.BoundPotential(make_reference_potential(ref, s), flat)
+                        rintg = ref.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 4321)
+                        rbaro = ref.MonteCarloBarostat(
+                            s["N"], PRESSURE_BAR, TEMPERATURE, [g.tolist() for g in groups], BAROSTAT_INTERVAL, [rbp], 99, True, 0.0
+                        )
+                        return ref.Context(x_eq, v_eq, s["box"], rintg, [rbp], [rbaro]), rbaro
+
+                    rt, rvol, _ = time_ctx(theirs)
+                out["reference_gpu"] = {"value": 86400.0 / rt * DT * 1e-3, "us_per_md_step": rt * 1e6, "final_volume_nm3": rvol}
+        except Exception as e:
+            out["reference_gpu"] = {"unavailable": repr(e)[:200]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,6 +337,7 @@ def main():
     ap.add_argument("--ligand-atoms", type=int, default=60)
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the compiled reference custom_ops on the GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-npt", action="store_true", help="skip the NPT (barostat) side measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -508,6 +569,11 @@ def main():
             except Exception as e:  # the reference is a baseline, never a dependency
                 ref_gpu = {"unavailable": repr(e)[:200]}
 
+    # ---------------- NPT variant of the same leg: + MonteCarloBarostat every 25 steps ----------------
+    npt = None
+    if rank == 0 and world == 1 and not args.no_npt:
+        npt = npt_arm(args, s, ops, impl, flats[my_state], x_eq, v_eq, dev, torch)
+
     if rank == 0:
         out = {
             "metric": "ns_per_day", "value": ns_day, "unit": "ns/day", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -516,7 +582,7 @@ def main():
                                                 timing="CUDA events on the MD stream per bench step, summed; max over ranks"),
             "clocks": clocks, "gpu_launches": int(gpu_launches), "nblist_rebuilds": int(nblist_rebuilds), "md_steps_timed": int(args.md_steps * args.steps), "wall_s": wall,
             "e2e": {"value": e2e_ns_day, "unit": "ns/day", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": ref_gpu,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": ref_gpu, "npt": npt,
             "us_per_md_step": total_ms * 1e3 / (args.md_steps * args.steps),
         }
         print(json.dumps(out))
