@@ -59,6 +59,18 @@ int tmb_harmonic_bond_create(int precision, const int32_t *bond_idxs, int n_valu
 int tmb_harmonic_angle_create(int precision, const int32_t *angle_idxs, int n_values, tmb_potential *out);
 /* PeriodicTorsion_{f32,f64}(torsion_idxs i32[T,4])                 wrap_kernels.cpp:1432-1444 */
 int tmb_periodic_torsion_create(int precision, const int32_t *torsion_idxs, int n_values, tmb_potential *out);
+/* the rest of the HostGuestSystem potential set (fe/system.py:133-143)
+ * FlatBottomBond_{f32,f64}(bond_idxs[B,2])                          wrap_kernels.cpp:1324-1335, flat_bottom_bond.cu
+ * ChiralAtomRestraint_{f32,f64}(idxs[R,4])                          wrap_kernels.cpp:1366-1378, chiral_atom_restraint.cu
+ * ChiralBondRestraint_{f32,f64}(idxs[R,4], signs[R] in {1,-1})      wrap_kernels.cpp:1380-1394, chiral_bond_restraint.cu
+ * NonbondedPairListPrecomputed_{f32,f64}(pair_idxs[M,2], beta, cutoff); params [M,4] = (q_ij, sig_ij, eps_ij, w_ij)
+ *                                                                   wrap_kernels.cpp:1351-1364, nonbonded_precomputed.cu */
+int tmb_flat_bottom_bond_create(int precision, const int32_t *bond_idxs, int n_values, tmb_potential *out);
+int tmb_chiral_atom_restraint_create(int precision, const int32_t *idxs, int n_values, tmb_potential *out);
+int tmb_chiral_bond_restraint_create(
+    int precision, const int32_t *idxs, int n_values, const int32_t *signs, int n_signs, tmb_potential *out);
+int tmb_nonbonded_pair_list_precomputed_create(
+    int precision, const int32_t *pair_idxs, int n_values, double beta, double cutoff, tmb_potential *out);
 /* NonbondedAllPairs_*(num_atoms, beta, cutoff, atom_idxs|None, disable_hilbert_sort, nblist_padding)
  *                                                                  wrap_kernels.cpp:1446-1478 ; n_atom_idxs < 0 = None */
 int tmb_nonbonded_all_pairs_create(

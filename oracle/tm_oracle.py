@@ -618,3 +618,134 @@ def get_group_indices(bond_list, num_atoms):
         assert np.all(np.diff(g) == 1)
     groups += [np.array([i], dtype=np.int32) for i in range(num_atoms) if i not in bonded]
     return groups
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Restraints and the precomputed pair list.  Energies restate the reference's Python potentials
+# (timemachine/potentials/bonded.py:219-242 flat_bottom_bond; chiral_restraints.py:10-125; nonbonded.py:403-446
+# nonbonded_on_precomputed_pairs) and are pinned to them through tests/golden/restraints.npz; gradients are the
+# analytic forms of the kernels (k_flat_bottom_bond.cuh:137-170, chiral_utils.cuh:94-181,
+# k_nonbonded_precomputed.cuh:88-181), checked against finite differences of the pinned energies.
+def flat_bottom_bond(x, params, box, bond_idxs):
+    """u = k/4 (r - rmax)^4 for r > rmax, k/4 (r - rmin)^4 for r < rmin, minimum image.  Returns (u, du_dx, du_dp)."""
+    x = np.asarray(x, dtype=np.float64)
+    params = np.asarray(params, dtype=np.float64).reshape(-1, 3)
+    i, j = np.asarray(bond_idxs).reshape(-1, 2).T
+    d = delta_r(x[i], x[j], box)
+    r = np.linalg.norm(d, axis=1)
+    k, rmin, rmax = params.T
+    lo, hi = (r < rmin), (r > rmax)
+    dlo, dhi = r - rmin, r - rmax
+    u = np.sum(k / 4 * (lo * dlo**4 + hi * dhi**4))
+    du_dr = k * (lo * dlo**3 + hi * dhi**3)
+    g = (du_dr / r)[:, None] * d
+    du_dx = np.zeros_like(x)
+    np.add.at(du_dx, i, g)
+    np.add.at(du_dx, j, -g)
+    du_dp = np.stack([(lo * dlo**4 + hi * dhi**4) / 4, lo * (-k * dlo**3), hi * (-k * dhi**3)], axis=1)
+    return u, du_dx, du_dp
+
+
+def _unit_and_jac(v):
+    n = np.linalg.norm(v)
+    u = v / n
+    return u, (np.eye(3) - np.outer(u, u)) / n
+
+
+def _cross_jacs(a, b):
+    """Rows r: d(a x b)_r / da and / db."""
+    ja = np.array([[0, b[2], -b[1]], [-b[2], 0, b[0]], [b[1], -b[0], 0]])
+    jb = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return ja, jb
+
+
+def pyramidal_volume_and_grad(xc, x1, x2, x3):
+    """(x^ x y^) . z^ with x = x1 - xc etc.; gradients wrt (xc, x1, x2, x3)  (chiral_utils.cuh:94-137)."""
+    xx, yy, zz = x1 - xc, x2 - xc, x3 - xc
+    (x, jx), (y, jy), (z, jz) = _unit_and_jac(xx), _unit_and_jac(yy), _unit_and_jac(zz)
+    xy = np.cross(x, y)
+    ja, jb = _cross_jacs(x, y)
+    g1, g2, g3 = (z @ ja) @ jx, (z @ jb) @ jy, xy @ jz
+    return float(xy @ z), (-g1 - g2 - g3, g1, g2, g3)
+
+
+def torsion_volume_and_grad(x0, x1, x2, x3):
+    """(x^ x y^) . (y^ x z^) with x = x1 - x0, y = x1 - x2, z = x3 - x2  (chiral_utils.cuh:139-181)."""
+    xx, yy, zz = x1 - x0, x1 - x2, x3 - x2
+    (x, jx), (y, jy), (z, jz) = _unit_and_jac(xx), _unit_and_jac(yy), _unit_and_jac(zz)
+    xy, yz = np.cross(x, y), np.cross(y, z)
+    j0x, j0y = _cross_jacs(x, y)
+    j1y, j1z = _cross_jacs(y, z)
+    gx = (yz @ j0x) @ jx
+    gy = (yz @ j0y) @ jy + (xy @ j1y) @ jy
+    gz = (xy @ j1z) @ jz
+    return float(xy @ yz), (-gx, gx + gy, -gy - gz, gz)
+
+
+def chiral_atom_restraint(x, params, idxs):
+    """u = sum k vol^2 over restraints with vol > 0 (chiral_restraints.py:64-75,103-112).  Returns (u, du_dx, du_dp)."""
+    x = np.asarray(x, dtype=np.float64)
+    params = np.asarray(params, dtype=np.float64).reshape(-1)
+    du_dx, du_dp, u = np.zeros_like(x), np.zeros_like(params), 0.0
+    for t, quad in enumerate(np.asarray(idxs).reshape(-1, 4)):
+        vol, grads = pyramidal_volume_and_grad(*x[quad])
+        if vol > 0:
+            u += params[t] * vol * vol
+            if params[t] == 0:
+                continue  # the kernels skip a restraint with k == 0 entirely, du/dk included (k_chiral_restraint.cuh:60-62)
+            du_dp[t] = vol * vol
+            for atom, g in zip(quad, grads):
+                du_dx[atom] += 2 * params[t] * vol * g
+    return u, du_dx, du_dp
+
+
+def chiral_bond_restraint(x, params, idxs, signs):
+    """u = sum k vol^2 over restraints with sign * vol > 0 (chiral_restraints.py:77-100,115-125)."""
+    x = np.asarray(x, dtype=np.float64)
+    params = np.asarray(params, dtype=np.float64).reshape(-1)
+    du_dx, du_dp, u = np.zeros_like(x), np.zeros_like(params), 0.0
+    for t, quad in enumerate(np.asarray(idxs).reshape(-1, 4)):
+        vol, grads = torsion_volume_and_grad(*x[quad])
+        if signs[t] * vol > 0:
+            u += params[t] * vol * vol
+            if params[t] == 0:
+                continue  # as above (k_chiral_restraint.cuh:150-152)
+            du_dp[t] = vol * vol
+            for atom, g in zip(quad, grads):
+                du_dx[atom] += 2 * params[t] * vol * g
+    return u, du_dx, du_dp
+
+
+def nonbonded_precomputed(x, params, box, pair_idxs, beta, cutoff):
+    """Pairs with their own (q_ij, sig_ij, eps_ij, w_ij): u = q_ij erfc(beta d) S(d) / d + 4 eps_ij (s^12 - s^6),
+    s = sig_ij / d, d^2 = |dx|_pbc^2 + w_ij^2 < cutoff^2 (nonbonded.py:403-446).  Returns (u, du_dx, du_dp[M,4])."""
+    x = np.asarray(x, dtype=np.float64)
+    params = np.asarray(params, dtype=np.float64).reshape(-1, 4)
+    i, j = np.asarray(pair_idxs).reshape(-1, 2).T
+    q, sig, eps, w = params.T
+    dx = delta_r(x[i], x[j], box)
+    d = np.sqrt(np.sum(dx * dx, axis=1) + w * w)
+    keep = d < cutoff
+    from scipy.special import erfc
+
+    damping = erfc(beta * d) * switch_fn(d)
+    d_damping = -2 * beta / np.sqrt(np.pi) * np.exp(-((beta * d) ** 2)) * switch_fn(d) + erfc(beta * d) * d_switch_fn(d)
+    u_es = q * damping / d
+    du_dd_es = q * (d_damping / d - damping / d**2)
+    lj_on = (eps != 0) & (sig != 0)
+    s6 = np.where(lj_on, (sig / d) ** 6, 0.0)
+    u_lj = 4 * eps * (s6 * s6 - s6)
+    du_dd_lj = np.where(lj_on, 24 * eps * (s6 - 2 * s6 * s6) / d, 0.0)
+    es_on = q != 0
+    u = np.sum(np.where(keep, np.where(es_on, u_es, 0) + u_lj, 0.0))
+    du_dd = np.where(keep, np.where(es_on, du_dd_es, 0) + du_dd_lj, 0.0)
+    g = (du_dd / d)[:, None] * dx
+    du_dx = np.zeros_like(x)
+    np.add.at(du_dx, i, g)
+    np.add.at(du_dx, j, -g)
+    du_dp = np.zeros_like(params)
+    du_dp[:, 0] = np.where(keep & es_on, damping / d, 0)
+    du_dp[:, 1] = np.where(keep & lj_on, 4 * eps * (12 * s6 * s6 - 6 * s6) / np.where(sig != 0, sig, 1.0), 0)
+    du_dp[:, 2] = np.where(keep & lj_on, 4 * (s6 * s6 - s6), 0)
+    du_dp[:, 3] = (du_dd / d) * w
+    return u, du_dx, du_dp

@@ -277,6 +277,52 @@ def main():
     )
     print(f"barostat: {n_mols} groups, {offsets[-1]} atoms, scale {scale}")
 
+    # ---- restraints and the precomputed pair list ------------------------------------------------------
+    spec = importlib.util.spec_from_file_location("timemachine.potentials.chiral_restraints", REF / "timemachine/potentials/chiral_restraints.py")
+    cr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cr)
+    N = 40
+    box = np.eye(3) * 2.4
+    x = rng.uniform(0, 2.4, (N, 3))
+    quads = np.array([rng.choice(N, 4, replace=False) for _ in range(24)], dtype=np.int32)
+    k_atom = rng.uniform(10, 1000, len(quads))
+    k_atom[::7] = 0.0
+    signs = rng.choice([-1, 1], len(quads)).astype(np.int32)
+    k_bond = rng.uniform(10, 1000, len(quads))
+
+    def u_chiral_atom(xx, kk=k_atom):
+        # chiral_atom_restraint is sum_r U_chiral_atom(conf, idxs[r], params[r]) (chiral_restraints.py:97-112)
+        return float(sum(float(cr.U_chiral_atom(J(xx), quads[r], kk[r])) for r in range(len(quads))))
+
+    def u_chiral_bond(xx, kk=k_bond):
+        return float(sum(float(cr.U_chiral_bond(J(xx), quads[r], kk[r], signs[r])) for r in range(len(quads))))
+
+    fb_idxs = np.array([rng.choice(N, 2, replace=False) for _ in range(30)], dtype=np.int32)
+    fb_params = np.stack([rng.uniform(50, 500, 30), rng.uniform(0.0, 0.8, 30), rng.uniform(0.8, 1.6, 30)], 1)
+
+    def u_fb(xx, pp=fb_params):
+        return float(bd.flat_bottom_bond(J(xx), J(pp), J(box), fb_idxs))
+
+    pre_idxs = np.array([rng.choice(N, 2, replace=False) for _ in range(60)], dtype=np.int32)
+    pre_params = np.stack(
+        [rng.normal(0, 1.0, 60), rng.uniform(0.1, 0.35, 60), rng.uniform(0.05, 1.0, 60), rng.choice([0.0, 0.0, 0.1, 0.4], 60)], 1
+    )
+
+    def u_pre(xx, pp=pre_params):
+        vdw, es = nb.nonbonded_on_precomputed_pairs(J(xx), J(pp), J(box), pre_idxs, beta, cutoff)
+        return float(np.sum(vdw) + np.sum(es))
+
+    np.savez(
+        OUT / "restraints.npz", x=x, box=box, beta=beta, cutoff=cutoff, quads=quads, k_atom=k_atom, k_bond=k_bond, signs=signs,
+        u_chiral_atom=u_chiral_atom(x), u_chiral_bond=u_chiral_bond(x), chiral_atom_du_dx_fd=fd_grad(u_chiral_atom, x),
+        chiral_bond_du_dx_fd=fd_grad(u_chiral_bond, x),
+        fb_idxs=fb_idxs, fb_params=fb_params, u_fb=u_fb(x), fb_du_dx_fd=fd_grad(u_fb, x),
+        fb_du_dp_fd=fd_grad(lambda p: u_fb(x, p), fb_params, h=1e-6),
+        pre_idxs=pre_idxs, pre_params=pre_params, u_pre=u_pre(x), pre_du_dx_fd=fd_grad(u_pre, x),
+        pre_du_dp_fd=fd_grad(lambda p: u_pre(x, p), pre_params, h=1e-6),
+    )
+    print(f"restraints: u_chiral_atom={u_chiral_atom(x):.8f} u_chiral_bond={u_chiral_bond(x):.8f} u_fb={u_fb(x):.8f} u_pre={u_pre(x):.8f}")
+
 
 if __name__ == "__main__":
     main()

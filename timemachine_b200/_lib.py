@@ -41,6 +41,10 @@ SIGNATURES = {
     "tmb_harmonic_bond_create": [_int, _p_i32, _int, _ph],
     "tmb_harmonic_angle_create": [_int, _p_i32, _int, _ph],
     "tmb_periodic_torsion_create": [_int, _p_i32, _int, _ph],
+    "tmb_flat_bottom_bond_create": [_int, _p_i32, _int, _ph],
+    "tmb_chiral_atom_restraint_create": [_int, _p_i32, _int, _ph],
+    "tmb_chiral_bond_restraint_create": [_int, _p_i32, _int, _p_i32, _int, _ph],
+    "tmb_nonbonded_pair_list_precomputed_create": [_int, _p_i32, _int, _dbl, _dbl, _ph],
     "tmb_nonbonded_all_pairs_create": [_int, _int, _dbl, _dbl, _p_i32, _int, _int, _dbl, _ph],
     "tmb_nonbonded_all_pairs_set_atom_idxs": [_h, _p_i32, _int],
     "tmb_nonbonded_all_pairs_get_num_atom_idxs": [_h, C.POINTER(_int)],

@@ -109,6 +109,23 @@ static int create_bonded(int precision, const int32_t *idxs, int n_values, tmb_p
     });
 }
 
+template <template <typename> class PotT>
+static int create_restraint(
+    int precision, const int32_t *idxs, int n_values, const int32_t *signs, int n_signs, double beta, double cutoff,
+    tmb_potential *out) {
+    return guarded([&] {
+        check_precision(precision);
+        std::vector<int> v(idxs, idxs + (n_values > 0 ? n_values : 0));
+        std::vector<int> sg(signs, signs + (n_signs > 0 ? n_signs : 0));
+        PotPtr p;
+        if (precision == TMB_F32) {
+            p = std::make_shared<PotT<float>>(v, sg, beta, cutoff);
+        } else {
+            p = std::make_shared<PotT<double>>(v, sg, beta, cutoff);
+        }
+        *out = new PotPtr(p);
+    });
+}
 extern "C" {
 
 const char *tmb_last_error(void) { return g_last_error.c_str(); }
@@ -135,6 +152,21 @@ int tmb_harmonic_angle_create(int precision, const int32_t *angle_idxs, int n_va
 }
 int tmb_periodic_torsion_create(int precision, const int32_t *torsion_idxs, int n_values, tmb_potential *out) {
     return create_bonded<PeriodicTorsion>(precision, torsion_idxs, n_values, out);
+}
+
+int tmb_flat_bottom_bond_create(int precision, const int32_t *bond_idxs, int n_values, tmb_potential *out) {
+    return create_restraint<FlatBottomBond>(precision, bond_idxs, n_values, nullptr, 0, 0.0, 0.0, out);
+}
+int tmb_chiral_atom_restraint_create(int precision, const int32_t *idxs, int n_values, tmb_potential *out) {
+    return create_restraint<ChiralAtomRestraint>(precision, idxs, n_values, nullptr, 0, 0.0, 0.0, out);
+}
+int tmb_chiral_bond_restraint_create(
+    int precision, const int32_t *idxs, int n_values, const int32_t *signs, int n_signs, tmb_potential *out) {
+    return create_restraint<ChiralBondRestraint>(precision, idxs, n_values, signs, n_signs, 0.0, 0.0, out);
+}
+int tmb_nonbonded_pair_list_precomputed_create(
+    int precision, const int32_t *pair_idxs, int n_values, double beta, double cutoff, tmb_potential *out) {
+    return create_restraint<NonbondedPairListPrecomputed>(precision, pair_idxs, n_values, nullptr, 0, beta, cutoff, out);
 }
 
 int tmb_nonbonded_all_pairs_create(

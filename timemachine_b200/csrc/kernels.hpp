@@ -164,6 +164,18 @@ struct BondedArgs {
     i128 *d_u;
 };
 int bonded_grid(int n_terms);
+// Restraints and the precomputed pair list (the rest of the HostGuestSystem potential set)
+struct RestraintArgs {
+    BondedArgs b;
+    const double *box = nullptr; // flat-bottom bond, precomputed pairs
+    const int *signs = nullptr;  // chiral bond restraint [R]
+    double beta = 0;             // precomputed pairs
+    double cutoff = 0;
+};
+template <typename Real> void launch_flat_bottom_bond(const RestraintArgs &args, cudaStream_t stream);
+template <typename Real> void launch_chiral_atom_restraint(const RestraintArgs &args, cudaStream_t stream);
+template <typename Real> void launch_chiral_bond_restraint(const RestraintArgs &args, cudaStream_t stream);
+template <typename Real> void launch_nonbonded_precomputed(const RestraintArgs &args, cudaStream_t stream);
 template <typename Real> void launch_harmonic_bond(const BondedArgs &args, cudaStream_t stream);
 template <typename Real> void launch_harmonic_angle(const BondedArgs &args, cudaStream_t stream);
 template <typename Real> void launch_periodic_torsion(const BondedArgs &args, cudaStream_t stream);

@@ -173,6 +173,30 @@ template <typename Real> using HarmonicBond = BondedPotential<Real, BondedKind::
 template <typename Real> using HarmonicAngle = BondedPotential<Real, BondedKind::Angle>;
 template <typename Real> using PeriodicTorsion = BondedPotential<Real, BondedKind::Torsion>;
 
+// Restraints + precomputed pair list (reference flat_bottom_bond.hpp, chiral_atom_restraint.hpp,
+// chiral_bond_restraint.hpp, nonbonded_precomputed.hpp)
+enum class RestraintKind { FlatBottomBond, ChiralAtom, ChiralBond, PrecomputedPairs };
+
+template <typename Real, RestraintKind KIND> class RestraintPotential : public Potential {
+public:
+    static constexpr int ARITY = (KIND == RestraintKind::FlatBottomBond || KIND == RestraintKind::PrecomputedPairs) ? 2 : 4;
+    static constexpr int PARAMS = KIND == RestraintKind::FlatBottomBond ? 3 : (KIND == RestraintKind::PrecomputedPairs ? 4 : 1);
+    RestraintPotential(const std::vector<int> &idxs, const std::vector<int> &signs, double beta, double cutoff);
+    void execute_device(int, int, const double *, const double *, const double *, u64 *, u64 *, i128 *, cudaStream_t) override;
+    void du_dp_fixed_to_float(int N, int P, const u64 *du_dp, double *out) const override;
+    int num_terms() const { return n_terms_; }
+private:
+    int n_terms_;
+    double beta_, cutoff_;
+    DeviceBuffer<int> d_idxs_, d_signs_;
+    DeviceBuffer<i128> d_partials_;
+    DeviceBuffer<unsigned int> d_ticket_;
+};
+template <typename Real> using FlatBottomBond = RestraintPotential<Real, RestraintKind::FlatBottomBond>;
+template <typename Real> using ChiralAtomRestraint = RestraintPotential<Real, RestraintKind::ChiralAtom>;
+template <typename Real> using ChiralBondRestraint = RestraintPotential<Real, RestraintKind::ChiralBond>;
+template <typename Real> using NonbondedPairListPrecomputed = RestraintPotential<Real, RestraintKind::PrecomputedPairs>;
+
 // ---------------------------------------------------------------------------------------------------------------
 class HilbertSort {
 public:

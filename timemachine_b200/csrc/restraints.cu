@@ -1,0 +1,139 @@
+// Host classes of the restraints and the precomputed pair list.  Reference:
+// flat_bottom_bond.cu:11-94, chiral_atom_restraint.cu:11-70, chiral_bond_restraint.cu:11-85,
+// nonbonded_precomputed.cu:12-109; argument checks and messages follow those files.
+#include "fixed_point.cuh"
+#include "potential.hpp"
+
+namespace tmb {
+
+template <typename Real, RestraintKind KIND>
+RestraintPotential<Real, KIND>::RestraintPotential(
+    const std::vector<int> &idxs, const std::vector<int> &signs, double beta, double cutoff)
+    : n_terms_(static_cast<int>(idxs.size() / ARITY)), beta_(beta), cutoff_(cutoff) {
+    if (idxs.size() % ARITY != 0) {
+        switch (KIND) {
+        case RestraintKind::FlatBottomBond:
+            throw std::runtime_error("bond_idxs.size() must be exactly 2*k!");
+        case RestraintKind::ChiralAtom:
+            throw std::runtime_error("idxs.size() must be exactly 4*k!");
+        case RestraintKind::ChiralBond:
+            throw std::runtime_error("idxs.size() must be exactly 4*R!");
+        case RestraintKind::PrecomputedPairs:
+            throw std::runtime_error("idxs.size() must be exactly 2*B!");
+        }
+    }
+    if (KIND == RestraintKind::ChiralBond) {
+        if (static_cast<size_t>(n_terms_) != signs.size()) {
+            throw std::runtime_error("signs.size() must be exactly R!");
+        }
+        for (int s : signs) {
+            if (s != 1 && s != -1) {
+                throw std::runtime_error("signs must be comprised exclusively of 1 or -1");
+            }
+        }
+    }
+    if (KIND == RestraintKind::FlatBottomBond || KIND == RestraintKind::PrecomputedPairs) {
+        for (int t = 0; t < n_terms_; t++) {
+            const int src = idxs[t * 2 + 0], dst = idxs[t * 2 + 1];
+            if (src == dst) {
+                if (KIND == RestraintKind::FlatBottomBond) {
+                    throw std::runtime_error("src == dst");
+                }
+                throw std::runtime_error("illegal pair with src == dst: " + std::to_string(src) + ", " + std::to_string(dst));
+            }
+            if (KIND == RestraintKind::FlatBottomBond && (src < 0 || dst < 0)) {
+                throw std::runtime_error("idxs must be non-negative");
+            }
+        }
+    }
+    d_idxs_.realloc(std::max<size_t>(1, idxs.size()));
+    if (!idxs.empty()) {
+        TMB_CUDA(cudaMemcpy(d_idxs_.data, idxs.data(), idxs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (KIND == RestraintKind::ChiralBond) {
+        d_signs_.realloc(std::max<size_t>(1, signs.size()));
+        if (!signs.empty()) {
+            TMB_CUDA(cudaMemcpy(d_signs_.data, signs.data(), signs.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+    }
+    d_partials_.realloc(bonded_grid(n_terms_));
+    d_ticket_.realloc(1);
+    d_ticket_.zero();
+    TMB_CUDA(cudaDeviceSynchronize());
+}
+
+template <typename Real, RestraintKind KIND>
+void RestraintPotential<Real, KIND>::execute_device(
+    int, int P, const double *d_x, const double *d_p, const double *d_box, u64 *d_du_dx, u64 *d_du_dp, i128 *d_u,
+    cudaStream_t stream) {
+    const int expected = PARAMS * n_terms_;
+    if (P != expected) {
+        switch (KIND) {
+        case RestraintKind::FlatBottomBond:
+            throw std::runtime_error(
+                "FlatBottomBond::execute_device(): expected P == " + std::to_string(expected) + ", got P=" + std::to_string(P));
+        case RestraintKind::ChiralAtom:
+            throw std::runtime_error(
+                "ChiralAtomRestraint::execute_device(): expected P == R, got P=" + std::to_string(P) +
+                ", R=" + std::to_string(n_terms_));
+        case RestraintKind::ChiralBond:
+            throw std::runtime_error(
+                "ChiralBondRestraint::execute_device(): expected P == R, got P=" + std::to_string(P) +
+                ", R=" + std::to_string(n_terms_));
+        case RestraintKind::PrecomputedPairs:
+            throw std::runtime_error(
+                "NonbondedPairListPrecomputed::execute_device(): expected P == 4*B, got P=" + std::to_string(P) +
+                ", 4*B=" + std::to_string(expected));
+        }
+    }
+    if (n_terms_ <= 0) {
+        return;
+    }
+    RestraintArgs a;
+    a.b.n_terms = n_terms_;
+    a.b.x = d_x;
+    a.b.p = d_p;
+    a.b.idxs = d_idxs_.data;
+    a.b.du_dx = d_du_dx;
+    a.b.du_dp = d_du_dp;
+    a.b.u_partials = d_partials_.data;
+    a.b.ticket = d_ticket_.data;
+    a.b.d_u = d_u;
+    a.box = d_box;
+    a.signs = d_signs_.data;
+    a.beta = beta_;
+    a.cutoff = cutoff_;
+    switch (KIND) {
+    case RestraintKind::FlatBottomBond:
+        launch_flat_bottom_bond<Real>(a, stream);
+        break;
+    case RestraintKind::ChiralAtom:
+        launch_chiral_atom_restraint<Real>(a, stream);
+        break;
+    case RestraintKind::ChiralBond:
+        launch_chiral_bond_restraint<Real>(a, stream);
+        break;
+    case RestraintKind::PrecomputedPairs:
+        launch_nonbonded_precomputed<Real>(a, stream);
+        break;
+    }
+}
+
+template <typename Real, RestraintKind KIND>
+void RestraintPotential<Real, KIND>::du_dp_fixed_to_float(int N, int P, const u64 *du_dp, double *out) const {
+    if (KIND == RestraintKind::PrecomputedPairs) {
+        nonbonded_du_dp_fixed_to_float(n_terms_, P, du_dp, out); // per-column scales, rows are pairs
+    } else {
+        Potential::du_dp_fixed_to_float(N, P, du_dp, out);
+    }
+}
+
+#define TMB_INSTANTIATE(KIND)                                                                                          \
+    template class RestraintPotential<float, KIND>;                                                                    \
+    template class RestraintPotential<double, KIND>;
+TMB_INSTANTIATE(RestraintKind::FlatBottomBond)
+TMB_INSTANTIATE(RestraintKind::ChiralAtom)
+TMB_INSTANTIATE(RestraintKind::ChiralBond)
+TMB_INSTANTIATE(RestraintKind::PrecomputedPairs)
+
+} // namespace tmb

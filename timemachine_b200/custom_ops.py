@@ -275,6 +275,61 @@ PeriodicTorsion_f32 = _make_bonded("PeriodicTorsion_f32", _L.tmb_periodic_torsio
 PeriodicTorsion_f64 = _make_bonded("PeriodicTorsion_f64", _L.tmb_periodic_torsion_create, F64)
 
 
+FlatBottomBond_f32 = _make_bonded("FlatBottomBond_f32", _L.tmb_flat_bottom_bond_create, F32)
+FlatBottomBond_f64 = _make_bonded("FlatBottomBond_f64", _L.tmb_flat_bottom_bond_create, F64)
+ChiralAtomRestraint_f32 = _make_bonded("ChiralAtomRestraint_f32", _L.tmb_chiral_atom_restraint_create, F32)
+ChiralAtomRestraint_f64 = _make_bonded("ChiralAtomRestraint_f64", _L.tmb_chiral_atom_restraint_create, F64)
+
+
+class _ChiralBondRestraint(Potential):
+    """ChiralBondRestraint_{f32,f64}(idxs[R,4], signs[R]) (wrap_kernels.cpp:1380-1394)."""
+
+    _precision = F32
+
+    def __init__(self, idxs, signs):
+        idxs, signs = _i32(idxs), _i32(signs)
+        h = _new_handle()
+        _check(
+            _L.tmb_chiral_bond_restraint_create(
+                self._precision, _ptr(idxs, C.c_int32), idxs.size, _ptr(signs, C.c_int32), signs.size, C.byref(h)
+            )
+        )
+        self._adopt(h)
+
+
+class ChiralBondRestraint_f32(_ChiralBondRestraint):
+    _precision = F32
+
+
+class ChiralBondRestraint_f64(_ChiralBondRestraint):
+    _precision = F64
+
+
+class _NonbondedPairListPrecomputed(Potential):
+    """NonbondedPairListPrecomputed_{f32,f64}(pair_idxs[M,2], beta, cutoff); params are per pair
+    (q_ij, sig_ij, eps_ij, w_offset_ij) (wrap_kernels.cpp:1351-1364)."""
+
+    _precision = F32
+
+    def __init__(self, pair_idxs, beta, cutoff):
+        pair_idxs = _i32(pair_idxs)
+        h = _new_handle()
+        _check(
+            _L.tmb_nonbonded_pair_list_precomputed_create(
+                self._precision, _ptr(pair_idxs, C.c_int32), pair_idxs.size, float(beta), float(cutoff), C.byref(h)
+            )
+        )
+        self._adopt(h)
+
+
+class NonbondedPairListPrecomputed_f32(_NonbondedPairListPrecomputed):
+    _precision = F32
+
+
+class NonbondedPairListPrecomputed_f64(_NonbondedPairListPrecomputed):
+    _precision = F64
+
+
 class _TiledExtras:
     """Introspection / measurement hooks of the tile-list potentials (not part of the reference API)."""
 

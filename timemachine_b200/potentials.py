@@ -86,6 +86,37 @@ class PeriodicTorsion(Potential):
 
 
 @dataclass
+class FlatBottomBond(Potential):
+    """potentials.py:77-83"""
+
+    idxs: np.ndarray
+
+
+@dataclass
+class ChiralAtomRestraint(Potential):
+    """potentials.py:60-66"""
+
+    idxs: np.ndarray
+
+
+@dataclass
+class ChiralBondRestraint(Potential):
+    """potentials.py:68-75"""
+
+    idxs: np.ndarray
+    signs: np.ndarray
+
+
+@dataclass
+class NonbondedPairListPrecomputed(Potential):
+    """potentials.py:218-237: per-pair parameters (q_ij, sig_ij, eps_ij, w_offset_ij), combining rules already applied."""
+
+    idxs: np.ndarray
+    beta: float
+    cutoff: float
+
+
+@dataclass
 class NonbondedAllPairs(Potential):
     num_atoms: int
     beta: float
