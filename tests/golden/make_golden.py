@@ -43,6 +43,11 @@ class _At:
                 out[idx] = val
                 return out
 
+            def add(self, val):
+                out = np.array(arr, copy=True).view(JArr)
+                out[idx] += val
+                return out
+
         return _Setter()
 
 
@@ -321,6 +326,35 @@ def main():
         pre_idxs=pre_idxs, pre_params=pre_params, u_pre=u_pre(x), pre_du_dx_fd=fd_grad(u_pre, x),
         pre_du_dp_fd=fd_grad(lambda p: u_pre(x, p), pre_params, h=1e-6),
     )
+    # ---- HREX neighbour swaps: the reference's _run_neighbor_swaps (md/hrex.py:50-129) ------------------------------------
+    # hrex.py imports md.moves and scipy.stats at module scope; the one pure function is exec'd from the reference source
+    # text (unmodified) with python stand-ins for jax.lax.scan / cond.
+    lax = types.SimpleNamespace(
+        cond=lambda pred, t, f: t() if bool(pred) else f(),
+        scan=lambda f, init, xs: (
+            __import__("functools").reduce(lambda c, x: f(c, x)[0], list(zip(*xs)), init),
+            None,
+        ),
+    )
+    jx = types.SimpleNamespace(jit=lambda f: f, lax=lax)
+    src = (REF / "timemachine/md/hrex.py").read_text()
+    jn = types.SimpleNamespace(zeros=lambda n, dt: np.zeros(n, dt).view(JArr), minimum=np.minimum, exp=np.exp, uint32=np.uint32)
+    ns = {"jax": jx, "jnp": jn, "Array": np.ndarray, "np": np}
+    exec(src[src.index("@jax.jit\ndef _run_neighbor_swaps") : src.index("@dataclass(frozen=True)\nclass HREX")], ns)
+    n_states = 8
+    log_q = -rng.uniform(0, 6, (n_states, n_states))
+    pairs = np.array([(s, s + 1) for s in range(n_states - 1)])
+    n_attempts = 300
+    pair_idxs = rng.integers(0, len(pairs), n_attempts)
+    uniforms = rng.random(n_attempts)
+    start = rng.permutation(n_states)
+    final, proposed, accepted = ns["_run_neighbor_swaps"](start.view(JArr), pairs.view(JArr), log_q.view(JArr), pair_idxs, uniforms)
+    np.savez(
+        OUT / "hrex.npz", log_q=log_q, neighbor_pairs=pairs, pair_idxs=pair_idxs, uniform_samples=uniforms, start=start,
+        final=np.asarray(final), proposed=np.asarray(proposed), accepted=np.asarray(accepted),
+    )
+    print(f"hrex: final={np.asarray(final).tolist()} accepted={int(np.sum(accepted))}/{n_attempts}")
+
     print(f"restraints: u_chiral_atom={u_chiral_atom(x):.8f} u_chiral_bond={u_chiral_bond(x):.8f} u_fb={u_fb(x):.8f} u_pre={u_pre(x):.8f}")
 
 

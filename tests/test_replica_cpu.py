@@ -80,3 +80,21 @@ def test_single_rank_paths():
     assert replica.i128_to_energy(1 << 36, 0) == 1.0
     assert replica.i128_to_energy((-(1 << 36)) & ((1 << 64) - 1), -1) == -1.0
     assert np.isnan(replica.i128_to_energy(0, 1))
+
+
+def test_run_neighbor_swaps_matches_reference_golden():
+    """replica.run_neighbor_swaps against the reference's own `_run_neighbor_swaps` (md/hrex.py:50-129), executed from the
+    reference source by tests/golden/make_golden.py -> hrex.npz."""
+    from pathlib import Path
+
+    from timemachine_b200 import replica
+
+    g = np.load(Path(__file__).parent / "golden" / "hrex.npz")
+    final, proposed, accepted = replica.run_neighbor_swaps(
+        g["start"], g["neighbor_pairs"], g["log_q"], g["pair_idxs"], g["uniform_samples"]
+    )
+    np.testing.assert_array_equal(final, g["final"])
+    np.testing.assert_array_equal(proposed, g["proposed"])
+    np.testing.assert_array_equal(accepted, g["accepted"])
+    assert sorted(final.tolist()) == list(range(len(final)))  # still a permutation
+    assert proposed.sum() == len(g["pair_idxs"]) and 0 < accepted.sum() < proposed.sum()

@@ -70,6 +70,29 @@ def neighbour_swaps(u_matrix: np.ndarray, states: np.ndarray, temperature: float
     return states
 
 
+def run_neighbor_swaps(replica_idx_by_state, neighbor_pairs, log_q_kl, pair_idxs, uniform_samples):
+    """A batch of neighbour-swap attempts with the reference's semantics (timemachine/md/hrex.py:50-129,
+    `_run_neighbor_swaps`): attempt i picks the state pair neighbor_pairs[pair_idxs[i]] = (s_a, s_b), held by replicas
+    (r_a, r_b); it is accepted iff uniform_samples[i] < exp(min(0, log_q[r_a, s_b] + log_q[r_b, s_a] - log_q[r_a, s_a]
+    - log_q[r_b, s_b])), and then the two states exchange replicas.  log_q_kl[r, s] = -u(x_r; state s) / kT.
+    Deterministic given (pair_idxs, uniform_samples): every rank runs it on the all-gathered matrix and agrees.
+    Returns (replica_idx_by_state, proposed_by_pair, accepted_by_pair)."""
+    replica_idx_by_state = np.array(replica_idx_by_state, copy=True)
+    neighbor_pairs = np.asarray(neighbor_pairs)
+    log_q_kl = np.asarray(log_q_kl, dtype=np.float64)
+    proposed = np.zeros(len(neighbor_pairs), dtype=np.uint32)
+    accepted = np.zeros(len(neighbor_pairs), dtype=np.uint32)
+    for pair_idx, u in zip(np.asarray(pair_idxs), np.asarray(uniform_samples)):
+        s_a, s_b = neighbor_pairs[pair_idx]
+        proposed[pair_idx] += 1
+        r_a, r_b = replica_idx_by_state[s_a], replica_idx_by_state[s_b]
+        log_q_diff = (log_q_kl[r_a, s_b] + log_q_kl[r_b, s_a]) - (log_q_kl[r_a, s_a] + log_q_kl[r_b, s_b])
+        if u < np.exp(min(log_q_diff, 0.0)):
+            replica_idx_by_state[s_a], replica_idx_by_state[s_b] = r_b, r_a
+            accepted[pair_idx] += 1
+    return replica_idx_by_state, proposed, accepted
+
+
 def i128_to_energy(lo: int, hi: int) -> float:
     """Fixed-point int128 energy -> kJ/mol, NaN when it left the int64 range (reference wrap_kernels.cpp:83-89)."""
     v = (int(hi) << 64) | (int(lo) & ((1 << 64) - 1))
