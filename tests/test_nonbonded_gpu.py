@@ -186,6 +186,26 @@ def test_rebuild_padding_invariance(precision, rng):
 
 # ---- exclusions ----------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("precision", [np.float64, np.float32])
+def test_small_box_change_reuses_the_list(precision):
+    """A barostat-sized box change (and the matching coordinate scaling) is absorbed by the padding: no rebuild, and the
+    result is bitwise the one of a potential that builds its list from scratch at the new box.  A change of the order of
+    the padding rebuilds."""
+    n = 1500
+    x, params, box = random_nonbonded_system(n, seed=21, w_pattern="zero")
+    x, params = round_to_f32(x), round_to_f32(params)
+    impl = pots().NonbondedAllPairs(n, BETA, CUTOFF).to_gpu(precision).unbound_impl
+    impl.execute(x, params, box)
+    assert impl.get_num_rebuilds() == 1
+    for scale, expect_rebuilds in ((1.002, 1), (0.999, 1), (1.05, 2)):
+        x2, box2 = x * scale, box * scale
+        got = impl.execute(x2, params, box2)
+        assert impl.get_num_rebuilds() == expect_rebuilds, scale
+        fresh = pots().NonbondedAllPairs(n, BETA, CUTOFF).to_gpu(precision).unbound_impl.execute(x2, params, box2)
+        for a, b in zip(got, fresh):
+            np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("precision", [np.float64, np.float32])
 def test_nonbonded_with_exclusions_water(precision):
     sys = water_box(120, seed=5)
     N = sys["N"]

@@ -21,9 +21,21 @@ template <typename Real> __global__ void __launch_bounds__(MISC_THREADS) k_nb_pr
         *a.tile_cursor = 0;
         rebuild = a.force_rebuild != 0;
     }
-    if (k < 9) {
+    // Box changes (barostat proposals) are treated like displacements instead of forcing a rebuild as the reference does
+    // (k_nonbonded.cuh:24-30): a periodic image moves by the atom's displacement plus the change of the box vector, so
+    // a pair can approach by at most d_i + d_j + |dbox| and the list stays complete while every atom has moved less than
+    // (padding - |dbox|) / 2.  Only a change of at least the padding, or an off-diagonal element, rebuilds by itself.
+    double dbox = 0; // |change of the image vector (+-1, +-1, +-1) . box|, the largest any minimum image can shift by
+    for (int c = 0; c < 3; c++) {
+        const double dc = a.box[c * 4] - a.box_build[c * 4];
+        dbox += dc * dc;
+    }
+    dbox = sqrt(dbox);
+    rebuild = rebuild || !(dbox < a.padding); // also catches NaN
+    if (k < 9 && (k % 4) != 0) {
         rebuild = rebuild || (a.box[k] != a.box_build[k]);
     }
+    const double half_room = 0.5 * (a.padding - dbox);
     Vec4<Real> c = {0, 0, 0, 0};
     if (k < a.K) {
         const unsigned int atom = a.perm[k];
@@ -51,7 +63,7 @@ template <typename Real> __global__ void __launch_bounds__(MISC_THREADS) k_nb_pr
         const Real dy = o.y - c.y;
         const Real dz = o.z - c.z;
         const Real d2 = dx * dx + dy * dy + dz * dz;
-        rebuild = rebuild || (static_cast<double>(d2) > 0.25 * a.padding * a.padding);
+        rebuild = rebuild || (static_cast<double>(d2) > half_room * half_room);
     }
     if (rebuild) {
         // benign races: every writer stores the same values, and nothing reads them before the kernel ends

@@ -92,18 +92,6 @@ template <typename Real> void launch_block_bounds(const BlockBoundsArgs<Real> &a
 template void launch_block_bounds<float>(const BlockBoundsArgs<float> &, cudaStream_t);
 template void launch_block_bounds<double>(const BlockBoundsArgs<double> &, cudaStream_t);
 
-__global__ void k_reset_tile_count(unsigned int *count, unsigned int *overflow, const unsigned int *flag) {
-    if (flag != nullptr && *flag == 0) {
-        return;
-    }
-    *count = 0;
-    *overflow = 0;
-}
-
-void launch_reset_tile_count(const TileList &tiles, const unsigned int *flag, cudaStream_t stream) {
-    TMB_LAUNCH(k_reset_tile_count, 1, 1, 0, stream, tiles.count, tiles.overflow, flag);
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int BT_WARPS = 4;
 constexpr int BT_THREADS = BT_WARPS * WARP;

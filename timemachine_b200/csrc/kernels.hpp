@@ -115,8 +115,7 @@ template <typename Real> struct BuildTilesArgs {
     double *snap_box_build = nullptr;
     int snap_slots = 0;
 };
-// The tile counter must be reset with launch_reset_tile_count before each build.
-void launch_reset_tile_count(const TileList &tiles, const unsigned int *flag, cudaStream_t stream);
+// The tile counter is reset by the bounds pass that precedes a build (k_block_bounds, or k_nb_prepare when fused).
 template <typename Real> void launch_build_tiles(const BuildTilesArgs<Real> &args, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------
