@@ -78,6 +78,7 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
         if force or not obj.exists() or obj.stat().st_mtime < max(s.stat().st_mtime, hdr_time):
             todo.append(s)
     extra = ["-Xptxas", "-v"] if ptxas_info else []
+    extra += os.environ.get("TMB_NVCC_EXTRA", "").split()  # experiments, e.g. -DCQ_MIN_CTAS=3
     if todo:
         if verbose:
             print(f"[tmb200] compiling {len(todo)} translation units with {NVCC}", file=sys.stderr)

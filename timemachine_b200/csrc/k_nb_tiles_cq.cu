@@ -21,7 +21,24 @@
 //
 // Invalid atoms (padding of the last block / of a partial tile) are given NaN coordinates in the shared copy: every
 // comparison d2 < cutoff2 is then false, so no validity logic is needed in the inner loop.
+//
+// Prefilter (phase A of most tiles): the 32 x 32 distance tests do not need f32.  For a tile with no 4D atoms and no
+// i < j rule, the 64 atoms are re-expressed relative to row atom 0 (minimum image, f32), rounded to half precision and
+// tested two columns at a time with packed f16x2 arithmetic against a slightly LARGER threshold; only the 5-bit (i, j)
+// codes of the candidates are queued, and phase B recomputes the exact f32 minimum-image displacement from the exact
+// shared copy and applies the reference's strict d2 < cutoff2 before evaluating.  The set of evaluated pairs and every
+// evaluated term are therefore bit-identical to the exact path; the prefilter only has to be conservative:
+//   * same periodic image: all |rel| < A = b/2 - cutoff/2 - 0.01 per axis (checked per tile with one vote), so
+//     |rel_i - rel_j| < b - cutoff - 0.02 and the difference of the relative coordinates IS the minimum-image vector of
+//     any pair closer than the cutoff;
+//   * rounding: |rel| < 4 -> conversion error <= 2^-10 per coordinate; a half difference below 2 rounds with <= 2^-11;
+//     so each component is off by <= 0.00245, which moves d2 by <= 0.00245 (2 sqrt(3) 1.5 + 0.0074) = 0.0128 for
+//     d <= 1.5 nm; the three half roundings of the squared sum add <= 3 * 2^-10.  Total < 0.0158: the threshold is
+//     cutoff^2 + 0.02 rounded up to half, and the prefilter is only used for cutoff <= 1.5 nm (else: exact path).
+// The exact 38-instruction round per 32 pairs becomes ~29 instructions per 64 pairs (ncu r1 -> r2 in profiles/).
 #include <algorithm>
+
+#include <cuda_fp16.h>
 
 #include "fixed_point.cuh"
 #include "kernels.hpp"
@@ -30,6 +47,9 @@
 
 namespace tmb {
 
+#ifndef CQ_MIN_CTAS
+#define CQ_MIN_CTAS 4
+#endif
 constexpr int CQ_THREADS = 256;
 constexpr int CQ_WARPS = CQ_THREADS / WARP;
 // Scheduling: every warp first takes args.static_tiles consecutive tiles (runs of equal row block stay together), the
@@ -46,6 +66,14 @@ constexpr int S_JSLOT = 448;                // int[32]
 constexpr int S_ACCX = 480;                 // int[3 comps][2 limbs][64 atoms]: rows [0,32) get +, columns [32,64) get + (negated at fold)
 constexpr int S_Q4 = S_ACCX + 6 * 64;       // queue: float4 {dx, dy, dz, bits(i | j << 5)} (16-byte aligned: 864 words)
 constexpr int S_QDW = S_Q4 + 4 * CQ_QUEUE;  // queue: dw (alchemical tiles only)
+// prefilter tiles reuse the (then idle) exact queue: half-precision column coordinates as f16x2 words, per component
+// the 32 pairs P[k] = {c_k, c_k+1 mod 32} stored twice in a row (64 words), so that lane i reads the columns
+// (i + 2R, i + 2R + 1) of double round R as word i + 2R: 32 distinct banks, no wrap; and a queue of candidate codes
+// (i + (j << 5), j not reduced mod 32)
+constexpr int S_H2 = S_Q4;                  // [3 comps][64 words]
+constexpr int CQ_CODES = 128;               // ring capacity (a double round appends <= 64, a batch removes 32)
+constexpr int S_QC = S_H2 + 192;            // int[CQ_CODES]
+static_assert(S_QC + CQ_CODES <= S_QDW + CQ_QUEUE, "prefilter scratch must fit in the exact queue");
 constexpr int S_ACCP = S_QDW + CQ_QUEUE;    // int[4 params][2 limbs][64 atoms] (du/dp variants only)
 constexpr int S_WORDS_X = S_ACCP;           // 1184 words = 4736 B per warp
 constexpr int S_WORDS_P = S_ACCP + 8 * 64;  // 1696 words = 6784 B per warp
@@ -77,20 +105,101 @@ struct CqSink {
     int row_base; // sorted slot of row atom 0 of the current tile
 };
 
+// One pair inside the cutoff: evaluate, round every term to fixed point, add the limbs to the row atom i (0..31) and
+// the column atom j (32..63) of the warp's shared block.
+template <bool ALCH, bool U, bool X, bool P>
+__device__ __forceinline__ void cq_pair(
+    float *S, const int i, const int j, const float dx, const float dy, const float dz, const float dw, const float d2,
+    const float beta, const CqSink &sink, i128 &energy) {
+    int *SI = reinterpret_cast<int *>(S);
+    const float qi = S[S_Q + i], qj = S[S_Q + j];
+    const float ei = S[S_EPS + i], ej = S[S_EPS + j];
+    const PairTerms<float> t = pair_terms<float, U>(1.0f, 1.0f, qi, qj, S[S_SIG + i], S[S_SIG + j], ei, ej, d2, beta);
+    const int si = sink.row_base + i; // sorted slots, translated to atoms on the (rare) direct path only
+    const int sj = SI[S_JSLOT + j - 32];
+    if (X) {
+        const float rx = t.prefactor * dx, ry = t.prefactor * dy, rz = t.prefactor * dz;
+        const u64 fx = to_fixed_force(rx);
+        const u64 fy = to_fixed_force(ry);
+        const u64 fz = to_fixed_force(rz);
+        int *acc = SI + S_ACCX;
+        // all three fixed-point values below 2^52 in magnitude (two limbs hold 2^53); NaN / inf compare false
+        if (fabsf(rx) + fabsf(ry) + fabsf(rz) < 65536.0f) {
+            limb_add(acc + 0 * 128, i, fx);
+            limb_add(acc + 1 * 128, i, fy);
+            limb_add(acc + 2 * 128, i, fz);
+            // the column atom receives the exact negation; it is accumulated positively and negated once at the fold
+            limb_add(acc + 0 * 128, j, fx);
+            limb_add(acc + 1 * 128, j, fy);
+            limb_add(acc + 2 * 128, j, fz);
+        } else {
+            // clashing atoms: too large for two limbs, add to the global accumulators directly
+            u64 *gi = sink.du_dx + static_cast<size_t>(sink.perm[si]) * 3;
+            u64 *gj = sink.du_dx + static_cast<size_t>(sink.perm[sj]) * 3;
+            atomicAdd(gi + 0, fx);
+            atomicAdd(gi + 1, fy);
+            atomicAdd(gi + 2, fz);
+            atomicAdd(gj + 0, 0ull - fx);
+            atomicAdd(gj + 1, 0ull - fy);
+            atomicAdd(gj + 2, 0ull - fz);
+        }
+    }
+    if (P) {
+        int *acc = SI + S_ACCP;
+        const u64 pqi = to_fixed<FIXED_EXPONENT_DU_DCHARGE>(qj * t.inv_d * t.damping);
+        const u64 pqj = to_fixed<FIXED_EXPONENT_DU_DCHARGE>(qi * t.inv_d * t.damping);
+        u64 psig = 0, pei = 0, pej = 0, pw = 0;
+        if (t.lj) {
+            psig = to_fixed<FIXED_EXPONENT_DU_DSIG>(t.sig_grad);
+            pei = to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ej);
+            pej = to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ei);
+        }
+        if (ALCH) {
+            pw = to_fixed<FIXED_EXPONENT_DU_DW>(t.prefactor * dw); // antisymmetric: the column atom gets -pw
+        }
+        if (limb_small(pqi) && limb_small(pqj) && limb_small(psig) && limb_small(pei) && limb_small(pej) &&
+            limb_small(pw)) {
+            limb_add(acc + P_CHARGE * 128, i, pqi);
+            limb_add(acc + P_CHARGE * 128, j, pqj);
+            if (t.lj) {
+                limb_add(acc + P_SIG * 128, i, psig);
+                limb_add(acc + P_SIG * 128, j, psig);
+                limb_add(acc + P_EPS * 128, i, pei);
+                limb_add(acc + P_EPS * 128, j, pej);
+            }
+            if (ALCH) {
+                limb_add(acc + P_W * 128, i, pw);
+                limb_add(acc + P_W * 128, j, 0ull - pw);
+            }
+        } else {
+            u64 *gi = sink.du_dp + static_cast<size_t>(sink.perm[si]) * P_PER_ATOM;
+            u64 *gj = sink.du_dp + static_cast<size_t>(sink.perm[sj]) * P_PER_ATOM;
+            atomicAdd(gi + P_CHARGE, pqi);
+            atomicAdd(gj + P_CHARGE, pqj);
+            atomicAdd(gi + P_SIG, psig);
+            atomicAdd(gj + P_SIG, psig);
+            atomicAdd(gi + P_EPS, pei);
+            atomicAdd(gj + P_EPS, pej);
+            atomicAdd(gi + P_W, pw);
+            atomicAdd(gj + P_W, 0ull - pw);
+        }
+    }
+    if (U) {
+        energy += energy_to_fixed<float>(t.u);
+    }
+}
+
 // Phase B: evaluate `count` (<= 32) queued pairs, one per lane.
 template <bool ALCH, bool U, bool X, bool P>
 __device__ __forceinline__ void cq_process(
     float *S, const int head, const int count, const float beta, const CqSink &sink, i128 &energy) {
     const int lane = threadIdx.x & 31;
-    int *SI = reinterpret_cast<int *>(S);
     __syncwarp();
     if (lane < count) {
         const int k = (head + lane) & (CQ_QUEUE - 1);
         const float4 item = reinterpret_cast<const float4 *>(S + S_Q4)[k];
         const float dx = item.x, dy = item.y, dz = item.z;
         const int idx = __float_as_int(item.w);
-        const int i = idx & 31;
-        const int j = 32 + (idx >> 5);
         // same expression as phase A: the queue does not carry d2
         float d2 = dist2_3d(dx, dy, dz);
         float dw = 0.0f;
@@ -98,81 +207,94 @@ __device__ __forceinline__ void cq_process(
             dw = S[S_QDW + k];
             d2 = fma_(dw, dw, d2);
         }
-        const float qi = S[S_Q + i], qj = S[S_Q + j];
-        const float ei = S[S_EPS + i], ej = S[S_EPS + j];
-        const PairTerms<float> t = pair_terms<float, U>(1.0f, 1.0f, qi, qj, S[S_SIG + i], S[S_SIG + j], ei, ej, d2, beta);
-        const int si = sink.row_base + i;      // sorted slots, translated to atoms on the (rare) direct path only
-        const int sj = SI[S_JSLOT + j - 32];
-        if (X) {
-            const u64 fx = to_fixed_force(t.prefactor * dx);
-            const u64 fy = to_fixed_force(t.prefactor * dy);
-            const u64 fz = to_fixed_force(t.prefactor * dz);
-            int *acc = SI + S_ACCX;
-            if (limb_small(fx) && limb_small(fy) && limb_small(fz)) {
-                limb_add(acc + 0 * 128, i, fx);
-                limb_add(acc + 1 * 128, i, fy);
-                limb_add(acc + 2 * 128, i, fz);
-                // the column atom receives the exact negation; it is accumulated positively and negated once at the fold
-                limb_add(acc + 0 * 128, j, fx);
-                limb_add(acc + 1 * 128, j, fy);
-                limb_add(acc + 2 * 128, j, fz);
-            } else {
-                // clashing atoms: too large for two limbs, add to the global accumulators directly
-                u64 *gi = sink.du_dx + static_cast<size_t>(sink.perm[si]) * 3;
-                u64 *gj = sink.du_dx + static_cast<size_t>(sink.perm[sj]) * 3;
-                atomicAdd(gi + 0, fx);
-                atomicAdd(gi + 1, fy);
-                atomicAdd(gi + 2, fz);
-                atomicAdd(gj + 0, 0ull - fx);
-                atomicAdd(gj + 1, 0ull - fy);
-                atomicAdd(gj + 2, 0ull - fz);
-            }
-        }
-        if (P) {
-            int *acc = SI + S_ACCP;
-            const u64 pqi = to_fixed<FIXED_EXPONENT_DU_DCHARGE>(qj * t.inv_d * t.damping);
-            const u64 pqj = to_fixed<FIXED_EXPONENT_DU_DCHARGE>(qi * t.inv_d * t.damping);
-            u64 psig = 0, pei = 0, pej = 0, pw = 0;
-            if (t.lj) {
-                psig = to_fixed<FIXED_EXPONENT_DU_DSIG>(t.sig_grad);
-                pei = to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ej);
-                pej = to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ei);
-            }
-            if (ALCH) {
-                pw = to_fixed<FIXED_EXPONENT_DU_DW>(t.prefactor * dw); // antisymmetric: the column atom gets -pw
-            }
-            if (limb_small(pqi) && limb_small(pqj) && limb_small(psig) && limb_small(pei) && limb_small(pej) &&
-                limb_small(pw)) {
-                limb_add(acc + P_CHARGE * 128, i, pqi);
-                limb_add(acc + P_CHARGE * 128, j, pqj);
-                if (t.lj) {
-                    limb_add(acc + P_SIG * 128, i, psig);
-                    limb_add(acc + P_SIG * 128, j, psig);
-                    limb_add(acc + P_EPS * 128, i, pei);
-                    limb_add(acc + P_EPS * 128, j, pej);
-                }
-                if (ALCH) {
-                    limb_add(acc + P_W * 128, i, pw);
-                    limb_add(acc + P_W * 128, j, 0ull - pw);
-                }
-            } else {
-                u64 *gi = sink.du_dp + static_cast<size_t>(sink.perm[si]) * P_PER_ATOM;
-                u64 *gj = sink.du_dp + static_cast<size_t>(sink.perm[sj]) * P_PER_ATOM;
-                atomicAdd(gi + P_CHARGE, pqi);
-                atomicAdd(gj + P_CHARGE, pqj);
-                atomicAdd(gi + P_SIG, psig);
-                atomicAdd(gj + P_SIG, psig);
-                atomicAdd(gi + P_EPS, pei);
-                atomicAdd(gj + P_EPS, pej);
-                atomicAdd(gi + P_W, pw);
-                atomicAdd(gj + P_W, 0ull - pw);
-            }
-        }
-        if (U) {
-            energy += energy_to_fixed<float>(t.u);
+        cq_pair<ALCH, U, X, P>(S, idx & 31, 32 + (idx >> 5), dx, dy, dz, dw, d2, beta, sink, energy);
+    }
+    __syncwarp();
+}
+
+struct CqBox {
+    float bx, by, bz, inv_bx, inv_by, inv_bz;
+};
+
+// Phase B of a prefilter tile: `count` (<= 32) queued candidate codes, one per lane, the oldest at byte offset head4 of
+// the ring.  The exact f32 displacement is formed here with the very expressions of the exact phase A (min_image,
+// dist2_3d) and the reference's strict test.
+template <bool U, bool X, bool P>
+__device__ __forceinline__ void cq_process_codes(
+    float *S, const int head4, const int count, const CqBox &b, const float cutoff2, const float beta, const CqSink &sink,
+    i128 &energy) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (lane < count) {
+        const char *Q = reinterpret_cast<const char *>(S + S_QC);
+        const int code = *reinterpret_cast<const int *>(Q + ((head4 + 4 * lane) & (4 * CQ_CODES - 4)));
+        const int i = code & 31;
+        const int j = 32 + ((code >> 5) & 31);
+        const float dx = min_image(S[S_X + i] - S[S_X + j], b.bx, b.inv_bx);
+        const float dy = min_image(S[S_Y + i] - S[S_Y + j], b.by, b.inv_by);
+        const float dz = min_image(S[S_Z + i] - S[S_Z + j], b.bz, b.inv_bz);
+        const float d2 = dist2_3d(dx, dy, dz);
+        if (d2 < cutoff2) {
+            cq_pair<false, U, X, P>(S, i, j, dx, dy, dz, 0.0f, d2, beta, sink, energy);
         }
     }
     __syncwarp();
+}
+
+__device__ __forceinline__ unsigned int h2_bits(const __half2 v) { return *reinterpret_cast<const unsigned int *>(&v); }
+__device__ __forceinline__ __half2 bits_h2(const unsigned int v) { return *reinterpret_cast<const __half2 *>(&v); }
+
+// Prefilter tile: phase A in packed half precision on the relative coordinates staged at S_H2 (see the file header),
+// two columns per lane and round.  DROUNDS == 16: the whole tile; 8: double rounds [dround0, dround0 + 8).
+// hx/hy/hz: this lane's row atom, each value duplicated in both halves.  thr2: the enlarged threshold, duplicated.
+template <bool U, bool X, bool P, int DROUNDS>
+__device__ __forceinline__ void cq_tile_prefilter(
+    float *S, const CqBox &b, const float cutoff2, const unsigned int thr2, const float beta, const __half2 hx,
+    const __half2 hy, const __half2 hz, const int dround0, const CqSink &sink, i128 &energy) {
+    static_assert(DROUNDS % 2 == 0, "the round loop is unrolled by two");
+    const int lane = threadIdx.x & 31;
+    const unsigned int lane_bit = 1u << lane;
+    const unsigned int lt_mask = lane_bit - 1u;
+    char *Q = reinterpret_cast<char *>(S + S_QC);
+    const unsigned int *H = reinterpret_cast<const unsigned int *>(S) + S_H2 + lane + 2 * dround0;
+    int code = lane + ((lane + 2 * dround0) << 5); // i + (j << 5) of the first column of the pair; j taken mod 32 later
+    int tail4 = 0; // ring byte offset one past the newest queued candidate (reduced mod the ring size at use)
+    int count = 0; // queued candidates
+#pragma unroll 2
+    for (int r = 0; r < DROUNDS; r++) {
+        const __half2 dx = __hsub2(hx, bits_h2(H[2 * r]));
+        const __half2 dy = __hsub2(hy, bits_h2(H[64 + 2 * r]));
+        const __half2 dz = __hsub2(hz, bits_h2(H[128 + 2 * r]));
+        const __half2 d2 = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
+        unsigned int b0, b1; // lanes whose first / second column passes (NaN padding compares false)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, q;\n\t"
+            "setp.lt.f16x2 p|q, %2, %3;\n\t"
+            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+            "vote.sync.ballot.b32 %1, q, 0xffffffff;\n\t"
+            "}"
+            : "=r"(b0), "=r"(b1)
+            : "r"(h2_bits(d2)), "r"(thr2));
+        const int n0 = __popc(b0);
+        const int n01 = n0 + __popc(b1);
+        if (b0 & lane_bit) {
+            *reinterpret_cast<int *>(Q + ((tail4 + 4 * __popc(b0 & lt_mask)) & (4 * CQ_CODES - 4))) = code;
+        }
+        if (b1 & lane_bit) {
+            *reinterpret_cast<int *>(Q + ((tail4 + 4 * (n0 + __popc(b1 & lt_mask))) & (4 * CQ_CODES - 4))) = code + 32;
+        }
+        tail4 += 4 * n01;
+        count += n01;
+        code += 64;
+        // full batches, and whatever is left after the last round (one call site: one inlined copy of the evaluation)
+        const bool last = (r == DROUNDS - 1);
+        while (count >= WARP || (last && count > 0)) {
+            const int n = min(count, WARP);
+            cq_process_codes<U, X, P>(S, tail4 - 4 * count, n, b, cutoff2, beta, sink, energy);
+            count -= n;
+        }
+    }
 }
 
 // Phase A + B for one tile whose atoms are already in the warp's shared block.
@@ -232,7 +354,7 @@ __device__ __forceinline__ void cq_tile(
     }
 }
 
-template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 4) k_nb_tiles_cq(const NbTileArgs<float> a) {
+template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, CQ_MIN_CTAS) k_nb_tiles_cq(const NbTileArgs<float> a) {
     extern __shared__ __align__(16) float cq_smem[];
     __shared__ i128 scratch[CQ_WARPS];
     constexpr int WORDS = P ? S_WORDS_P : S_WORDS_X;
@@ -248,6 +370,12 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
     const float beta = static_cast<float>(a.beta);
     const bool triangular = (a.NR == a.K);
     const float nan = __int_as_float(0x7fc00000);
+    const CqBox cqbox = {bx, by, bz, inv_bx, inv_by, inv_bz};
+    // half-precision prefilter (file header): enlarged threshold, 0 = off
+    unsigned int thr2 = 0;
+    if (a.prefilter && cutoff <= 1.5f) {
+        thr2 = h2_bits(__half2half2(__float2half_ru(cutoff2 + 0.02f)));
+    }
 
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (*a.rebuild_flag != 0) {
@@ -371,7 +499,54 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
             // the i < j rule only bites when the column atoms overlap the row block itself
             const bool diag = triangular && __any_sync(0xffffffffu, j_valid && j_slot < (row + 1) * TILE);
             __syncwarp();
-            if (vanilla && !diag) {
+            bool prefilter = false;
+            __half2 hx, hy, hz;
+            if (thr2 != 0 && vanilla && !diag) {
+                // coordinates relative to row atom 0 (always a real atom); usable when both atoms of every pair inside
+                // the cutoff are guaranteed to sit in the same periodic image (file header)
+                const float rx = S[S_X], ry = S[S_Y], rz = S[S_Z];
+                const float ix = min_image(S[S_X + lane] - rx, bx, inv_bx);
+                const float iy = min_image(S[S_Y + lane] - ry, by, inv_by);
+                const float iz = min_image(S[S_Z + lane] - rz, bz, inv_bz);
+                const float jx = min_image(S[S_X + 32 + lane] - rx, bx, inv_bx);
+                const float jy = min_image(S[S_Y + 32 + lane] - ry, by, inv_by);
+                const float jz = min_image(S[S_Z + 32 + lane] - rz, bz, inv_bz);
+                const float ax = fminf(0.5f * (bx - cutoff) - 0.01f, 3.9f);
+                const float ay = fminf(0.5f * (by - cutoff) - 0.01f, 3.9f);
+                const float az = fminf(0.5f * (bz - cutoff) - 0.01f, 3.9f);
+                // NaN (padding) passes: it can never produce a candidate
+                const bool ok = !(fabsf(ix) >= ax) && !(fabsf(iy) >= ay) && !(fabsf(iz) >= az) && !(fabsf(jx) >= ax) &&
+                                !(fabsf(jy) >= ay) && !(fabsf(jz) >= az);
+                prefilter = __all_sync(0xffffffffu, ok);
+                if (prefilter) {
+                    hx = __half2half2(__float2half_rn(ix));
+                    hy = __half2half2(__float2half_rn(iy));
+                    hz = __half2half2(__float2half_rn(iz));
+                    // lane j builds the f16x2 word P[j] = {c_j, c_j+1} of each component and stores it twice (S_H2 layout)
+                    const unsigned int cxy = h2_bits(__floats2half2_rn(jx, jy));
+                    const unsigned int czz = h2_bits(__floats2half2_rn(jz, jz));
+                    const unsigned int nxy = __shfl_sync(0xffffffffu, cxy, (lane + 1) & 31);
+                    const unsigned int nzz = __shfl_sync(0xffffffffu, czz, (lane + 1) & 31);
+                    unsigned int *HW = reinterpret_cast<unsigned int *>(S) + S_H2 + lane;
+                    const unsigned int wx = __byte_perm(cxy, nxy, 0x5410);
+                    const unsigned int wy = __byte_perm(cxy, nxy, 0x7632);
+                    const unsigned int wz = __byte_perm(czz, nzz, 0x5410);
+                    HW[0] = wx;
+                    HW[32] = wx;
+                    HW[64] = wy;
+                    HW[64 + 32] = wy;
+                    HW[128] = wz;
+                    HW[128 + 32] = wz;
+                    __syncwarp();
+                }
+            }
+            if (prefilter) {
+                if (half >= 0) {
+                    cq_tile_prefilter<U, X, P, 8>(S, cqbox, cutoff2, thr2, beta, hx, hy, hz, half * 8, sink, energy);
+                } else {
+                    cq_tile_prefilter<U, X, P, 16>(S, cqbox, cutoff2, thr2, beta, hx, hy, hz, 0, sink, energy);
+                }
+            } else if (vanilla && !diag) {
                 if (half >= 0) {
                     cq_tile<false, false, U, X, P, 16>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, half * 16, sink, energy);
                 } else {

@@ -35,6 +35,7 @@ template <typename Real> struct NbTileArgs {
     unsigned int *tile_cursor;  // dynamic tile scheduling counter, zeroed by k_nb_prepare of the same evaluation
     int grid_ctas = 0;              // persistent grid size; 0 = every CTA slot of the device
     unsigned int static_tiles = 0;  // tiles each warp takes up front (clamped to tile_count / warps); the rest is dynamic
+    bool prefilter = true;          // f32 cq kernel: packed-half distance prefilter (k_nb_tiles_cq.cu); results identical
 };
 // CTA slots a machine-filling tile launch leaves free so that a small concurrent tile launch (the ligand-environment
 // interaction group next to the environment all-pairs term) is not serialised behind it; TMB_NB_RESERVE overrides.

@@ -197,6 +197,13 @@ void NonbondedTiled<Real>::run(
             ta.static_tiles = 0;
         }
     }
+    {
+        static const bool prefilter = [] {
+            const char *env = std::getenv("TMB_NB_PREFILTER"); // A/B knob: 0 = exact f32 distance rounds in every tile
+            return env == nullptr || std::atoi(env) != 0;
+        }();
+        ta.prefilter = prefilter;
+    }
     const bool timed = timing_ && timing_used_ < timing_events_.size();
     if (timed) {
         TMB_CUDA(cudaEventRecord(timing_events_[timing_used_].first, stream));
