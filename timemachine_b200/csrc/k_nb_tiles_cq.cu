@@ -66,17 +66,18 @@ constexpr int S_JSLOT = 448;                // int[32]
 constexpr int S_ACCX = 480;                 // int[3 comps][2 limbs][64 atoms]: rows [0,32) get +, columns [32,64) get + (negated at fold)
 constexpr int S_Q4 = S_ACCX + 6 * 64;       // queue: float4 {dx, dy, dz, bits(i | j << 5)} (16-byte aligned: 864 words)
 constexpr int S_QDW = S_Q4 + 4 * CQ_QUEUE;  // queue: dw (alchemical tiles only)
-// prefilter tiles reuse the (then idle) exact queue: half-precision column coordinates as f16x2 words, per component
-// the 32 pairs P[k] = {c_k, c_k+1 mod 32} stored twice in a row (64 words), so that lane i reads the columns
-// (i + 2R, i + 2R + 1) of double round R as word i + 2R: 32 distinct banks, no wrap; and a queue of candidate codes
-// (i + (j << 5), j not reduced mod 32)
+// prefilter tiles reuse the (then idle) exact queue for the half-precision column coordinates: f16x2 words, per
+// component the 32 pairs P[k] = {c_k, c_k+1 mod 32} stored twice in a row (64 words), so that lane i reads the columns
+// (i + 2R, i + 2R + 1) of double round R as word i + 2R: 32 distinct banks, no wrap
 constexpr int S_H2 = S_Q4;                  // [3 comps][64 words]
-constexpr int CQ_CODES = 128;               // ring capacity (a double round appends <= 64, a batch removes 32)
-constexpr int S_QC = S_H2 + 192;            // int[CQ_CODES]
-static_assert(S_QC + CQ_CODES <= S_QDW + CQ_QUEUE, "prefilter scratch must fit in the exact queue");
-constexpr int S_ACCP = S_QDW + CQ_QUEUE;    // int[4 params][2 limbs][64 atoms] (du/dp variants only)
-constexpr int S_WORDS_X = S_ACCP;           // 1184 words = 4736 B per warp
-constexpr int S_WORDS_P = S_ACCP + 8 * 64;  // 1696 words = 6784 B per warp
+static_assert(S_H2 + 192 <= S_QDW + CQ_QUEUE, "prefilter coordinates must fit in the exact queue");
+// and their own linear queue of 16-bit candidate codes (i + (j << 5), j not reduced mod 32): half a tile (8 double
+// rounds) appends at most 512 behind at most 31 left over from the previous half
+constexpr int CQ_CODES = 544;
+constexpr int S_QC = S_QDW + CQ_QUEUE;      // u16[CQ_CODES] = 272 words
+constexpr int S_ACCP = S_QC + CQ_CODES / 2;    // int[4 params][2 limbs][64 atoms] (du/dp variants only)
+constexpr int S_WORDS_X = S_ACCP;           // 1456 words = 5824 B per warp
+constexpr int S_WORDS_P = S_ACCP + 8 * 64;  // 1968 words = 7872 B per warp (3 CTAs per SM)
 static_assert(S_Q4 % 4 == 0 && S_WORDS_X % 4 == 0 && S_WORDS_P % 4 == 0, "float4 queue alignment");
 
 // |v| < 2^53 as a signed 64-bit number (tested on the high word only)
@@ -216,18 +217,16 @@ struct CqBox {
     float bx, by, bz, inv_bx, inv_by, inv_bz;
 };
 
-// Phase B of a prefilter tile: `count` (<= 32) queued candidate codes, one per lane, the oldest at byte offset head4 of
-// the ring.  The exact f32 displacement is formed here with the very expressions of the exact phase A (min_image,
+// Phase B of a prefilter tile: `count` (<= 32) queued candidate codes, one per lane, the oldest at index `head` of the
+// linear queue.  The exact f32 displacement is formed here with the very expressions of the exact phase A (min_image,
 // dist2_3d) and the reference's strict test.
 template <bool U, bool X, bool P>
 __device__ __forceinline__ void cq_process_codes(
-    float *S, const int head4, const int count, const CqBox &b, const float cutoff2, const float beta, const CqSink &sink,
+    float *S, const int head, const int count, const CqBox &b, const float cutoff2, const float beta, const CqSink &sink,
     i128 &energy) {
     const int lane = threadIdx.x & 31;
-    __syncwarp();
     if (lane < count) {
-        const char *Q = reinterpret_cast<const char *>(S + S_QC);
-        const int code = *reinterpret_cast<const int *>(Q + ((head4 + 4 * lane) & (4 * CQ_CODES - 4)));
+        const int code = reinterpret_cast<const unsigned short *>(S + S_QC)[head + lane];
         const int i = code & 31;
         const int j = 32 + ((code >> 5) & 31);
         const float dx = min_image(S[S_X + i] - S[S_X + j], b.bx, b.inv_bx);
@@ -238,63 +237,79 @@ __device__ __forceinline__ void cq_process_codes(
             cq_pair<false, U, X, P>(S, i, j, dx, dy, dz, 0.0f, d2, beta, sink, energy);
         }
     }
-    __syncwarp();
 }
 
 __device__ __forceinline__ unsigned int h2_bits(const __half2 v) { return *reinterpret_cast<const unsigned int *>(&v); }
 __device__ __forceinline__ __half2 bits_h2(const unsigned int v) { return *reinterpret_cast<const __half2 *>(&v); }
 
 // Prefilter tile: phase A in packed half precision on the relative coordinates staged at S_H2 (see the file header),
-// two columns per lane and round.  DROUNDS == 16: the whole tile; 8: double rounds [dround0, dround0 + 8).
+// two columns per lane and round, in halves of 8 double rounds: the 8 rounds are fully unrolled (immediate offsets, no
+// evaluation code inside, few live registers) and append their candidates to the linear queue; then full batches are
+// evaluated and the < 32 left over move to the front of the queue for the next half.  Halves [h0, h1) are processed:
+// {0, 2} is the whole tile, {h, h + 1} one half of a split tile; the last half also evaluates the partial batch.
 // hx/hy/hz: this lane's row atom, each value duplicated in both halves.  thr2: the enlarged threshold, duplicated.
-template <bool U, bool X, bool P, int DROUNDS>
+template <bool U, bool X, bool P>
 __device__ __forceinline__ void cq_tile_prefilter(
     float *S, const CqBox &b, const float cutoff2, const unsigned int thr2, const float beta, const __half2 hx,
-    const __half2 hy, const __half2 hz, const int dround0, const CqSink &sink, i128 &energy) {
-    static_assert(DROUNDS % 2 == 0, "the round loop is unrolled by two");
+    const __half2 hy, const __half2 hz, const int h0, const int h1, const CqSink &sink, i128 &energy) {
     const int lane = threadIdx.x & 31;
-    const unsigned int lane_bit = 1u << lane;
-    const unsigned int lt_mask = lane_bit - 1u;
-    char *Q = reinterpret_cast<char *>(S + S_QC);
-    const unsigned int *H = reinterpret_cast<const unsigned int *>(S) + S_H2 + lane + 2 * dround0;
-    int code = lane + ((lane + 2 * dround0) << 5); // i + (j << 5) of the first column of the pair; j taken mod 32 later
-    int tail4 = 0; // ring byte offset one past the newest queued candidate (reduced mod the ring size at use)
-    int count = 0; // queued candidates
-#pragma unroll 2
-    for (int r = 0; r < DROUNDS; r++) {
-        const __half2 dx = __hsub2(hx, bits_h2(H[2 * r]));
-        const __half2 dy = __hsub2(hy, bits_h2(H[64 + 2 * r]));
-        const __half2 dz = __hsub2(hz, bits_h2(H[128 + 2 * r]));
-        const __half2 d2 = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
-        unsigned int b0, b1; // lanes whose first / second column passes (NaN padding compares false)
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p, q;\n\t"
-            "setp.lt.f16x2 p|q, %2, %3;\n\t"
-            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
-            "vote.sync.ballot.b32 %1, q, 0xffffffff;\n\t"
-            "}"
-            : "=r"(b0), "=r"(b1)
-            : "r"(h2_bits(d2)), "r"(thr2));
-        const int n0 = __popc(b0);
-        const int n01 = n0 + __popc(b1);
-        if (b0 & lane_bit) {
-            *reinterpret_cast<int *>(Q + ((tail4 + 4 * __popc(b0 & lt_mask)) & (4 * CQ_CODES - 4))) = code;
+    unsigned short *Q = reinterpret_cast<unsigned short *>(S + S_QC);
+    int count = 0; // queued candidates, at [0, count)
+#pragma unroll 1
+    for (int h = h0; h < h1; h++) {
+        {
+            const unsigned int lane_bit = 1u << lane;
+            const unsigned int lt_mask = lane_bit - 1u;
+            const unsigned int *H = reinterpret_cast<const unsigned int *>(S) + S_H2 + lane + 16 * h;
+            const int code = lane + ((lane + 16 * h) << 5); // i + (j << 5), first column of round 0; j mod 32 later
+            unsigned short *tail = Q + count;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const __half2 dx = __hsub2(hx, bits_h2(H[2 * r]));
+                const __half2 dy = __hsub2(hy, bits_h2(H[64 + 2 * r]));
+                const __half2 dz = __hsub2(hz, bits_h2(H[128 + 2 * r]));
+                const __half2 d2 = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
+                unsigned int b0, b1; // lanes whose first / second column passes (NaN padding compares false)
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p, q;\n\t"
+                    "setp.lt.f16x2 p|q, %2, %3;\n\t"
+                    "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+                    "vote.sync.ballot.b32 %1, q, 0xffffffff;\n\t"
+                    "}"
+                    : "=r"(b0), "=r"(b1)
+                    : "r"(h2_bits(d2)), "r"(thr2));
+                const int n0 = __popc(b0);
+                if (b0 & lane_bit) {
+                    tail[__popc(b0 & lt_mask)] = static_cast<unsigned short>(code + 64 * r);
+                }
+                if (b1 & lane_bit) {
+                    tail[n0 + __popc(b1 & lt_mask)] = static_cast<unsigned short>(code + 64 * r + 32);
+                }
+                tail += n0 + __popc(b1);
+            }
+            count = static_cast<int>(tail - Q);
         }
-        if (b1 & lane_bit) {
-            *reinterpret_cast<int *>(Q + ((tail4 + 4 * (n0 + __popc(b1 & lt_mask))) & (4 * CQ_CODES - 4))) = code + 32;
-        }
-        tail4 += 4 * n01;
-        count += n01;
-        code += 64;
-        // full batches, and whatever is left after the last round (one call site: one inlined copy of the evaluation)
-        const bool last = (r == DROUNDS - 1);
+        __syncwarp();
+        const bool last = (h == h1 - 1);
+        int head = 0;
         while (count >= WARP || (last && count > 0)) {
             const int n = min(count, WARP);
-            cq_process_codes<U, X, P>(S, tail4 - 4 * count, n, b, cutoff2, beta, sink, energy);
+            cq_process_codes<U, X, P>(S, head, n, b, cutoff2, beta, sink, energy);
+            head += n;
             count -= n;
         }
+        if (!last && head > 0 && count > 0) {
+            // what is left (< 32) moves to the front; every lane has finished reading [0, head) once this converges
+            __syncwarp();
+            const unsigned short v = Q[head + (lane < count ? lane : 0)];
+            __syncwarp();
+            if (lane < count) {
+                Q[lane] = v;
+            }
+        }
     }
+    __syncwarp();
 }
 
 // Phase A + B for one tile whose atoms are already in the warp's shared block.
@@ -541,11 +556,8 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
                 }
             }
             if (prefilter) {
-                if (half >= 0) {
-                    cq_tile_prefilter<U, X, P, 8>(S, cqbox, cutoff2, thr2, beta, hx, hy, hz, half * 8, sink, energy);
-                } else {
-                    cq_tile_prefilter<U, X, P, 16>(S, cqbox, cutoff2, thr2, beta, hx, hy, hz, 0, sink, energy);
-                }
+                cq_tile_prefilter<U, X, P>(
+                    S, cqbox, cutoff2, thr2, beta, hx, hy, hz, half >= 0 ? half : 0, half >= 0 ? half + 1 : 2, sink, energy);
             } else if (vanilla && !diag) {
                 if (half >= 0) {
                     cq_tile<false, false, U, X, P, 16>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, half * 16, sink, energy);
