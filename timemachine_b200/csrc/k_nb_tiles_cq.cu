@@ -217,16 +217,15 @@ struct CqBox {
     float bx, by, bz, inv_bx, inv_by, inv_bz;
 };
 
-// Phase B of a prefilter tile: `count` (<= 32) queued candidate codes, one per lane, the oldest at index `head` of the
-// linear queue.  The exact f32 displacement is formed here with the very expressions of the exact phase A (min_image,
-// dist2_3d) and the reference's strict test.
+// Phase B of a prefilter tile: one queued candidate code per lane (`q` points at this lane's entry, `active` says
+// whether there is one).  The exact f32 displacement is formed here with the very expressions of the exact phase A
+// (min_image, dist2_3d) and the reference's strict test.
 template <bool U, bool X, bool P>
 __device__ __forceinline__ void cq_process_codes(
-    float *S, const int head, const int count, const CqBox &b, const float cutoff2, const float beta, const CqSink &sink,
-    i128 &energy) {
-    const int lane = threadIdx.x & 31;
-    if (lane < count) {
-        const int code = reinterpret_cast<const unsigned short *>(S + S_QC)[head + lane];
+    float *S, const unsigned short *q, const bool active, const CqBox &b, const float cutoff2, const float beta,
+    const CqSink &sink, i128 &energy) {
+    if (active) {
+        const int code = *q;
         const int i = code & 31;
         const int j = 32 + ((code >> 5) & 31);
         const float dx = min_image(S[S_X + i] - S[S_X + j], b.bx, b.inv_bx);
@@ -291,14 +290,15 @@ __device__ __forceinline__ void cq_tile_prefilter(
             count = static_cast<int>(tail - Q);
         }
         __syncwarp();
+        // full batches; the last half also evaluates the partial one (one call site: one inlined copy of the evaluation)
         const bool last = (h == h1 - 1);
-        int head = 0;
-        while (count >= WARP || (last && count > 0)) {
-            const int n = min(count, WARP);
-            cq_process_codes<U, X, P>(S, head, n, b, cutoff2, beta, sink, energy);
-            head += n;
-            count -= n;
+        const int end = last ? count : (count & ~(WARP - 1));
+        const unsigned short *q = Q + lane;
+        for (int base = 0; base < end; base += WARP, q += WARP) {
+            cq_process_codes<U, X, P>(S, q, base + lane < end, b, cutoff2, beta, sink, energy);
         }
+        const int head = end; // entries consumed
+        count -= end;
         if (!last && head > 0 && count > 0) {
             // what is left (< 32) moves to the front; every lane has finished reading [0, head) once this converges
             __syncwarp();
