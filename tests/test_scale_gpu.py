@@ -117,3 +117,58 @@ def test_large_boxes_exact_properties(n_waters):
     assert_forces_close(a[0], b[0], 1e-9)
     tiles = impl.get_potentials()[0].get_tile_count()
     assert 0.5 * N < tiles < 2.0 * N
+
+
+def test_half_precision_prefilter_equals_exact_distance_rounds_bitwise(tmp_path):
+    """k_nb_tiles_cq.cu tests the 32 x 32 distances of most tiles in packed half precision against an enlarged
+    threshold and re-checks candidates in f32 (TMB_NB_PREFILTER=0 in a fresh process: exact f32 rounds everywhere).
+    The filter must never lose a pair: du_dx, du_dp and u are compared bit for bit on
+      * the DHFR-sized box (box 6.17 nm: every vanilla tile takes the prefilter; ~25k pairs within 1e-3 nm of the cutoff),
+      * the same box with molecules displaced by whole box vectors (imaging inside the prefilter),
+      * a dense blob (every pair of a tile inside the cutoff: the candidate queue runs at capacity),
+      * a box too small for the prefilter's same-image condition (falls back per tile)."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    script = tmp_path / "dump.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {str(root)!r})\n"
+        "from tests.common import water_box, random_nonbonded_system, round_to_f32\n"
+        "from timemachine_b200 import potentials as P\n"
+        "out = {}\n"
+        "def run(tag, x, p, box, n, cutoff=1.2, flags=(True, True, True)):\n"
+        "    impl = P.NonbondedAllPairs(n, 2.0, cutoff).to_gpu(np.float32).unbound_impl\n"
+        "    for rep in range(2):\n"  # second call reuses the list
+        "        dx, dp, u = impl.execute(round_to_f32(x), round_to_f32(p), box, *flags)\n"
+        "    for k, v in (('dx', dx), ('dp', dp), ('u', u)):\n"
+        "        if v is not None: out[tag + k] = v\n"
+        "s = water_box(7853, seed=23)\n"
+        "run('dhfr', s['x'], s['params'], s['box'], s['N'])\n"
+        "run('dhfr_x', s['x'], s['params'], s['box'], s['N'], flags=(True, False, False))\n"
+        "rng = np.random.default_rng(5)\n"
+        "shift = rng.integers(-3, 4, size=(s['N'] // 3, 1, 3)) * np.diag(s['box'])\n"
+        "run('shifted', (s['x'].reshape(-1, 3, 3) + shift).reshape(-1, 3), s['params'], s['box'], s['N'])\n"
+        "x, p, box = random_nonbonded_system(4000, seed=11, box_len=8.0)\n"
+        "x[:2000] = 4.0 + rng.normal(0, 0.25, size=(2000, 3))\n"  # blob: thousands of atoms within the cutoff of each other
+        "run('blob', x, p, box, 4000)\n"
+        "x, p, box = random_nonbonded_system(3000, seed=12, box_len=2.7)\n"
+        "run('small', x, p, box, 3000)\n"
+        "x, p, box = random_nonbonded_system(6000, seed=13, box_len=7.0)\n"
+        "run('short', x, p, box, 6000, cutoff=0.9)\n"
+        "np.savez(sys.argv[1], **out)\n"
+    )
+    results = {}
+    for mode in ("0", "1"):
+        env = dict(os.environ, TMB_NB_PREFILTER=mode)
+        path = tmp_path / f"out{mode}.npz"
+        subprocess.check_call([sys.executable, str(script), str(path)], env=env)
+        results[mode] = dict(np.load(path))
+    assert set(results["0"]) == set(results["1"]) and len(results["0"]) >= 16
+    for k in results["0"]:
+        np.testing.assert_array_equal(results["0"][k], results["1"][k], err_msg=k)
+    # the displaced copy is the same physical system: equal up to the f32 rounding of the larger coordinates
+    assert_forces_close(results["1"]["dhfrdx"], results["1"]["shifteddx"], 5e-3)
