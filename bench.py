@@ -340,6 +340,13 @@ def main():
     ap.add_argument("--no-npt", action="store_true", help="skip the NPT (barostat) side measurement")
     args = ap.parse_args()
 
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner, the
+    # reference's C++ warns with std::cout): keep a private handle to the real stdout for the JSON line and point file
+    # descriptor 1 at stderr for everything else.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -370,7 +377,7 @@ def main():
             "e2e": {"value": ns_day, "unit": "ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), file=json_out, flush=True)
         return
 
     # ---------------- our arm -----------------------------------------------------------------------------------------
@@ -585,7 +592,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": ref_gpu, "npt": npt,
             "us_per_md_step": total_ms * 1e3 / (args.md_steps * args.steps),
         }
-        print(json.dumps(out))
+        print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -41,6 +41,13 @@ template <int MODE> __global__ void k_bench(unsigned long long *out_cycles, unsi
             f = fmaf(f, 1.0001f, 0.5f);
         } else if (MODE == 9) { // 64-bit shuffle
             a64 = __shfl_sync(0xffffffffu, a64, (lane + 1) & 31);
+        } else if (MODE == 11) { // MATCH.ANY on a key with ~11 distinct values x multiplicity 3 (round-2 question: dedupe before ATOMS?)
+            acc += __match_any_sync(0xffffffffu, (lane * stride + it + (acc & 1)) % 11);
+        } else if (MODE == 12) { // REDUX.SUM over match groups (cooperative-groups labeled-partition pattern)
+            const unsigned int m = 0x49249249u << (lane % 3); // three interleaved groups, precomputed mask
+            acc += __reduce_add_sync(m, acc);
+        } else if (MODE == 13) { // ATOMS.ADD.32, 3 lanes per address (the batch pattern of the tile kernel)
+            atomicAdd(&sm32[warp_base + ((lane + it) % 11)], acc);
         } else if (MODE == 10) { // global RED.64 to warp-contiguous addresses (L2 atomics)
             atomicAdd(reinterpret_cast<unsigned long long *>(sink) + ((blockIdx.x * blockDim.x + threadIdx.x) & 8191), a64);
         }
@@ -75,6 +82,11 @@ template <int MODE> void run(const char *name, int warps_per_block, int stride =
 }
 
 int main() {
+    for (int w : {8, 16}) {
+        run<11>("MATCH.ANY (11 groups)", w);
+        run<12>("REDUX.SUM (3 groups)", w);
+        run<13>("ATOMS.ADD.32 3 lanes per address", w);
+    }
     for (int w : {1, 8, 16}) {
         run<0>("ATOMS.ADD.32 conflict-free", w);
         run<1>("ATOMS.ADD.32 scattered(64 words)", w);
