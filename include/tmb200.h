@@ -152,6 +152,12 @@ int tmb_langevin_integrator_create(
 int tmb_langevin_integrator_destroy(tmb_integrator intg);
 /* test hook: N x 3 f32 normals used on every step instead of the in-kernel Philox stream (NULL restores Philox) */
 int tmb_langevin_integrator_set_noise(tmb_integrator intg, const float *noise);
+/* Position of the integrator in its counter-based noise stream: step s of atom a draws Philox(seed; a, s).  The
+ * reference's cuRAND generator has no such handle (langevin_integrator.cu:35-37: its state is not exposed, SURVEY.md §5
+ * "checkpoint / resume"); here a driver can give every replica its own sub-stream (high bits) and resume it exactly, which
+ * makes HREX trajectories independent of how replicas are laid out over GPUs (timemachine_b200/hrex.py). */
+int tmb_langevin_integrator_set_step(tmb_integrator intg, unsigned long long step);
+int tmb_langevin_integrator_get_step(tmb_integrator intg, unsigned long long *step);
 
 /* ---- Mover / MonteCarloBarostat           wrap_kernels.cpp:1591-1659, barostat.cu ------------- */
 /* MonteCarloBarostat<float>(N, pressure[bar], temperature[K], group_idxs, interval, bps, seed, adaptive_scaling_enabled,

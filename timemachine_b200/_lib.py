@@ -77,6 +77,8 @@ SIGNATURES = {
     "tmb_langevin_integrator_create": [_p_f64, _int, _dbl, _dbl, _dbl, _int, _ph],
     "tmb_langevin_integrator_destroy": [_h],
     "tmb_langevin_integrator_set_noise": [_h, _p_f32],
+    "tmb_langevin_integrator_set_step": [_h, C.c_uint64],
+    "tmb_langevin_integrator_get_step": [_h, _p_u64],
     "tmb_context_create": [_p_f64, _p_f64, _p_f64, _int, _h, _ph, _int, _ph],
     "tmb_context_create_with_movers": [_p_f64, _p_f64, _p_f64, _int, _h, _ph, _int, _ph, _int, _ph],
     "tmb_barostat_create": [_int, _dbl, _dbl, _p_i32, _p_i32, _int, _int, _ph, _int, _int, _int, _dbl, _ph],

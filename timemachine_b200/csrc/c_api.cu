@@ -476,6 +476,12 @@ int tmb_langevin_integrator_destroy(tmb_integrator intg) {
 int tmb_langevin_integrator_set_noise(tmb_integrator intg, const float *noise) {
     return guarded([&] { as_intg(intg)->set_external_noise(noise); });
 }
+int tmb_langevin_integrator_set_step(tmb_integrator intg, unsigned long long step) {
+    return guarded([&] { as_intg(intg)->set_step(static_cast<long long>(step)); });
+}
+int tmb_langevin_integrator_get_step(tmb_integrator intg, unsigned long long *step) {
+    return guarded([&] { *step = static_cast<unsigned long long>(as_intg(intg)->step_count()); });
+}
 
 int tmb_context_create(
     const double *x0, const double *v0, const double *box, int N, tmb_integrator intg, const tmb_bound_potential *bps,

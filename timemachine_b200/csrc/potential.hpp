@@ -371,6 +371,8 @@ public:
     void set_external_noise(const float *h_noise); // tests: N x 3 normals reused every step; nullptr restores Philox
     long long step_count() const { return step_; }
     void advance(int n) { step_ += n; }
+    // reposition the counter-based noise stream (graph replays read the counter from the device: no re-capture needed)
+    void set_step(long long step) { step_ = step; }
 private:
     int N_;
     double temperature_;

@@ -648,6 +648,17 @@ class LangevinIntegrator(Integrator):
             raise RuntimeError("noise must have shape (N, 3)")
         _check(_L.tmb_langevin_integrator_set_noise(self._handle, _ptr(noise, C.c_float)))
 
+    def set_step(self, step: int) -> None:
+        """Reposition the counter-based noise stream: the next step of atom a draws Philox(seed; a, step).  The
+        reference's cuRAND state cannot be set (langevin_integrator.cu:35-37); hrex.py uses this to give every replica
+        its own resumable sub-stream, which makes HREX trajectories independent of the replica-to-GPU layout."""
+        _check(_L.tmb_langevin_integrator_set_step(self._handle, C.c_uint64(int(step) & ((1 << 63) - 1))))
+
+    def get_step(self) -> int:
+        out = C.c_uint64(0)
+        _check(_L.tmb_langevin_integrator_get_step(self._handle, C.byref(out)))
+        return int(out.value)
+
 
 class Mover:
     """Base of the movers Context runs after every integrator step (wrap_kernels.cpp:1591-1617, mover.hpp:11-50)."""
