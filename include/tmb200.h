@@ -194,6 +194,17 @@ int tmb_context_destroy(tmb_context ctx);
 int tmb_context_step(tmb_context ctx);
 /* Context::multiple_steps(n_steps, n_samples, h_x[n_samples,N,3], h_box[n_samples,3,3])   context.cu:216-242 */
 int tmb_context_multiple_steps(tmb_context ctx, int n_steps, int n_samples, double *h_x, double *h_box);
+/* Local MD: Context.setup_local_md / multiple_steps_local / multiple_steps_local_selection (wrap_kernels.cpp:368-612,
+ * context.cu:90-214).  h_x [n_samples, N, 3], h_box [n_samples, 3, 3].  tmb_context_local_md_free_idxs: the free-atom
+ * array of the last local call, out[i] = i if atom i was free else N (introspection for tests). */
+int tmb_context_setup_local_md(tmb_context ctx, double temperature, int freeze_reference);
+int tmb_context_multiple_steps_local(
+    tmb_context ctx, int n_steps, const int *local_idxs, int n_local_idxs, int n_samples, double radius, double k, int seed,
+    double *h_x, double *h_box);
+int tmb_context_multiple_steps_local_selection(
+    tmb_context ctx, int n_steps, int reference_idx, const int *selection_idxs, int n_selection_idxs, int n_samples,
+    double radius, double k, double *h_x, double *h_box);
+int tmb_context_local_md_free_idxs(tmb_context ctx, unsigned int *out);
 int tmb_context_set_x_t(tmb_context ctx, const double *x);
 int tmb_context_set_v_t(tmb_context ctx, const double *v);
 int tmb_context_set_box(tmb_context ctx, const double *box);

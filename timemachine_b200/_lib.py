@@ -97,6 +97,10 @@ SIGNATURES = {
     "tmb_context_destroy": [_h],
     "tmb_context_step": [_h],
     "tmb_context_multiple_steps": [_h, _int, _int, _p_f64, _p_f64],
+    "tmb_context_setup_local_md": [_h, _dbl, _int],
+    "tmb_context_multiple_steps_local": [_h, _int, _p_i32, _int, _int, _dbl, _dbl, _int, _p_f64, _p_f64],
+    "tmb_context_multiple_steps_local_selection": [_h, _int, _int, _p_i32, _int, _int, _dbl, _dbl, _p_f64, _p_f64],
+    "tmb_context_local_md_free_idxs": [_h, _p_u32],
     "tmb_context_set_x_t": [_h, _p_f64],
     "tmb_context_set_v_t": [_h, _p_f64],
     "tmb_context_set_box": [_h, _p_f64],

@@ -583,6 +583,35 @@ int tmb_context_step(tmb_context ctx) {
 int tmb_context_multiple_steps(tmb_context ctx, int n_steps, int n_samples, double *h_x, double *h_box) {
     return guarded([&] { as_ctx(ctx).multiple_steps(n_steps, n_samples, h_x, h_box); });
 }
+int tmb_context_setup_local_md(tmb_context ctx, double temperature, int freeze_reference) {
+    return guarded([&] { as_ctx(ctx).setup_local_md(temperature, freeze_reference != 0); });
+}
+int tmb_context_multiple_steps_local(
+    tmb_context ctx, int n_steps, const int *local_idxs, int n_local_idxs, int n_samples, double radius, double k, int seed,
+    double *h_x, double *h_box) {
+    return guarded([&] {
+        as_ctx(ctx).multiple_steps_local(
+            n_steps, std::vector<int>(local_idxs, local_idxs + n_local_idxs), n_samples, radius, k, seed, h_x, h_box);
+    });
+}
+int tmb_context_multiple_steps_local_selection(
+    tmb_context ctx, int n_steps, int reference_idx, const int *selection_idxs, int n_selection_idxs, int n_samples,
+    double radius, double k, double *h_x, double *h_box) {
+    return guarded([&] {
+        as_ctx(ctx).multiple_steps_local_selection(
+            n_steps, reference_idx, std::vector<int>(selection_idxs, selection_idxs + n_selection_idxs), n_samples, radius, k,
+            h_x, h_box);
+    });
+}
+int tmb_context_local_md_free_idxs(tmb_context ctx, unsigned int *out) {
+    return guarded([&] {
+        const LocalMD *l = as_ctx(ctx).local_md();
+        if (l == nullptr) {
+            throw std::runtime_error("local md has not been set up");
+        }
+        std::copy(l->selected_host().begin(), l->selected_host().end(), out);
+    });
+}
 int tmb_context_set_x_t(tmb_context ctx, const double *x) {
     return guarded([&] { as_ctx(ctx).set_x_t(x); });
 }

@@ -246,6 +246,73 @@ void Context::multiple_steps(int n_steps, int n_samples, double *h_x, double *h_
     TMB_CUDA(cudaStreamSynchronize(stream));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Local MD (reference context.cu:90-214)
+void Context::setup_local_md(double temperature, bool freeze_reference) {
+    if (local_md_ != nullptr) {
+        if (local_md_->temperature != temperature || local_md_->freeze_reference != freeze_reference) {
+            throw std::runtime_error(
+                "local md configured with different parameters, current parameters: Temperature " +
+                std::to_string(local_md_->temperature) + " Freeze Reference " + std::to_string(local_md_->freeze_reference));
+        }
+        return;
+    }
+    local_md_.reset(new LocalMD(N_, bps_, freeze_reference, temperature));
+}
+
+void Context::run_local_steps(int n_steps, int n_samples, double *h_x, double *h_box, cudaStream_t stream) {
+    const int interval = n_samples > 0 ? n_steps / n_samples : n_steps + 1;
+    // the all-pairs potential now holds other atoms: a graph captured for the full system must not be replayed later
+    destroy_graph();
+    std::vector<std::shared_ptr<BoundPotential>> &pots = local_md_->potentials();
+    try {
+        for (int i = 1; i <= n_steps; i++) {
+            intg_->step_fwd(pots, d_x_.data, d_v_.data, d_box_.data, local_md_->free_idxs(), stream, -1);
+            if (i % interval == 0) {
+                double *xp = h_x + static_cast<size_t>(i / interval - 1) * N_ * 3;
+                double *bp = h_box + static_cast<size_t>(i / interval - 1) * 9;
+                TMB_CUDA(cudaMemcpyAsync(xp, d_x_.data, d_x_.bytes(), cudaMemcpyDeviceToHost, stream));
+                TMB_CUDA(cudaMemcpyAsync(bp, d_box_.data, d_box_.bytes(), cudaMemcpyDeviceToHost, stream));
+                TMB_CUDA(cudaStreamSynchronize(stream));
+                verify_frame(xp, bp);
+            }
+        }
+    } catch (...) {
+        cudaStreamSynchronize(stream);
+        local_md_->reset();
+        throw;
+    }
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    local_md_->reset();
+}
+
+void Context::multiple_steps_local(
+    int n_steps, const std::vector<int> &local_idxs, int n_samples, double radius, double k, int seed, double *h_x, double *h_box) {
+    if (n_samples < 0) {
+        throw std::runtime_error("n_samples < 0");
+    }
+    if (local_md_ == nullptr) {
+        setup_local_md(intg_->get_temperature(), true);
+    }
+    cudaStream_t stream = active_stream();
+    local_md_->setup_from_idxs(d_x_.data, d_box_.data, local_idxs, seed, radius, k, stream);
+    run_local_steps(n_steps, n_samples, h_x, h_box, stream);
+}
+
+void Context::multiple_steps_local_selection(
+    int n_steps, int reference_idx, const std::vector<int> &selection_idxs, int n_samples, double radius, double k, double *h_x,
+    double *h_box) {
+    if (n_samples < 0) {
+        throw std::runtime_error("n_samples < 0");
+    }
+    if (local_md_ == nullptr) {
+        setup_local_md(intg_->get_temperature(), true);
+    }
+    cudaStream_t stream = active_stream();
+    local_md_->setup_from_selection(reference_idx, selection_idxs, radius, k, stream);
+    run_local_steps(n_steps, n_samples, h_x, h_box, stream);
+}
+
 void Context::set_x_t(const double *h) { d_x_.copy_from(h); }
 void Context::set_v_t(const double *h) { d_v_.copy_from(h); }
 void Context::set_box(const double *h) { d_box_.copy_from(h); }

@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "kernels.hpp"
 
+struct curandGenerator_st; // <curand.h>, only local_md.cu and barostat.cu include it
+
 namespace tmb {
 
 // The stream host-level entry points run on (default: the legacy default stream, like the reference's
@@ -277,6 +279,7 @@ public:
     std::vector<float> drain_kernel_times(); // milliseconds per launch since the last drain (synchronises)
     void advance(int n) override { steps_since_last_sort_ += n; }
     double get_cutoff() const { return cutoff_; }
+    double get_beta() const { return beta_; }
     double get_nblist_padding() const { return nblist_padding_; }
     unsigned int num_tiles();
     unsigned int num_rebuilds(); // neighbour-list builds since construction (device counter; synchronises)
@@ -392,6 +395,38 @@ private:
 #include "barostat.hpp"
 namespace tmb {
 
+// Local MD: potentials and free-atom selection for simulating a shell around one reference atom (local_md.cu)
+class LocalMD {
+public:
+    LocalMD(int N, const std::vector<std::shared_ptr<BoundPotential>> &bps, bool freeze_reference, double temperature);
+    ~LocalMD();
+    const bool freeze_reference;
+    const double temperature;
+    // reference LocalMDPotentials::setup_from_idxs / setup_from_selection (local_md_potentials.cu:108-176)
+    void setup_from_idxs(const double *d_x, const double *d_box, const std::vector<int> &local_idxs, int seed, double radius,
+                         double k, cudaStream_t stream);
+    void setup_from_selection(int reference_idx, const std::vector<int> &selection_idxs, double radius, double k, cudaStream_t stream);
+    std::vector<std::shared_ptr<BoundPotential>> &potentials() { return active_; }
+    unsigned int *free_idxs() { return d_selected_.data; } // [N]: atom index if free, N if frozen (the integrator's idxs)
+    const std::vector<unsigned int> &selected_host() const { return h_selected_; }
+    int num_free() const { return num_free_; }
+    void reset(); // give the NonbondedAllPairs its original atoms back (local_md_potentials.cu:330-335)
+private:
+    int N_;
+    std::vector<std::shared_ptr<BoundPotential>> base_, active_;
+    std::shared_ptr<Potential> all_pairs_;
+    std::vector<int> original_idxs_;
+    std::shared_ptr<BoundPotential> ixn_group_, free_restraint_;
+    DeviceBuffer<float> d_uniforms_;
+    DeviceBuffer<unsigned int> d_selected_;
+    std::vector<unsigned int> h_selected_;
+    ::curandGenerator_st *rng_ = nullptr; // curandGenerator_t
+    int num_free_ = 0;
+    bool modified_ = false;
+    void set_all_pairs_idxs(const std::vector<int> &idxs);
+    void configure(unsigned int reference_idx, double radius, double k);
+};
+
 class Context {
 public:
     Context(int N, const double *x0, const double *v0, const double *box0, std::shared_ptr<LangevinIntegrator> intg,
@@ -403,6 +438,13 @@ public:
     void finalize() {}
     // n_samples frames of x/box are written to h_x/h_box (reference context.cu:216-242)
     void multiple_steps(int n_steps, int n_samples, double *h_x, double *h_box);
+    // local MD (reference context.cu:90-214); movers do not run during local steps
+    void setup_local_md(double temperature, bool freeze_reference);
+    void multiple_steps_local(int n_steps, const std::vector<int> &local_idxs, int n_samples, double radius, double k, int seed,
+                              double *h_x, double *h_box);
+    void multiple_steps_local_selection(int n_steps, int reference_idx, const std::vector<int> &selection_idxs, int n_samples,
+                                        double radius, double k, double *h_x, double *h_box);
+    const LocalMD *local_md() const { return local_md_.get(); }
     void set_x_t(const double *h);
     void set_v_t(const double *h);
     void set_box(const double *h);
@@ -439,6 +481,8 @@ private:
     void eager_step(cudaStream_t stream); // integrator step, then every mover (reference context.cu:261-277)
     void verify_frame(const double *h_x, const double *h_box) const;
     void destroy_graph();
+    std::unique_ptr<LocalMD> local_md_;
+    void run_local_steps(int n_steps, int n_samples, double *h_x, double *h_box, cudaStream_t stream);
 };
 
 void collect_nonbonded_cutoffs(const std::shared_ptr<Potential> &pot, std::vector<double> &out);

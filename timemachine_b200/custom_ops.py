@@ -820,6 +820,83 @@ class Context:
         _check(_L.tmb_context_multiple_steps(self._handle, n_steps, n_samples, _ptr(xs, C.c_double), _ptr(boxes, C.c_double)))
         return xs, boxes
 
+    # ---- local MD (wrap_kernels.cpp:368-612): a shell of atoms around one frozen reference atom is simulated -------------
+    @staticmethod
+    def _verify_local_md_parameters(radius: float, k: float) -> None:
+        """local_md_utils.cu:95-116"""
+        if radius < 0.1:
+            raise RuntimeError("radius must be greater or equal to 0.100000")
+        if k < 1.0:
+            raise RuntimeError("k must be at least one")
+        if k > 1e6:
+            raise RuntimeError("k must be less than than 1e+06")
+
+    def _verify_atom_idxs(self, idxs: np.ndarray) -> None:
+        """verify_atom_idxs (nonbonded_common.cpp): same checks and messages as the potentials' index arguments"""
+        if idxs.size == 0:
+            raise RuntimeError("indices can't be empty")
+        if np.unique(idxs).size != idxs.size:
+            raise RuntimeError("atom indices must be unique")
+        if idxs.max() >= self._n:
+            raise RuntimeError(f"index values must be less than N({self._n})")
+        if idxs.min() < 0:
+            raise RuntimeError("index values must be greater or equal to zero")
+
+    def setup_local_md(self, temperature: float, freeze_reference: bool) -> None:
+        """Configure local MD before its first use (default on first use: the integrator's temperature, frozen reference)."""
+        _check(_L.tmb_context_setup_local_md(self._handle, float(temperature), int(bool(freeze_reference))))
+
+    def _local_frames(self, n_steps: int, store_x_interval: int):
+        if n_steps <= 0:
+            raise RuntimeError("local steps must be at least one")
+        if store_x_interval < 0:
+            raise RuntimeError("store_x_interval must be greater than or equal to zero")
+        x_interval = n_steps if store_x_interval == 0 else int(store_x_interval)
+        n_samples = n_steps // x_interval
+        return n_samples, np.empty((n_samples, self._n, 3), dtype=np.float64), np.empty((n_samples, 3, 3), dtype=np.float64)
+
+    def multiple_steps_local(self, n_steps: int, local_idxs, store_x_interval: int = 0, radius: float = 1.2, k: float = 10000.0, seed: int = 2022):
+        """Steps of the atoms selected (with probability exp(-U_flat_bottom / kT)) around one atom drawn from local_idxs;
+        that atom and everything unselected stay frozen.  Movers (barostat) do not run.  Returns (xs, boxes)."""
+        n_steps = int(n_steps)
+        n_samples, xs, boxes = self._local_frames(n_steps, int(store_x_interval))
+        self._verify_local_md_parameters(float(radius), float(k))
+        idxs = _i32(local_idxs).reshape(-1)
+        self._verify_atom_idxs(idxs)
+        _check(
+            _L.tmb_context_multiple_steps_local(
+                self._handle, n_steps, _ptr(idxs, C.c_int32), idxs.size, n_samples, float(radius), float(k), int(seed),
+                _ptr(xs, C.c_double), _ptr(boxes, C.c_double),
+            )
+        )
+        return xs, boxes
+
+    def multiple_steps_local_selection(self, n_steps: int, reference_idx: int, selection_idxs, store_x_interval: int = 0, radius: float = 1.2, k: float = 10000.0):
+        """Steps of the given selection of free atoms, restrained to reference_idx by a flat-bottom bond."""
+        n_steps = int(n_steps)
+        n_samples, xs, boxes = self._local_frames(n_steps, int(store_x_interval))
+        self._verify_local_md_parameters(float(radius), float(k))
+        reference_idx = int(reference_idx)
+        if reference_idx < 0 or reference_idx >= self._n:
+            raise RuntimeError(f"reference idx must be at least 0 and less than {self._n}")
+        idxs = _i32(selection_idxs).reshape(-1)
+        self._verify_atom_idxs(idxs)
+        if reference_idx in set(idxs.tolist()):
+            raise RuntimeError("reference idx must not be in selection idxs")
+        _check(
+            _L.tmb_context_multiple_steps_local_selection(
+                self._handle, n_steps, reference_idx, _ptr(idxs, C.c_int32), idxs.size, n_samples, float(radius), float(k),
+                _ptr(xs, C.c_double), _ptr(boxes, C.c_double),
+            )
+        )
+        return xs, boxes
+
+    def local_md_free_idxs(self) -> np.ndarray:
+        """Atoms that were free in the last local MD call (introspection; not part of the reference API)."""
+        out = np.empty(self._n, dtype=np.uint32)
+        _check(_L.tmb_context_local_md_free_idxs(self._handle, _ptr(out, C.c_uint32)))
+        return np.flatnonzero(out < self._n).astype(np.int32)
+
     def set_x_t(self, coords) -> None:
         coords = _f64(coords)
         if coords.shape != (self._n, 3):
