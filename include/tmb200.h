@@ -66,6 +66,8 @@ int tmb_periodic_torsion_create(int precision, const int32_t *torsion_idxs, int 
  * NonbondedPairListPrecomputed_{f32,f64}(pair_idxs[M,2], beta, cutoff); params [M,4] = (q_ij, sig_ij, eps_ij, w_ij)
  *                                                                   wrap_kernels.cpp:1351-1364, nonbonded_precomputed.cu */
 int tmb_flat_bottom_bond_create(int precision, const int32_t *bond_idxs, int n_values, tmb_potential *out);
+/* LogFlatBottomBond_{f32,f64}(bond_idxs[B,2], beta)   wrap_kernels.cpp:1337-1349, log_flat_bottom_bond.cu; params [B,3] */
+int tmb_log_flat_bottom_bond_create(int precision, const int32_t *bond_idxs, int n_values, double beta, tmb_potential *out);
 int tmb_chiral_atom_restraint_create(int precision, const int32_t *idxs, int n_values, tmb_potential *out);
 int tmb_chiral_bond_restraint_create(
     int precision, const int32_t *idxs, int n_values, const int32_t *signs, int n_signs, tmb_potential *out);

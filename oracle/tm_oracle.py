@@ -646,6 +646,32 @@ def flat_bottom_bond(x, params, box, bond_idxs):
     return u, du_dx, du_dp
 
 
+def log_flat_bottom_bond(x, params, box, bond_idxs, beta):
+    """u = -sum log(1 - exp(-beta u_fb_b)) / beta over bonds (reference potentials/bonded.py:245-253, kernel
+    k_log_flat_bottom_bond.cuh:7-117); gradients are the flat-bottom ones scaled per bond by
+    -exp(-beta u_fb) / (1 - exp(-beta u_fb)).  Returns (u, du_dx, du_dp)."""
+    x = np.asarray(x, dtype=np.float64)
+    params = np.asarray(params, dtype=np.float64).reshape(-1, 3)
+    i, j = np.asarray(bond_idxs).reshape(-1, 2).T
+    d = delta_r(x[i], x[j], box)
+    r = np.linalg.norm(d, axis=1)
+    k, rmin, rmax = params.T
+    lo, hi = (r < rmin), (r > rmax)
+    dlo, dhi = r - rmin, r - rmax
+    nrg = k / 4 * (lo * dlo**4 + hi * dhi**4)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u = np.sum(-np.log(-np.expm1(-beta * nrg))) / beta
+        e = np.exp(-beta * nrg)
+        pre = -e / (1.0 - e)
+    du_dr = k * (lo * dlo**3 + hi * dhi**3)
+    g = (pre * du_dr / r)[:, None] * d
+    du_dx = np.zeros_like(x)
+    np.add.at(du_dx, i, g)
+    np.add.at(du_dx, j, -g)
+    du_dp = pre[:, None] * np.stack([(lo * dlo**4 + hi * dhi**4) / 4, lo * (-k * dlo**3), hi * (-k * dhi**3)], axis=1)
+    return u, du_dx, du_dp
+
+
 def _unit_and_jac(v):
     n = np.linalg.norm(v)
     u = v / n

@@ -188,6 +188,80 @@ def test_local_md_validation(system):
     ctx.setup_local_md(TEMPERATURE, True)  # same parameters: fine
     with pytest.raises(RuntimeError, match="local md configured with different parameters"):
         ctx.setup_local_md(TEMPERATURE + 1.0, True)
-    other = make_context(s)
-    with pytest.raises(RuntimeError, match="freeze_reference = false is not built"):
-        other.setup_local_md(TEMPERATURE, False)
+
+
+def test_unfrozen_reference_variant(system):
+    """setup_local_md(temperature, freeze_reference=False): the reference atom moves too, the frozen shell is tied to it by
+    a LogFlatBottomBond.  One step against the definition (bitwise), then against the compiled reference."""
+    ops, lib, P = mods()
+    s = system
+    N, ref_idx, radius, k = s["N"], 600, 0.6, 3000.0
+    ctx = make_context(s)
+    ctx.setup_local_md(TEMPERATURE, False)
+    xs, _ = ctx.multiple_steps_local(1, np.array([ref_idx], dtype=np.int32), radius=radius, k=k, seed=21)
+    free = ctx.local_md_free_idxs()
+    frozen = np.setdiff1d(np.arange(N), free)
+    assert ref_idx in free and len(frozen) > 100
+    np.testing.assert_array_equal(xs[0][frozen], s["x"][frozen])
+    fixed = np.zeros((N, 3), dtype=np.int64)
+    for bp in make_context(s).get_potentials():
+        fixed += np.rint(bp.execute(s["x"], s["box"])[0] * 2.0**36).astype(np.int64)
+    others = free[free != ref_idx]
+    fb = P.FlatBottomBond(np.stack([np.full(len(others), ref_idx), others], 1).astype(np.int32)).to_gpu(np.float32).unbound_impl
+    fixed += np.rint(fb.execute(s["x"], np.tile([k, 0.0, radius], (len(others), 1)), s["box"])[0] * 2.0**36).astype(np.int64)
+    beta = 1.0 / (0.008314462618 * TEMPERATURE)
+    lfb = P.LogFlatBottomBond(np.stack([np.full(len(frozen), ref_idx), frozen], 1).astype(np.int32), beta).to_gpu(np.float32).unbound_impl
+    fixed += np.rint(lfb.execute(s["x"], np.tile([k, 0.0, radius], (len(frozen), 1)), s["box"])[0] * 2.0**36).astype(np.int64)
+    x1, v1 = O.baoab_step_mixed(s["x"], s["v"], fixed.view(np.uint64), s["masses"], TEMPERATURE, DT, 0.0, np.zeros((N, 3), np.float32))
+    np.testing.assert_array_equal(xs[0][free], x1[free])
+
+    ref = load_reference_ops()
+    if ref is not None:
+        ours, theirs = make_context(s), make_context(s, module=ref)
+        ours.setup_local_md(TEMPERATURE, False)
+        theirs.setup_local_md(TEMPERATURE, False)
+        local_idxs = np.array([ref_idx, 77], dtype=np.int32)
+        a, _ = ours.multiple_steps_local(20, local_idxs, radius=radius, k=k, seed=8)
+        b, _ = theirs.multiple_steps_local(20, local_idxs, 0, radius, k, 8)
+        np.testing.assert_array_equal(np.any(a[-1] != s["x"], axis=1), np.any(b[-1] != s["x"], axis=1))
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+
+
+def test_log_flat_bottom_bond_potential():
+    """LogFlatBottomBond_{f32,f64} against the oracle (pinned to the reference's Python potential) and, where built, the
+    compiled reference; argument checks with the reference's messages."""
+    from pathlib import Path
+
+    ops, lib, P = mods()
+    g = np.load(Path(__file__).parent / "golden" / "log_flat_bottom_bond.npz")
+    x, box, idxs, params, beta = g["x"], g["box"], g["idxs"], g["params"], float(g["beta"])
+    ref_u, ref_dx, ref_dp = O.log_flat_bottom_bond(x, params, box, idxs, beta)
+    np.testing.assert_allclose(ref_u, g["u"], rtol=1e-12)
+    for precision, rtol in ((np.float64, 1e-9), (np.float32, 2e-4)):
+        impl = P.LogFlatBottomBond(idxs, beta).to_gpu(precision).unbound_impl
+        xx, pp = (x, params) if precision == np.float64 else (round_to_f32(x), round_to_f32(params))
+        ou, odx, odp = O.log_flat_bottom_bond(xx, pp, box, idxs, beta)
+        dx, dp, u = impl.execute(xx, pp, box)
+        np.testing.assert_allclose(u, ou, rtol=rtol)
+        np.testing.assert_allclose(dx, odx, rtol=rtol, atol=rtol * np.abs(odx).max())
+        np.testing.assert_allclose(dp, odp, rtol=rtol, atol=rtol * np.abs(odp).max())
+        dx2, dp2, u2 = impl.execute(xx, pp, box)
+        np.testing.assert_array_equal(dx, dx2)
+        assert u == u2
+        assert impl.execute(xx, pp, box, True, False, False)[2] is None
+    ref = load_reference_ops()
+    if ref is not None:
+        rimpl = ref.LogFlatBottomBond_f32(idxs, beta)
+        rdx, rdp, ru = rimpl.execute(round_to_f32(x), round_to_f32(params), box, True, True, True)
+        dx, dp, u = P.LogFlatBottomBond(idxs, beta).to_gpu(np.float32).unbound_impl.execute(round_to_f32(x), round_to_f32(params), box)
+        np.testing.assert_allclose(u, ru, rtol=1e-5)
+        np.testing.assert_allclose(dx, rdx, rtol=1e-5, atol=1e-5 * np.abs(rdx).max())
+        np.testing.assert_allclose(dp, rdp, rtol=1e-5, atol=1e-5 * np.abs(rdp).max())
+    with pytest.raises(RuntimeError, match="beta must be positive"):
+        ops.LogFlatBottomBond_f32(idxs, 0.0)
+    with pytest.raises(RuntimeError, match="bond_idxs.size\(\) must be exactly 2\*k!"):
+        ops.LogFlatBottomBond_f32(np.array([0, 1, 2], dtype=np.int32), 1.0)
+    with pytest.raises(RuntimeError, match="src == dst"):
+        ops.LogFlatBottomBond_f32(np.array([[1, 1]], dtype=np.int32), 1.0)
+    with pytest.raises(RuntimeError, match="LogFlatBottomBond::execute_device\(\): expected P == 90, got P=3"):
+        ops.LogFlatBottomBond_f32(idxs, 1.0).execute(x, params[:1], box)

@@ -58,3 +58,19 @@ def test_volume_gradients_against_finite_differences():
                 fd = (fn(*hp)[0] - fn(*hm)[0]) / 2e-6
                 assert grads[a][c] == pytest.approx(fd, abs=1e-7)
         np.testing.assert_allclose(np.sum(grads, axis=0), 0, atol=1e-12)  # translation invariance
+
+
+def test_log_flat_bottom_bond_matches_reference_python():
+    """oracle.log_flat_bottom_bond against the reference's `log_flat_bottom_bond` (bonded.py:245-253), executed by
+    tests/golden/make_golden_logfb.py; gradients against finite differences of the reference energy."""
+    from pathlib import Path
+
+    import numpy as np
+
+    from oracle import tm_oracle as O
+
+    g = np.load(Path(__file__).parent / "golden" / "log_flat_bottom_bond.npz")
+    u, du_dx, du_dp = O.log_flat_bottom_bond(g["x"], g["params"], g["box"], g["idxs"], float(g["beta"]))
+    np.testing.assert_allclose(u, g["u"], rtol=1e-12)
+    np.testing.assert_allclose(du_dx, g["du_dx_fd"], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(du_dp, g["du_dp_fd"], rtol=2e-5, atol=1e-6)

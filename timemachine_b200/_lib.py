@@ -42,6 +42,7 @@ SIGNATURES = {
     "tmb_harmonic_angle_create": [_int, _p_i32, _int, _ph],
     "tmb_periodic_torsion_create": [_int, _p_i32, _int, _ph],
     "tmb_flat_bottom_bond_create": [_int, _p_i32, _int, _ph],
+    "tmb_log_flat_bottom_bond_create": [_int, _p_i32, _int, _dbl, _ph],
     "tmb_chiral_atom_restraint_create": [_int, _p_i32, _int, _ph],
     "tmb_chiral_bond_restraint_create": [_int, _p_i32, _int, _p_i32, _int, _ph],
     "tmb_nonbonded_pair_list_precomputed_create": [_int, _p_i32, _int, _dbl, _dbl, _ph],

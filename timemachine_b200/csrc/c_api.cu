@@ -157,6 +157,9 @@ int tmb_periodic_torsion_create(int precision, const int32_t *torsion_idxs, int 
 int tmb_flat_bottom_bond_create(int precision, const int32_t *bond_idxs, int n_values, tmb_potential *out) {
     return create_restraint<FlatBottomBond>(precision, bond_idxs, n_values, nullptr, 0, 0.0, 0.0, out);
 }
+int tmb_log_flat_bottom_bond_create(int precision, const int32_t *bond_idxs, int n_values, double beta, tmb_potential *out) {
+    return create_restraint<LogFlatBottomBond>(precision, bond_idxs, n_values, nullptr, 0, beta, 0.0, out);
+}
 int tmb_chiral_atom_restraint_create(int precision, const int32_t *idxs, int n_values, tmb_potential *out) {
     return create_restraint<ChiralAtomRestraint>(precision, idxs, n_values, nullptr, 0, 0.0, 0.0, out);
 }

@@ -121,6 +121,63 @@ template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_flat_bo
     }
 }
 
+// ---- log flat-bottom bond: u = -log(1 - exp(-beta u_fb)) / beta (reference k_log_flat_bottom_bond.cuh:7-117) ---------------
+// The restraint local MD puts on the FROZEN shell when its reference atom moves: it diverges where the flat-bottom energy
+// vanishes.  log(1 - exp(-x)) is evaluated as log(-expm1(-x)) below log 2 and log1p(-exp(-x)) above, like the reference.
+template <typename Real> __device__ __forceinline__ Real log_1_exp_neg(Real x) {
+    return x < static_cast<Real>(0.693147180559945309417232121) ? log(-expm1(-x)) : log1p(-exp(-x));
+}
+
+template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_log_flat_bottom_bond(const RestraintArgs a) {
+    __shared__ i128 scratch[RS_THREADS / WARP];
+    i128 energy = 0;
+    const Real beta = static_cast<Real>(a.beta);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.b.n_terms; b += gridDim.x * blockDim.x) {
+        const int src = a.b.idxs[b * 2 + 0], dst = a.b.idxs[b * 2 + 1];
+        const Real k = static_cast<Real>(a.b.p[b * 3 + 0]);
+        const Real rmin = static_cast<Real>(a.b.p[b * 3 + 1]);
+        const Real rmax = static_cast<Real>(a.b.p[b * 3 + 2]);
+        Real dx[3];
+        Real r2 = 0;
+        for (int d = 0; d < 3; d++) {
+            double delta = a.b.x[src * 3 + d] - a.b.x[dst * 3 + d];
+            const double bd = a.box[d * 3 + d];
+            delta -= bd * nearbyint(delta / bd);
+            dx[d] = static_cast<Real>(delta);
+            r2 = static_cast<Real>(static_cast<double>(r2) + delta * delta);
+        }
+        const Real r = sqrt(r2);
+        const Real above = static_cast<Real>(r > rmax), below = static_cast<Real>(r < rmin);
+        const Real d_min = r - rmin, d_max = r - rmax;
+        const Real d_min2 = d_min * d_min, d_max2 = d_max * d_max;
+        const Real nrg = (k / 4) * ((below * (d_min2 * d_min2)) + (above * (d_max2 * d_max2)));
+        if (a.b.d_u != nullptr) {
+            energy += energy_to_fixed<Real>(-log_1_exp_neg<Real>(beta * nrg) / beta);
+        }
+        // d/d(nrg) of the log form: -exp(-beta nrg) / (1 - exp(-beta nrg)); every flat-bottom gradient is scaled by it
+        Real pre = -exp(-beta * nrg);
+        pre = pre / (static_cast<Real>(1) + pre);
+        const Real d_min3 = d_min2 * d_min, d_max3 = d_max2 * d_max;
+        if (a.b.du_dp != nullptr) {
+            atomicAdd(a.b.du_dp + b * 3 + 0, to_fixed_force((above * ((d_max3 * d_max) / 4) + below * ((d_min3 * d_min) / 4)) * pre));
+            atomicAdd(a.b.du_dp + b * 3 + 1, to_fixed_force((below * (-k * d_min3)) * pre));
+            atomicAdd(a.b.du_dp + b * 3 + 2, to_fixed_force((above * (-k * d_max3)) * pre));
+        }
+        if (a.b.du_dx != nullptr) {
+            const Real du_dr = k * ((above * d_max3) + (below * d_min3));
+            const Real inv_r = 1 / r;
+            for (int d = 0; d < 3; d++) {
+                const Real g = du_dr * dx[d] * inv_r;
+                atomicAdd(a.b.du_dx + src * 3 + d, to_fixed_force(pre * g));
+                atomicAdd(a.b.du_dx + dst * 3 + d, to_fixed_force(pre * (-g)));
+            }
+        }
+    }
+    if (a.b.d_u != nullptr) {
+        grid_finish_energy(energy, scratch, a.b.u_partials, a.b.ticket, a.b.d_u);
+    }
+}
+
 // ---- chiral atom restraint: vol = (x^ x y^) . z^ around a centre; u = k vol^2 where vol > 0 ------------------------
 template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_chiral_atom_restraint(const RestraintArgs a) {
     __shared__ i128 scratch[RS_THREADS / WARP];
@@ -294,6 +351,7 @@ template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_nonbond
     template void name<double>(const RestraintArgs &, cudaStream_t);
 
 TMB_RESTRAINT_LAUNCHER(launch_flat_bottom_bond, k_flat_bottom_bond)
+TMB_RESTRAINT_LAUNCHER(launch_log_flat_bottom_bond, k_log_flat_bottom_bond)
 TMB_RESTRAINT_LAUNCHER(launch_chiral_atom_restraint, k_chiral_atom_restraint)
 TMB_RESTRAINT_LAUNCHER(launch_chiral_bond_restraint, k_chiral_bond_restraint)
 TMB_RESTRAINT_LAUNCHER(launch_nonbonded_precomputed, k_nonbonded_precomputed)

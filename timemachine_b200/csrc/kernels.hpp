@@ -169,10 +169,11 @@ struct RestraintArgs {
     BondedArgs b;
     const double *box = nullptr; // flat-bottom bond, precomputed pairs
     const int *signs = nullptr;  // chiral bond restraint [R]
-    double beta = 0;             // precomputed pairs
+    double beta = 0;             // precomputed pairs; log flat-bottom bond (1 / kT)
     double cutoff = 0;
 };
 template <typename Real> void launch_flat_bottom_bond(const RestraintArgs &args, cudaStream_t stream);
+template <typename Real> void launch_log_flat_bottom_bond(const RestraintArgs &args, cudaStream_t stream);
 template <typename Real> void launch_chiral_atom_restraint(const RestraintArgs &args, cudaStream_t stream);
 template <typename Real> void launch_chiral_bond_restraint(const RestraintArgs &args, cudaStream_t stream);
 template <typename Real> void launch_nonbonded_precomputed(const RestraintArgs &args, cudaStream_t stream);

@@ -8,6 +8,8 @@
 //   potentials  every potential of the context as it is (bonded terms, exclusions: forces on frozen atoms are computed
 //               and ignored), the NonbondedAllPairs restricted to the free atoms, plus a NonbondedInteractionGroup
 //               free x frozen and a FlatBottomBond (k, 0, radius) from every free atom to the reference atom.
+//               freeze_reference = false: the reference atom moves too, and a LogFlatBottomBond (beta = 1 / kT, same
+//               k and radius) between it and every frozen atom keeps it from dragging the shell over frozen atoms.
 //   integrator  BAOAB over the free atoms only (k_baoab with an index array; frozen entries are N).
 //
 // The reference keeps all index bookkeeping on the device (cub::DevicePartition) but synchronises the stream to read the
@@ -99,11 +101,6 @@ LocalMD::LocalMD(int N, const std::vector<std::shared_ptr<BoundPotential>> &bps,
     if (temperature <= 0.0) {
         throw std::runtime_error("temperature must be greater than 0");
     }
-    if (!freeze_reference) {
-        // the unfrozen-reference variant restrains the frozen shell with a LogFlatBottomBond (local_md_potentials.cu:76-81),
-        // a potential this library does not have yet
-        throw std::runtime_error("local MD with freeze_reference = false is not built (needs LogFlatBottomBond)");
-    }
     if (N < 2) {
         throw std::runtime_error("N must be greater than 1");
     }
@@ -175,8 +172,13 @@ void LocalMD::setup_from_selection(int reference_idx, const std::vector<int> &se
 }
 
 void LocalMD::configure(unsigned int reference_idx, double radius, double k) {
+    if (!freeze_reference) {
+        // the reference atom is integrated as well (local_md_potentials.cu:184-189)
+        h_selected_[reference_idx] = reference_idx;
+        TMB_CUDA(cudaMemcpy(d_selected_.data + reference_idx, &reference_idx, sizeof(unsigned int), cudaMemcpyHostToDevice));
+    }
     // free atoms that the all-pairs term knows about become its (and the interaction group's row) atoms; the rest of its
-    // atoms, the reference among them, are the columns (local_md_potentials.cu:190-300)
+    // atoms (the reference among them when it is frozen) are the columns (local_md_potentials.cu:190-300)
     std::vector<int> rows, cols;
     for (int a : original_idxs_) {
         (h_selected_[a] < static_cast<unsigned int>(N_) ? rows : cols).push_back(a);
@@ -184,33 +186,50 @@ void LocalMD::configure(unsigned int reference_idx, double radius, double k) {
     if (rows.empty()) {
         throw std::runtime_error("LocalMDPotentials setup has no free particles selected");
     }
-    if (static_cast<int>(rows.size()) == N_ - 1) {
+    const int n_rows = static_cast<int>(rows.size());
+    if (n_rows == N_ - 1 || (!freeze_reference && n_rows == N_)) {
         fprintf(stderr, "LocalMDPotentials setup has entire system selected\n");
     }
     set_all_pairs_idxs(rows);
     modified_ = true;
-    if (auto f = std::dynamic_pointer_cast<NonbondedInteractionGroup<float>>(ixn_group_->potential)) {
-        f->set_atom_idxs(rows, cols);
-    } else {
-        std::dynamic_pointer_cast<NonbondedInteractionGroup<double>>(ixn_group_->potential)->set_atom_idxs(rows, cols);
+    if (!cols.empty()) {
+        if (auto f = std::dynamic_pointer_cast<NonbondedInteractionGroup<float>>(ixn_group_->potential)) {
+            f->set_atom_idxs(rows, cols);
+        } else {
+            std::dynamic_pointer_cast<NonbondedInteractionGroup<double>>(ixn_group_->potential)->set_atom_idxs(rows, cols);
+        }
     }
+    auto bonds_to_reference = [&](const std::vector<int> &atoms, std::vector<int> &bonds, std::vector<double> &params) {
+        for (int a : atoms) {
+            if (a == static_cast<int>(reference_idx)) {
+                continue; // the reference builds a (reference, reference) bond here, which contributes nothing
+            }
+            bonds.push_back(static_cast<int>(reference_idx));
+            bonds.push_back(a);
+            params.push_back(k);
+            params.push_back(0.0);
+            params.push_back(radius);
+        }
+    };
     std::vector<int> bonds;
     std::vector<double> params;
-    bonds.reserve(2 * rows.size());
-    params.reserve(3 * rows.size());
-    for (int a : rows) {
-        bonds.push_back(static_cast<int>(reference_idx));
-        bonds.push_back(a);
-        params.push_back(k);
-        params.push_back(0.0);
-        params.push_back(radius);
-    }
+    bonds_to_reference(rows, bonds, params);
     auto restraint = std::make_shared<FlatBottomBond<float>>(bonds, std::vector<int>{}, 0.0, 0.0);
     free_restraint_ = std::make_shared<BoundPotential>(restraint, params);
     active_ = base_;
     active_.push_back(free_restraint_);
-    active_.push_back(ixn_group_);
-    num_free_ = static_cast<int>(rows.size());
+    if (!cols.empty()) {
+        active_.push_back(ixn_group_);
+    }
+    if (!freeze_reference && !cols.empty()) {
+        std::vector<int> fbonds;
+        std::vector<double> fparams;
+        bonds_to_reference(cols, fbonds, fparams);
+        auto frozen = std::make_shared<LogFlatBottomBond<float>>(fbonds, std::vector<int>{}, 1.0 / (0.008314462618 * temperature), 0.0);
+        frozen_restraint_ = std::make_shared<BoundPotential>(frozen, fparams);
+        active_.push_back(frozen_restraint_);
+    }
+    num_free_ = n_rows;
 }
 
 void LocalMD::reset() {

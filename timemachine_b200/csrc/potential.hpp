@@ -177,12 +177,13 @@ template <typename Real> using PeriodicTorsion = BondedPotential<Real, BondedKin
 
 // Restraints + precomputed pair list (reference flat_bottom_bond.hpp, chiral_atom_restraint.hpp,
 // chiral_bond_restraint.hpp, nonbonded_precomputed.hpp)
-enum class RestraintKind { FlatBottomBond, ChiralAtom, ChiralBond, PrecomputedPairs };
+enum class RestraintKind { FlatBottomBond, ChiralAtom, ChiralBond, PrecomputedPairs, LogFlatBottomBond };
 
 template <typename Real, RestraintKind KIND> class RestraintPotential : public Potential {
 public:
-    static constexpr int ARITY = (KIND == RestraintKind::FlatBottomBond || KIND == RestraintKind::PrecomputedPairs) ? 2 : 4;
-    static constexpr int PARAMS = KIND == RestraintKind::FlatBottomBond ? 3 : (KIND == RestraintKind::PrecomputedPairs ? 4 : 1);
+    static constexpr bool IS_FB = KIND == RestraintKind::FlatBottomBond || KIND == RestraintKind::LogFlatBottomBond;
+    static constexpr int ARITY = (IS_FB || KIND == RestraintKind::PrecomputedPairs) ? 2 : 4;
+    static constexpr int PARAMS = IS_FB ? 3 : (KIND == RestraintKind::PrecomputedPairs ? 4 : 1);
     RestraintPotential(const std::vector<int> &idxs, const std::vector<int> &signs, double beta, double cutoff);
     void execute_device(int, int, const double *, const double *, const double *, u64 *, u64 *, i128 *, cudaStream_t) override;
     void du_dp_fixed_to_float(int N, int P, const u64 *du_dp, double *out) const override;
@@ -195,6 +196,8 @@ private:
     DeviceBuffer<unsigned int> d_ticket_;
 };
 template <typename Real> using FlatBottomBond = RestraintPotential<Real, RestraintKind::FlatBottomBond>;
+// LogFlatBottomBond(bond_idxs, beta): reference log_flat_bottom_bond.cu (the (idxs, signs, beta, cutoff) ctor with beta)
+template <typename Real> using LogFlatBottomBond = RestraintPotential<Real, RestraintKind::LogFlatBottomBond>;
 template <typename Real> using ChiralAtomRestraint = RestraintPotential<Real, RestraintKind::ChiralAtom>;
 template <typename Real> using ChiralBondRestraint = RestraintPotential<Real, RestraintKind::ChiralBond>;
 template <typename Real> using NonbondedPairListPrecomputed = RestraintPotential<Real, RestraintKind::PrecomputedPairs>;
@@ -416,7 +419,7 @@ private:
     std::vector<std::shared_ptr<BoundPotential>> base_, active_;
     std::shared_ptr<Potential> all_pairs_;
     std::vector<int> original_idxs_;
-    std::shared_ptr<BoundPotential> ixn_group_, free_restraint_;
+    std::shared_ptr<BoundPotential> ixn_group_, free_restraint_, frozen_restraint_;
     DeviceBuffer<float> d_uniforms_;
     DeviceBuffer<unsigned int> d_selected_;
     std::vector<unsigned int> h_selected_;

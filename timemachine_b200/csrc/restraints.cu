@@ -10,9 +10,13 @@ template <typename Real, RestraintKind KIND>
 RestraintPotential<Real, KIND>::RestraintPotential(
     const std::vector<int> &idxs, const std::vector<int> &signs, double beta, double cutoff)
     : n_terms_(static_cast<int>(idxs.size() / ARITY)), beta_(beta), cutoff_(cutoff) {
+    if (KIND == RestraintKind::LogFlatBottomBond && beta <= 0) {
+        throw std::runtime_error("beta must be positive"); // log_flat_bottom_bond.cu:15-17
+    }
     if (idxs.size() % ARITY != 0) {
         switch (KIND) {
         case RestraintKind::FlatBottomBond:
+        case RestraintKind::LogFlatBottomBond:
             throw std::runtime_error("bond_idxs.size() must be exactly 2*k!");
         case RestraintKind::ChiralAtom:
             throw std::runtime_error("idxs.size() must be exactly 4*k!");
@@ -32,16 +36,16 @@ RestraintPotential<Real, KIND>::RestraintPotential(
             }
         }
     }
-    if (KIND == RestraintKind::FlatBottomBond || KIND == RestraintKind::PrecomputedPairs) {
+    if (IS_FB || KIND == RestraintKind::PrecomputedPairs) {
         for (int t = 0; t < n_terms_; t++) {
             const int src = idxs[t * 2 + 0], dst = idxs[t * 2 + 1];
             if (src == dst) {
-                if (KIND == RestraintKind::FlatBottomBond) {
+                if (IS_FB) {
                     throw std::runtime_error("src == dst");
                 }
                 throw std::runtime_error("illegal pair with src == dst: " + std::to_string(src) + ", " + std::to_string(dst));
             }
-            if (KIND == RestraintKind::FlatBottomBond && (src < 0 || dst < 0)) {
+            if (IS_FB && (src < 0 || dst < 0)) {
                 throw std::runtime_error("idxs must be non-negative");
             }
         }
@@ -72,6 +76,9 @@ void RestraintPotential<Real, KIND>::execute_device(
         case RestraintKind::FlatBottomBond:
             throw std::runtime_error(
                 "FlatBottomBond::execute_device(): expected P == " + std::to_string(expected) + ", got P=" + std::to_string(P));
+        case RestraintKind::LogFlatBottomBond:
+            throw std::runtime_error(
+                "LogFlatBottomBond::execute_device(): expected P == " + std::to_string(expected) + ", got P=" + std::to_string(P));
         case RestraintKind::ChiralAtom:
             throw std::runtime_error(
                 "ChiralAtomRestraint::execute_device(): expected P == R, got P=" + std::to_string(P) +
@@ -107,6 +114,9 @@ void RestraintPotential<Real, KIND>::execute_device(
     case RestraintKind::FlatBottomBond:
         launch_flat_bottom_bond<Real>(a, stream);
         break;
+    case RestraintKind::LogFlatBottomBond:
+        launch_log_flat_bottom_bond<Real>(a, stream);
+        break;
     case RestraintKind::ChiralAtom:
         launch_chiral_atom_restraint<Real>(a, stream);
         break;
@@ -135,5 +145,6 @@ TMB_INSTANTIATE(RestraintKind::FlatBottomBond)
 TMB_INSTANTIATE(RestraintKind::ChiralAtom)
 TMB_INSTANTIATE(RestraintKind::ChiralBond)
 TMB_INSTANTIATE(RestraintKind::PrecomputedPairs)
+TMB_INSTANTIATE(RestraintKind::LogFlatBottomBond)
 
 } // namespace tmb

@@ -281,6 +281,27 @@ ChiralAtomRestraint_f32 = _make_bonded("ChiralAtomRestraint_f32", _L.tmb_chiral_
 ChiralAtomRestraint_f64 = _make_bonded("ChiralAtomRestraint_f64", _L.tmb_chiral_atom_restraint_create, F64)
 
 
+class _LogFlatBottomBond(Potential):
+    """LogFlatBottomBond_{f32,f64}(bond_idxs[B,2], beta): -log(1 - exp(-beta u_flat_bottom)) / beta; params [B,3] = (k, r_min,
+    r_max) (wrap_kernels.cpp:1337-1349)."""
+
+    _precision = F32
+
+    def __init__(self, bond_idxs, beta):
+        idxs = _i32(bond_idxs)
+        h = _new_handle()
+        _check(_L.tmb_log_flat_bottom_bond_create(self._precision, _ptr(idxs, C.c_int32), idxs.size, float(beta), C.byref(h)))
+        self._adopt(h)
+
+
+class LogFlatBottomBond_f32(_LogFlatBottomBond):
+    _precision = F32
+
+
+class LogFlatBottomBond_f64(_LogFlatBottomBond):
+    _precision = F64
+
+
 class _ChiralBondRestraint(Potential):
     """ChiralBondRestraint_{f32,f64}(idxs[R,4], signs[R]) (wrap_kernels.cpp:1380-1394)."""
 

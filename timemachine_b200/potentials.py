@@ -93,6 +93,14 @@ class FlatBottomBond(Potential):
 
 
 @dataclass
+class LogFlatBottomBond(Potential):
+    """potentials.py:85-91"""
+
+    idxs: np.ndarray
+    beta: float
+
+
+@dataclass
 class ChiralAtomRestraint(Potential):
     """potentials.py:60-66"""
 
