@@ -259,9 +259,9 @@ def test_log_flat_bottom_bond_potential():
         np.testing.assert_allclose(dp, rdp, rtol=1e-5, atol=1e-5 * np.abs(rdp).max())
     with pytest.raises(RuntimeError, match="beta must be positive"):
         ops.LogFlatBottomBond_f32(idxs, 0.0)
-    with pytest.raises(RuntimeError, match="bond_idxs.size\(\) must be exactly 2\*k!"):
+    with pytest.raises(RuntimeError, match=r"bond_idxs.size\(\) must be exactly 2\*k!"):
         ops.LogFlatBottomBond_f32(np.array([0, 1, 2], dtype=np.int32), 1.0)
     with pytest.raises(RuntimeError, match="src == dst"):
         ops.LogFlatBottomBond_f32(np.array([[1, 1]], dtype=np.int32), 1.0)
-    with pytest.raises(RuntimeError, match="LogFlatBottomBond::execute_device\(\): expected P == 90, got P=3"):
+    with pytest.raises(RuntimeError, match=r"LogFlatBottomBond::execute_device\(\): expected P == 90, got P=3"):
         ops.LogFlatBottomBond_f32(idxs, 1.0).execute(x, params[:1], box)
