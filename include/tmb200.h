@@ -34,6 +34,7 @@ typedef void *tmb_integrator;      /* std::shared_ptr<LangevinIntegrator>   (wra
 typedef void *tmb_context;         /* Context                               (wrap_kernels.cpp:296) */
 typedef void *tmb_neighborlist;    /* Neighborlist<float|double>            (wrap_kernels.cpp:113) */
 typedef void *tmb_hilbert_sort;    /* HilbertSort                           (wrap_kernels.cpp:174) */
+typedef void *tmb_sampler;         /* SegmentedWeightedRandomSampler        (wrap_kernels.cpp:196) */
 typedef void *tmb_mover;           /* std::shared_ptr<Mover>                (wrap_kernels.cpp:1591 declare_mover) */
 
 #define TMB_OK 0
@@ -183,6 +184,59 @@ int tmb_barostat_set_pressure(tmb_mover m, double pressure);     /* :1658 */
 /* introspection for the parity tests: the two cuRAND uniforms of the last attempted move; {attempted, accepted} */
 int tmb_barostat_last_uniforms(tmb_mover m, float *out2);
 int tmb_barostat_counters(tmb_mover m, int *out2);
+
+/* ---- Water exchange by biased deletion      wrap_kernels.cpp:196-294, 1693-1900, 2004-2117 ----- */
+/* Molecules are passed flattened like the barostat's groups: atoms of molecule m are mol_atoms[mol_offsets[m] ..
+ * mol_offsets[m+1]).  Real-typed results are returned widened to double.  precision: TMB_F32 / TMB_F64. */
+/* BDExchangeMove_{f32,f64}(N, target_mols, params[N,4], temperature, nb_beta, cutoff, seed, num_proposals_per_move,
+ * interval, batch_size=1)                                            wrap_kernels.cpp:1732-1795, bd_exchange_move.cu */
+int tmb_bd_exchange_move_create(
+    int precision, int N, const int *mol_atoms, const int *mol_offsets, int n_mols, const double *params, int n_params,
+    double temperature, double nb_beta, double cutoff, int seed, int num_proposals_per_move, int interval, int batch_size,
+    tmb_mover *out);
+int tmb_bd_exchange_move_num_target_mols(tmb_mover m, int *out);
+int tmb_bd_exchange_move_batch_size(tmb_mover m, int *out);                      /* :1899 */
+/* compute_initial_log_weights(coords, box) -> [num_target_mols]       :1862-1873 */
+int tmb_bd_exchange_move_initial_log_weights(tmb_mover m, int N, const double *coords, const double *box, double *out);
+/* compute_incremental_log_weights(coords, box, mol_idxs[B], quaternions[B,4], translations[B,3]) -> [B, num_target_mols]
+ * (translations are used as given, not scaled by the box)             :1818-1861 */
+int tmb_bd_exchange_move_incremental_log_weights(
+    tmb_mover m, int N, const double *coords, const double *box, const int *mol_idxs, const double *quaternions,
+    const double *translations, double *out);
+int tmb_bd_exchange_move_get_params(tmb_mover m, double *out, int n_params);    /* :1874-1882 */
+int tmb_bd_exchange_move_set_params(tmb_mover m, const double *params, int n_params); /* :1883-1888 */
+int tmb_bd_exchange_move_last_log_probability(tmb_mover m, double *out);        /* :1889-1892 */
+int tmb_bd_exchange_move_last_raw_log_probability(tmb_mover m, double *out);    /* :1893 */
+int tmb_bd_exchange_move_n_accepted(tmb_mover m, unsigned long long *out);      /* :1894 */
+int tmb_bd_exchange_move_n_proposed(tmb_mover m, unsigned long long *out);      /* :1895 */
+int tmb_bd_exchange_move_before_log_weights(tmb_mover m, double *out);          /* [num_target_mols]      :1897 */
+int tmb_bd_exchange_move_after_log_weights(tmb_mover m, double *out);           /* [B * num_target_mols]  :1898 */
+/* NonbondedMolEnergyPotential_{f32,f64}(N, target_mols, beta, cutoff).execute(coords, params, box) -> [n_mols] fixed
+ * point energies (int128, 2^36).  coords == NULL: construct and validate only.   wrap_kernels.cpp:234-294 */
+int tmb_nonbonded_mol_energies(
+    int precision, int N, const int *mol_atoms, const int *mol_offsets, int n_mols, double beta, double cutoff,
+    const double *coords, const double *params, const double *box, tmb_i128 *out);
+/* atom_by_atom_energies_{f32,f64}(target_atoms[T], coords, params, box, nb_beta, cutoff) -> [T, N]   :2004-2030 */
+int tmb_atom_by_atom_energies(
+    int precision, int N, const int *target_atoms, int T, const double *coords, const double *params, const double *box,
+    double nb_beta, double cutoff, double *out);
+/* SegmentedSumExp_{f32,f64}(max_vals_per_segment, num_segments).logsumexp(values): segment s holds
+ * values[offsets[s] .. offsets[s+1])                                 :1693-1730, segmented_sumexp.cu:69-117 */
+int tmb_segmented_logsumexp(
+    int precision, int max_vals_per_segment, int num_segments_max, const double *values, const int *offsets,
+    int num_segments, double *out);
+/* SegmentedWeightedRandomSampler_{f32,f64}(max_vals_per_segment, segments, seed).sample(weights) -> [segments]
+ * (the cuRAND stream advances by max_vals_per_segment * segments uniforms per call, as in the reference)   :196-232 */
+int tmb_weighted_sampler_create(int precision, int max_vals_per_segment, int num_segments, int seed, tmb_sampler *out);
+int tmb_weighted_sampler_destroy(tmb_sampler s);
+int tmb_weighted_sampler_sample(tmb_sampler s, const double *weights, const int *offsets, int num_segments, int *out);
+/* rotate_coords_{f32,f64}(coords[N,3], quaternions[R,4]) -> [N, R, 3]                :2050-2070, rotations.cu:12-37 */
+int tmb_rotate_coords(int precision, int N, int n_rotations, const double *coords, const double *quaternions, double *out);
+/* rotate_and_translate_mol_{f32,f64}(coords[N,3], box, quaternions[B,4], translations[B,3]) -> [B, N, 3]; the
+ * translations are fractions of the box                                              :2072-2115, rotations.cu:39-92 */
+int tmb_rotate_and_translate_mol(
+    int precision, int N, int batch_size, const double *coords, const double *box, const double *quaternions,
+    const double *translations, double *out);
 
 /* ---- Context(x0, v0, box, integrator, bps)                       wrap_kernels.cpp:296-689, context.cu ------------- */
 int tmb_context_create(

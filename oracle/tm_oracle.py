@@ -775,3 +775,72 @@ def nonbonded_precomputed(x, params, box, pair_idxs, beta, cutoff):
     du_dp[:, 2] = np.where(keep & lj_on, 4 * (s6 * s6 - s6), 0)
     du_dp[:, 3] = (du_dd / d) * w
     return u, du_dx, du_dp
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# water exchange by biased deletion (timemachine/md/exchange/exchange_mover.py:64-234) - test oracle for
+# timemachine_b200/csrc/exchange.cu.  PINNING: the per-molecule energies are the interaction-group energies of the
+# oracle above (pinned to the reference's `nonbonded` through tests/golden/nonbonded_*.npz); the rest restates the
+# reference's Python line by line and is cross-checked on the GPU against the compiled reference (tests/test_exchange_gpu.py).
+def pair_energy_matrix(x, params, box, rows, cols, beta, cutoff):
+    """u_ij for i in rows, j in cols (0 outside the cutoff, NaN on a coincident pair), like
+    nonbonded_block_unsummed (nonbonded.py:82-150) / k_atom_by_atom_energies (k_nonbonded.cuh:604-700)."""
+    rows, cols = np.asarray(rows), np.asarray(cols)
+    xi, xj, pi, pj = x[rows], x[cols], params[rows], params[cols]
+    dxyz = delta_r(xi[:, None, :], xj[None, :, :], box)
+    dw = pi[:, None, 3] - pj[None, :, 3]
+    d2 = np.sum(dxyz * dxyz, axis=-1) + dw * dw
+    keep = d2 < cutoff * cutoff
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.sqrt(d2)
+        t = _pair_terms(d, pi[:, None, 0], pj[None, :, 0], pi[:, None, 1], pj[None, :, 1], pi[:, None, 2], pj[None, :, 2], beta)
+    return np.where(keep, t["u"], 0.0)
+
+
+def mol_energies(x, params, box, mols, beta, cutoff):
+    """Energy of every molecule with all atoms outside it (exchange_mover.py:100-138 batch_U_fn)."""
+    n = x.shape[0]
+    out = []
+    for m in mols:
+        others = np.delete(np.arange(n), np.asarray(m))
+        out.append(float(np.sum(pair_energy_matrix(x, params, box, m, others, beta, cutoff))))
+    return np.array(out)
+
+
+def bd_log_weights(x, params, box, mols, nb_beta, cutoff, temperature):
+    """exchange_mover.py:140-152 batch_log_weights: beta * U_mol."""
+    return mol_energies(x, params, box, mols, nb_beta, cutoff) / (BOLTZ * temperature)
+
+
+def logsumexp(v):
+    v = np.asarray(v, dtype=np.float64)
+    m = np.max(v)
+    return float(m + np.log(np.sum(np.exp(v - m))))
+
+
+def bd_log_acceptance(log_weights_before, log_weights_after):
+    """exchange_mover.py:229: min(logsumexp(before) - logsumexp(after), 0)."""
+    return min(logsumexp(log_weights_before) - logsumexp(log_weights_after), 0.0)
+
+
+def quaternion_rotate(coords, q):
+    """Rotate points by the (normalised) quaternion q = (w, x, y, z): q (0, v) q*  (k_rotations.cu:9-48)."""
+    w, x, y, z = np.asarray(q, dtype=np.float64) / np.linalg.norm(q)
+    R = np.array(
+        [
+            [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+            [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+            [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)],
+        ]
+    )
+    return np.asarray(coords) @ R.T
+
+
+def rotate_and_translate_mol(coords, box, q, translation, scale=True):
+    """Rotate about the centroid, then put the centroid at the translation imaged into the home box
+    (exchange_mover.py:29-42 randomly_rotate_and_translate with a given rotation; k_rotations.cu:112-193)."""
+    bd = np.diag(box)
+    t = np.asarray(translation, dtype=np.float64) * (bd if scale else 1.0)
+    t = t - bd * np.floor(t / bd)
+    c = np.mean(coords, axis=0, keepdims=True)
+    return quaternion_rotate(coords - c, q) + t

@@ -126,7 +126,8 @@ def test_half_precision_prefilter_equals_exact_distance_rounds_bitwise(tmp_path)
       * the DHFR-sized box (box 6.17 nm: every vanilla tile takes the prefilter; ~25k pairs within 1e-3 nm of the cutoff),
       * the same box with molecules displaced by whole box vectors (imaging inside the prefilter),
       * a dense blob (every pair of a tile inside the cutoff: the candidate queue runs at capacity),
-      * a box too small for the prefilter's same-image condition (falls back per tile)."""
+      * boxes of 2.7, 3.2 and 4.0 nm: from too small for the prefilter's same-image condition (falls back per tile)
+        to just large enough for every tile."""
     import os
     import subprocess
     import sys
@@ -159,6 +160,9 @@ def test_half_precision_prefilter_equals_exact_distance_rounds_bitwise(tmp_path)
         "run('small', x, p, box, 3000)\n"
         "x, p, box = random_nonbonded_system(6000, seed=13, box_len=7.0)\n"
         "run('short', x, p, box, 6000, cutoff=0.9)\n"
+        "for L in (3.2, 4.0):\n"  # every / most tiles qualify once b/2 - cutoff exceeds the extent of a row block
+        "    x, p, box = random_nonbonded_system(int(100 * L**3), seed=14, box_len=L)\n"
+        "    run(f'mid{L}', x, p, box, len(x))\n"
         "np.savez(sys.argv[1], **out)\n"
     )
     results = {}
@@ -167,7 +171,7 @@ def test_half_precision_prefilter_equals_exact_distance_rounds_bitwise(tmp_path)
         path = tmp_path / f"out{mode}.npz"
         subprocess.check_call([sys.executable, str(script), str(path)], env=env)
         results[mode] = dict(np.load(path))
-    assert set(results["0"]) == set(results["1"]) and len(results["0"]) >= 16
+    assert set(results["0"]) == set(results["1"]) and len(results["0"]) >= 22
     for k in results["0"]:
         np.testing.assert_array_equal(results["0"][k], results["1"][k], err_msg=k)
     # the displaced copy is the same physical system: equal up to the f32 rounding of the larger coordinates

@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtmb200.so"
+import os
+
+# TMB200_LIB: load another build of the same library (A/B measurements of kernel variants); the product path is the default
+LIB_PATH = Path(os.environ.get("TMB200_LIB") or (Path(__file__).resolve().parent / "lib" / "libtmb200.so"))
 
 TMB_OK = 0
 TMB_ERROR = 1
@@ -95,6 +98,27 @@ SIGNATURES = {
     "tmb_barostat_set_pressure": [_h, _dbl],
     "tmb_barostat_last_uniforms": [_h, _p_f32],
     "tmb_barostat_counters": [_h, C.POINTER(C.c_int)],
+    "tmb_bd_exchange_move_create": [_int, _int, _p_i32, _p_i32, _int, _p_f64, _int, _dbl, _dbl, _dbl, _int, _int, _int, _int, _ph],
+    "tmb_bd_exchange_move_num_target_mols": [_h, C.POINTER(C.c_int)],
+    "tmb_bd_exchange_move_batch_size": [_h, C.POINTER(C.c_int)],
+    "tmb_bd_exchange_move_initial_log_weights": [_h, _int, _p_f64, _p_f64, _p_f64],
+    "tmb_bd_exchange_move_incremental_log_weights": [_h, _int, _p_f64, _p_f64, _p_i32, _p_f64, _p_f64, _p_f64],
+    "tmb_bd_exchange_move_get_params": [_h, _p_f64, _int],
+    "tmb_bd_exchange_move_set_params": [_h, _p_f64, _int],
+    "tmb_bd_exchange_move_last_log_probability": [_h, C.POINTER(C.c_double)],
+    "tmb_bd_exchange_move_last_raw_log_probability": [_h, C.POINTER(C.c_double)],
+    "tmb_bd_exchange_move_n_accepted": [_h, C.POINTER(C.c_ulonglong)],
+    "tmb_bd_exchange_move_n_proposed": [_h, C.POINTER(C.c_ulonglong)],
+    "tmb_bd_exchange_move_before_log_weights": [_h, _p_f64],
+    "tmb_bd_exchange_move_after_log_weights": [_h, _p_f64],
+    "tmb_nonbonded_mol_energies": [_int, _int, _p_i32, _p_i32, _int, _dbl, _dbl, _p_f64, _p_f64, _p_f64, _p_i128],
+    "tmb_atom_by_atom_energies": [_int, _int, _p_i32, _int, _p_f64, _p_f64, _p_f64, _dbl, _dbl, _p_f64],
+    "tmb_segmented_logsumexp": [_int, _int, _int, _p_f64, _p_i32, _int, _p_f64],
+    "tmb_weighted_sampler_create": [_int, _int, _int, _int, _ph],
+    "tmb_weighted_sampler_destroy": [_h],
+    "tmb_weighted_sampler_sample": [_h, _p_f64, _p_i32, _int, _p_i32],
+    "tmb_rotate_coords": [_int, _int, _int, _p_f64, _p_f64, _p_f64],
+    "tmb_rotate_and_translate_mol": [_int, _int, _int, _p_f64, _p_f64, _p_f64, _p_f64, _p_f64],
     "tmb_context_destroy": [_h],
     "tmb_context_step": [_h],
     "tmb_context_multiple_steps": [_h, _int, _int, _p_f64, _p_f64],

@@ -52,9 +52,9 @@ def _headers_mtime() -> float:
     return max(h.stat().st_mtime for h in hs if h.exists())
 
 
-# barostat.cu inlines cbrtf / logf / exp from libdevice and must contract them like the reference build does (default
-# fmad); all of its own arithmetic is written with explicit round-to-nearest intrinsics.
-DEFAULT_FMAD_SOURCES = {"barostat.cu"}
+# barostat.cu and exchange.cu inline cbrtf / logf / expf from libdevice and must contract them like the reference build
+# does (default fmad); all of their own arithmetic is written with explicit round-to-nearest intrinsics.
+DEFAULT_FMAD_SOURCES = {"barostat.cu", "exchange.cu"}
 
 
 def _compile(src: Path, extra: list[str]) -> tuple[Path, str]:

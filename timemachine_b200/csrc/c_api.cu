@@ -2,6 +2,7 @@
 // status code + message, handle bookkeeping.  All compute goes through the classes in potential.hpp.
 #include "../../include/tmb200.h"
 #include "fixed_point.cuh"
+#include "exchange.hpp"
 #include "potential.hpp"
 
 #include <cstring>
@@ -529,6 +530,286 @@ int tmb_barostat_create(
             N, pressure, temperature, groups, interval, v, seed, adaptive_scaling_enabled != 0, initial_volume_scale_factor));
     });
 }
+// ---- water exchange (biased deletion) -----------------------------------------------------------------------------
+extern "C++" {
+static std::vector<std::vector<int>> unflatten_mols(const int *atoms, const int *offsets, int n_mols) {
+    std::vector<std::vector<int>> mols(n_mols > 0 ? n_mols : 0);
+    for (int m = 0; m < n_mols; m++) {
+        mols[m].assign(atoms + offsets[m], atoms + offsets[m + 1]);
+    }
+    return mols;
+}
+
+// f32 and f64 movers behind one set of entry points
+template <typename F32, typename F64> static auto with_bd(tmb_mover h, F32 &&f32, F64 &&f64) {
+    MoverPtr &m = as_mover(h);
+    if (auto a = std::dynamic_pointer_cast<BDExchangeMove<float>>(m)) {
+        return f32(*a);
+    }
+    if (auto b = std::dynamic_pointer_cast<BDExchangeMove<double>>(m)) {
+        return f64(*b);
+    }
+    throw std::runtime_error("mover is not a BDExchangeMove");
+}
+#define WITH_BD(h, expr) with_bd((h), [&](BDExchangeMove<float> &mv) { return expr; }, [&](BDExchangeMove<double> &mv) { return expr; })
+
+template <typename Real> static void widen(const std::vector<Real> &v, double *out) {
+    for (size_t i = 0; i < v.size(); i++) {
+        out[i] = static_cast<double>(v[i]);
+    }
+}
+
+} // extern "C++"
+int tmb_bd_exchange_move_create(
+    int precision, int N, const int *mol_atoms, const int *mol_offsets, int n_mols, const double *params, int n_params,
+    double temperature, double nb_beta, double cutoff, int seed, int num_proposals_per_move, int interval, int batch_size,
+    tmb_mover *out) {
+    return guarded([&] {
+        check_precision(precision);
+        // argument checks of the reference's binding, in its order (wrap_kernels.cpp:1749-1769)
+        if (num_proposals_per_move <= 0) {
+            throw std::runtime_error("proposals per move must be greater than 0");
+        }
+        if (n_params != N * P_PER_ATOM) {
+            throw std::runtime_error("Number of parameters must match N");
+        }
+        if (n_mols <= 0) {
+            throw std::runtime_error("must provide at least one molecule");
+        }
+        if (interval <= 0) {
+            throw std::runtime_error("must provide interval greater than 0");
+        }
+        if (batch_size <= 0) {
+            throw std::runtime_error("must provide batch size greater than 0");
+        }
+        if (batch_size > num_proposals_per_move) {
+            throw std::runtime_error("number of proposals per move must be greater than batch size");
+        }
+        auto mols = unflatten_mols(mol_atoms, mol_offsets, n_mols);
+        std::vector<double> p(params, params + n_params);
+        MoverPtr mv;
+        if (precision == TMB_F32) {
+            mv = std::make_shared<BDExchangeMove<float>>(N, mols, p, temperature, nb_beta, cutoff, seed, num_proposals_per_move, interval, batch_size);
+        } else {
+            mv = std::make_shared<BDExchangeMove<double>>(N, mols, p, temperature, nb_beta, cutoff, seed, num_proposals_per_move, interval, batch_size);
+        }
+        *out = new MoverPtr(mv);
+    });
+}
+int tmb_bd_exchange_move_num_target_mols(tmb_mover m, int *out) {
+    return guarded([&] { *out = WITH_BD(m, mv.num_target_mols()); });
+}
+int tmb_bd_exchange_move_batch_size(tmb_mover m, int *out) {
+    return guarded([&] { *out = static_cast<int>(WITH_BD(m, mv.batch_size())); });
+}
+int tmb_bd_exchange_move_initial_log_weights(tmb_mover m, int N, const double *coords, const double *box, double *out) {
+    return guarded([&] {
+        with_bd(
+            m, [&](BDExchangeMove<float> &mv) { widen(mv.compute_initial_log_weights_host(N, coords, box), out); },
+            [&](BDExchangeMove<double> &mv) { widen(mv.compute_initial_log_weights_host(N, coords, box), out); });
+    });
+}
+extern "C++" {
+template <typename Real>
+static void incremental_weights(
+    BDExchangeMove<Real> &mv, int N, const double *coords, const double *box, const int *mol_idxs, const double *quaternions,
+    const double *translations, double *out) {
+    const size_t B = mv.batch_size();
+    std::vector<Real> q(B * 4), t(B * 3);
+    for (size_t i = 0; i < q.size(); i++) {
+        q[i] = static_cast<Real>(quaternions[i]);
+    }
+    for (size_t i = 0; i < t.size(); i++) {
+        t[i] = static_cast<Real>(translations[i]);
+    }
+    auto w = mv.compute_incremental_log_weights_host(N, coords, box, mol_idxs, q.data(), t.data());
+    for (size_t b = 0; b < w.size(); b++) {
+        widen(w[b], out + b * w[b].size());
+    }
+}
+} // extern "C++"
+int tmb_bd_exchange_move_incremental_log_weights(
+    tmb_mover m, int N, const double *coords, const double *box, const int *mol_idxs, const double *quaternions,
+    const double *translations, double *out) {
+    return guarded([&] {
+        with_bd(
+            m, [&](BDExchangeMove<float> &mv) { incremental_weights(mv, N, coords, box, mol_idxs, quaternions, translations, out); },
+            [&](BDExchangeMove<double> &mv) { incremental_weights(mv, N, coords, box, mol_idxs, quaternions, translations, out); });
+    });
+}
+int tmb_bd_exchange_move_get_params(tmb_mover m, double *out, int n_params) {
+    return guarded([&] {
+        std::vector<double> p = WITH_BD(m, mv.get_params());
+        if (static_cast<int>(p.size()) != n_params) {
+            throw std::runtime_error("number of params don't match");
+        }
+        std::memcpy(out, p.data(), sizeof(double) * p.size());
+    });
+}
+int tmb_bd_exchange_move_set_params(tmb_mover m, const double *params, int n_params) {
+    return guarded([&] {
+        std::vector<double> p(params, params + (n_params > 0 ? n_params : 0));
+        with_bd(
+            m, [&](BDExchangeMove<float> &mv) { mv.set_params(p); }, [&](BDExchangeMove<double> &mv) { mv.set_params(p); });
+    });
+}
+int tmb_bd_exchange_move_last_log_probability(tmb_mover m, double *out) {
+    return guarded([&] { *out = WITH_BD(m, mv.log_probability_host()); });
+}
+int tmb_bd_exchange_move_last_raw_log_probability(tmb_mover m, double *out) {
+    return guarded([&] { *out = WITH_BD(m, mv.raw_log_probability_host()); });
+}
+int tmb_bd_exchange_move_n_accepted(tmb_mover m, unsigned long long *out) {
+    return guarded([&] { *out = WITH_BD(m, mv.n_accepted()); });
+}
+int tmb_bd_exchange_move_n_proposed(tmb_mover m, unsigned long long *out) {
+    return guarded([&] { *out = WITH_BD(m, mv.n_proposed()); });
+}
+int tmb_bd_exchange_move_before_log_weights(tmb_mover m, double *out) {
+    return guarded([&] {
+        with_bd(
+            m, [&](BDExchangeMove<float> &mv) { widen(mv.get_before_log_weights(), out); },
+            [&](BDExchangeMove<double> &mv) { widen(mv.get_before_log_weights(), out); });
+    });
+}
+int tmb_bd_exchange_move_after_log_weights(tmb_mover m, double *out) {
+    return guarded([&] {
+        with_bd(
+            m, [&](BDExchangeMove<float> &mv) { widen(mv.get_after_log_weights(), out); },
+            [&](BDExchangeMove<double> &mv) { widen(mv.get_after_log_weights(), out); });
+    });
+}
+
+extern "C++" {
+template <typename Real>
+static void mol_energies(
+    int N, const std::vector<std::vector<int>> &mols, double beta, double cutoff, const double *coords, const double *params,
+    const double *box, tmb_i128 *out) {
+    NonbondedMolEnergyPotential<Real> pot(N, mols, beta, cutoff);
+    if (coords == nullptr) {
+        return;
+    }
+    std::vector<i128> e = pot.mol_energies_host(N, N * P_PER_ATOM, coords, params, box);
+    std::memcpy(out, e.data(), sizeof(i128) * e.size());
+}
+} // extern "C++"
+int tmb_nonbonded_mol_energies(
+    int precision, int N, const int *mol_atoms, const int *mol_offsets, int n_mols, double beta, double cutoff,
+    const double *coords, const double *params, const double *box, tmb_i128 *out) {
+    return guarded([&] {
+        check_precision(precision);
+        auto mols = unflatten_mols(mol_atoms, mol_offsets, n_mols);
+        if (precision == TMB_F32) {
+            mol_energies<float>(N, mols, beta, cutoff, coords, params, box, out);
+        } else {
+            mol_energies<double>(N, mols, beta, cutoff, coords, params, box, out);
+        }
+    });
+}
+int tmb_atom_by_atom_energies(
+    int precision, int N, const int *target_atoms, int T, const double *coords, const double *params, const double *box,
+    double nb_beta, double cutoff, double *out) {
+    return guarded([&] {
+        check_precision(precision);
+        std::vector<int> t(target_atoms, target_atoms + (T > 0 ? T : 0));
+        if (precision == TMB_F32) {
+            widen(atom_by_atom_energies<float>(N, t, coords, params, box, static_cast<float>(nb_beta), static_cast<float>(cutoff)), out);
+        } else {
+            widen(atom_by_atom_energies<double>(N, t, coords, params, box, nb_beta, cutoff), out);
+        }
+    });
+}
+
+extern "C++" {
+template <typename Real> static std::vector<std::vector<Real>> unflatten_values(const double *values, const int *offsets, int num_segments) {
+    std::vector<std::vector<Real>> v(num_segments > 0 ? num_segments : 0);
+    for (int s = 0; s < num_segments; s++) {
+        for (int k = offsets[s]; k < offsets[s + 1]; k++) {
+            v[s].push_back(static_cast<Real>(values[k]));
+        }
+    }
+    return v;
+}
+} // extern "C++"
+int tmb_segmented_logsumexp(
+    int precision, int max_vals_per_segment, int num_segments_max, const double *values, const int *offsets, int num_segments,
+    double *out) {
+    return guarded([&] {
+        check_precision(precision);
+        if (precision == TMB_F32) {
+            SegmentedSumExp<float> s(max_vals_per_segment, num_segments_max);
+            auto v = unflatten_values<float>(values, offsets, num_segments);
+            widen(s.logsumexp_host(v), out);
+        } else {
+            SegmentedSumExp<double> s(max_vals_per_segment, num_segments_max);
+            auto v = unflatten_values<double>(values, offsets, num_segments);
+            widen(s.logsumexp_host(v), out);
+        }
+    });
+}
+
+extern "C++" {
+struct SamplerHandle {
+    std::unique_ptr<SegmentedWeightedRandomSampler<float>> f32;
+    std::unique_ptr<SegmentedWeightedRandomSampler<double>> f64;
+};
+} // extern "C++"
+int tmb_weighted_sampler_create(int precision, int max_vals_per_segment, int num_segments, int seed, tmb_sampler *out) {
+    return guarded([&] {
+        check_precision(precision);
+        auto h = std::make_unique<SamplerHandle>();
+        if (precision == TMB_F32) {
+            h->f32 = std::make_unique<SegmentedWeightedRandomSampler<float>>(max_vals_per_segment, num_segments, seed);
+        } else {
+            h->f64 = std::make_unique<SegmentedWeightedRandomSampler<double>>(max_vals_per_segment, num_segments, seed);
+        }
+        *out = h.release();
+    });
+}
+int tmb_weighted_sampler_destroy(tmb_sampler s) {
+    return guarded([&] { delete static_cast<SamplerHandle *>(s); });
+}
+int tmb_weighted_sampler_sample(tmb_sampler s, const double *weights, const int *offsets, int num_segments, int *out) {
+    return guarded([&] {
+        if (s == nullptr) {
+            throw std::runtime_error("null sampler handle");
+        }
+        SamplerHandle &h = *static_cast<SamplerHandle *>(s);
+        std::vector<int> r;
+        if (h.f32) {
+            r = h.f32->sample_host(unflatten_values<float>(weights, offsets, num_segments));
+        } else {
+            r = h.f64->sample_host(unflatten_values<double>(weights, offsets, num_segments));
+        }
+        std::memcpy(out, r.data(), sizeof(int) * r.size());
+    });
+}
+int tmb_rotate_coords(int precision, int N, int n_rotations, const double *coords, const double *quaternions, double *out) {
+    return guarded([&] {
+        check_precision(precision);
+        if (precision == TMB_F32) {
+            std::vector<float> q(quaternions, quaternions + static_cast<size_t>(n_rotations) * 4);
+            rotate_coordinates_host<float>(N, n_rotations, coords, q.data(), out);
+        } else {
+            rotate_coordinates_host<double>(N, n_rotations, coords, quaternions, out);
+        }
+    });
+}
+int tmb_rotate_and_translate_mol(
+    int precision, int N, int batch_size, const double *coords, const double *box, const double *quaternions,
+    const double *translations, double *out) {
+    return guarded([&] {
+        check_precision(precision);
+        if (precision == TMB_F32) {
+            std::vector<float> q(quaternions, quaternions + static_cast<size_t>(batch_size) * 4);
+            std::vector<float> t(translations, translations + static_cast<size_t>(batch_size) * 3);
+            rotate_and_translate_mol_host<float>(N, batch_size, coords, box, q.data(), t.data(), out);
+        } else {
+            rotate_and_translate_mol_host<double>(N, batch_size, coords, box, quaternions, translations, out);
+        }
+    });
+}
+
 int tmb_mover_destroy(tmb_mover m) {
     return guarded([&] { delete static_cast<MoverPtr *>(m); });
 }

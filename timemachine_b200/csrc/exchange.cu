@@ -1,0 +1,1277 @@
+// Biased-deletion water exchange and per-molecule nonbonded energies (see exchange.hpp for what follows the reference
+// and what does not).
+//
+// Compiled WITHOUT --fmad=false (build.py), like the reference build: logf / expf are inlined from libdevice and must
+// contract the same way.  Every other floating-point operation that feeds a decision is an explicit round-to-nearest
+// intrinsic in the order ptxas emits for the reference's kernels (read off oracle/_ref/obj/{all_atom_energies,
+// k_rotations,nonbonded_mol_energy}.o built for sm_100a):
+//   * d^2 = fma(dw, dw, fma(dz, dz, fma(dx, dx, dy * dy))), minimum image fma(-b, rint(d / b), d);
+//   * the energy-only pair term of compute_electrostatics / compute_lj <Real, true> (k_nonbonded_common.cuh:184-246);
+//   * the two Hamilton products of rotate_coordinates_by_quaternion (k_rotations.cu:9-48), whose contraction pattern
+//     differs between the first and the second product.
+#include "exchange.hpp"
+#include "fixed_point.cuh"
+
+#include <cooperative_groups.h>
+#include <curand.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+namespace cg = cooperative_groups;
+
+namespace tmb {
+
+static const double BOLTZ = 0.008314462618; // reference constants.hpp:5
+
+#define TMB_CURAND(expr)                                                                                               \
+    do {                                                                                                               \
+        curandStatus_t _st = (expr);                                                                                   \
+        if (_st != CURAND_STATUS_SUCCESS) {                                                                            \
+            throw std::runtime_error(std::string("cuRAND error ") + std::to_string(static_cast<int>(_st)) + " at " +   \
+                                     __FILE__ + ":" + std::to_string(__LINE__));                                       \
+        }                                                                                                              \
+    } while (0)
+
+static curandStatus_t gen_uniform(curandGenerator_t g, float *out, size_t n) { return curandGenerateUniform(g, out, n); }
+static curandStatus_t gen_uniform(curandGenerator_t g, double *out, size_t n) { return curandGenerateUniformDouble(g, out, n); }
+static curandStatus_t gen_normal(curandGenerator_t g, float *out, size_t n) { return curandGenerateNormal(g, out, n, 0.0f, 1.0f); }
+static curandStatus_t gen_normal(curandGenerator_t g, double *out, size_t n) { return curandGenerateNormalDouble(g, out, n, 0.0, 1.0); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// molecule bookkeeping (reference mol_utils.cpp)
+void verify_mols_contiguous(const std::vector<std::vector<int>> &group_idxs) {
+    int last_end = group_idxs[0][0] - 1;
+    for (size_t i = 0; i < group_idxs.size(); i++) {
+        std::vector<int> atoms = group_idxs[i];
+        if (atoms[0] != last_end + 1) {
+            throw std::runtime_error("Molecules are not contiguous: mol " + std::to_string(i));
+        }
+        std::sort(atoms.begin(), atoms.end());
+        for (size_t j = 1; j < atoms.size(); j++) {
+            if (atoms[j - 1] + 1 != atoms[j]) {
+                throw std::runtime_error("Molecule " + std::to_string(i) + "is not sequential in atom indices");
+            }
+        }
+        last_end = atoms.back();
+    }
+}
+
+MolLayout flatten_mols(const std::vector<std::vector<int>> &group_idxs) {
+    MolLayout l;
+    for (size_t i = 0; i < group_idxs.size(); i++) {
+        std::vector<int> atoms = group_idxs[i];
+        std::sort(atoms.begin(), atoms.end());
+        l.mol_offsets.push_back(static_cast<int>(l.atom_idxs.size()));
+        for (int a : atoms) {
+            l.atom_idxs.push_back(a);
+            l.mol_idxs.push_back(static_cast<int>(i));
+        }
+    }
+    l.mol_offsets.push_back(static_cast<int>(l.atom_idxs.size()));
+    return l;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// arithmetic helpers: explicit rounding, never contracted
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmad_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double fmad_(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ double div_(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float rsqrt_(float a) { return rsqrtf(a); }
+__device__ __forceinline__ double rsqrt_(double a) { return rsqrt(a); }
+__device__ __forceinline__ float rint_(float a) { return rintf(a); }
+__device__ __forceinline__ double rint_(double a) { return rint(a); }
+__device__ __forceinline__ float floor_(float a) { return floorf(a); }
+__device__ __forceinline__ double floor_(double a) { return floor(a); }
+__device__ __forceinline__ float log_(float a) { return logf(a); }
+__device__ __forceinline__ double log_(double a) { return log(a); }
+__device__ __forceinline__ float exp_(float a) { return expf(a); }
+__device__ __forceinline__ double exp_(double a) { return exp(a); }
+__device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+template <typename Real> __device__ __forceinline__ Real inf_() { return static_cast<Real>(INFINITY); }
+
+template <typename Real> struct Box3 {
+    Real x, y, z, ix, iy, iz;
+};
+template <typename Real> __device__ __forceinline__ Box3<Real> load_box3(const double *__restrict__ box) {
+    Box3<Real> b;
+    b.x = static_cast<Real>(box[0]);
+    b.y = static_cast<Real>(box[4]);
+    b.z = static_cast<Real>(box[8]);
+    b.ix = div_(static_cast<Real>(1), b.x);
+    b.iy = div_(static_cast<Real>(1), b.y);
+    b.iz = div_(static_cast<Real>(1), b.z);
+    return b;
+}
+
+// ---- energy-only pair term --------------------------------------------------------------------------------------
+// switching function cos^3(pi/2 (d / 1.2)^8), reference k_nonbonded_common.cuh:16-35 (f64), :96-130 (f32)
+__device__ __forceinline__ float switch_fn_(float d) {
+    constexpr float cutoff = 1.2f;
+    if (d >= cutoff) {
+        return 0.0f;
+    }
+    constexpr float pi = static_cast<float>(3.141592653589793115997963468544185161);
+    constexpr float inv_c = 1.0f / cutoff;
+    constexpr float k2 = inv_c * inv_c;
+    constexpr float k4 = k2 * k2;
+    constexpr float k8 = k4 * k4;
+    constexpr float half_pi = 0.5f * pi;
+    const float d2 = mul_(d, d);
+    const float d4 = mul_(d2, d2);
+    const float d8 = mul_(d4, d4);
+    const float c = __cosf(mul_(half_pi, mul_(d8, k8)));
+    return mul_(c, mul_(c, c));
+}
+__device__ __forceinline__ double switch_fn_(double d) {
+    constexpr double cutoff = 1.2;
+    if (d >= cutoff) {
+        return 0.0;
+    }
+    constexpr double inv_c = 1 / cutoff;
+    const double k = mul_(d, inv_c);
+    const double k2 = mul_(k, k);
+    const double k4 = mul_(k2, k2);
+    const double k8 = mul_(k4, k4);
+    const double c = cos(mul_(0.5 * 3.141592653589793115997963468544185161, k8));
+    return mul_(mul_(c, c), c);
+}
+// erfc: A&S 7.1.26 with __expf / __frcp_rn in f32 (reference k_nonbonded_common.cuh:132-160), erfc() in f64
+__device__ __forceinline__ float erfc_(float x) {
+    const float e = __expf(-mul_(x, x));
+    const float t = __frcp_rn(fmad_(0.3275911f, x, 1.0f));
+    float p = fmad_(1.061405429f, t, -1.453152027f);
+    p = fmad_(p, t, 1.421413741f);
+    p = fmad_(p, t, -0.284496736f);
+    p = fmad_(p, t, 0.254829592f);
+    return mul_(e, mul_(p, t));
+}
+__device__ __forceinline__ double erfc_(double x) { return erfc(x); }
+
+// u_ij for d2 already inside the cutoff (compute_electrostatics<Real, true> + compute_lj<Real, true> with scales of 1)
+template <typename Real>
+__device__ __forceinline__ Real pair_u(Real qi, Real qj, Real si, Real sj, Real ei, Real ej, Real d2, Real beta) {
+    const Real inv_d = rsqrt_(d2);
+    const Real d = mul_(d2, inv_d);
+    const Real damping = mul_(erfc_(mul_(beta, d)), switch_fn_(d));
+    Real u = mul_(mul_(mul_(qi, qj), inv_d), damping);
+    if (ei != static_cast<Real>(0) && ej != static_cast<Real>(0)) {
+        const Real eps4 = mul_(static_cast<Real>(4), mul_(ei, ej));
+        const Real s1 = mul_(add_(si, sj), inv_d);
+        const Real s2 = mul_(s1, s1);
+        const Real s4 = mul_(s2, s2);
+        const Real s6 = mul_(s4, s2);
+        u = fmad_(s6, mul_(eps4, sub_(s6, static_cast<Real>(1))), u);
+    }
+    return u;
+}
+
+// fixed-point energy of atom (xi, pi) with atom (xj, pj); 0 outside the cutoff (reference k_nonbonded.cuh:520-551, 667-697)
+template <typename Real>
+__device__ __forceinline__ Real
+pair_u_or_zero(const Vec4<Real> &xi, const Vec4<Real> &pi, const Vec4<Real> &xj, const Vec4<Real> &pj, const Box3<Real> &b, Real cutoff2, Real beta) {
+    Real dx = sub_(xi.x, xj.x);
+    Real dy = sub_(xi.y, xj.y);
+    Real dz = sub_(xi.z, xj.z);
+    const Real dw = sub_(xi.w, xj.w);
+    dx = fmad_(-b.x, rint_(mul_(dx, b.ix)), dx);
+    dy = fmad_(-b.y, rint_(mul_(dy, b.iy)), dy);
+    dz = fmad_(-b.z, rint_(mul_(dz, b.iz)), dz);
+    const Real d2 = fmad_(dw, dw, fmad_(dz, dz, fmad_(dx, dx, mul_(dy, dy))));
+    if (!(d2 < cutoff2)) {
+        return static_cast<Real>(0);
+    }
+    return pair_u(pi.x, pj.x, pi.y, pj.y, pi.z, pj.z, d2, beta);
+}
+template <typename Real>
+__device__ __forceinline__ i128
+pair_e(const Vec4<Real> &xi, const Vec4<Real> &pi, const Vec4<Real> &xj, const Vec4<Real> &pj, const Box3<Real> &b, Real cutoff2, Real beta) {
+    Real dx = sub_(xi.x, xj.x);
+    Real dy = sub_(xi.y, xj.y);
+    Real dz = sub_(xi.z, xj.z);
+    const Real dw = sub_(xi.w, xj.w);
+    dx = fmad_(-b.x, rint_(mul_(dx, b.ix)), dx);
+    dy = fmad_(-b.y, rint_(mul_(dy, b.iy)), dy);
+    dz = fmad_(-b.z, rint_(mul_(dz, b.iz)), dz);
+    const Real d2 = fmad_(dw, dw, fmad_(dz, dz, fmad_(dx, dx, mul_(dy, dy))));
+    if (!(d2 < cutoff2)) {
+        return 0;
+    }
+    return energy_to_fixed<Real>(pair_u(pi.x, pj.x, pi.y, pj.y, pi.z, pj.z, d2, beta));
+}
+
+// 128-bit accumulate through two 64-bit atomics; the final value does not depend on the order of the adds
+__device__ __forceinline__ void atomic_add_i128(i128 *addr, i128 v) {
+    u64 *p = reinterpret_cast<u64 *>(addr);
+    const u64 lo = static_cast<u64>(v);
+    u64 hi = static_cast<u64>(static_cast<unsigned __int128>(v) >> 64);
+    const u64 old = atomicAdd(p, lo);
+    if (old + lo < old) {
+        hi += 1;
+    }
+    if (hi != 0) {
+        atomicAdd(p + 1, hi);
+    }
+}
+
+__device__ __forceinline__ bool fixed_overflow(i128 v) { return v >= static_cast<i128>(LLONG_MAX) || v <= static_cast<i128>(LLONG_MIN); }
+
+// beta * E, +inf for an energy outside the int64 range (reference k_exchange.cu:32-42)
+template <typename Real> __device__ __forceinline__ Real log_weight(i128 e, Real beta) {
+    return fixed_overflow(e) ? inf_<Real>() : mul_(beta, fixed_to_real<Real>(static_cast<u64>(e)));
+}
+template <typename Real> __device__ __forceinline__ Real nan_to_inf(Real v) { return isnan(v) ? inf_<Real>() : v; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// staging: coordinates + w, and (q, sig, eps) per atom in Real (the reference casts per use: same values)
+template <typename Real>
+__global__ void k_stage_atoms(int N, const double *__restrict__ coords, const double *__restrict__ params, Vec4<Real> *__restrict__ xr, Vec4<Real> *__restrict__ pr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) {
+        return;
+    }
+    Vec4<Real> x, p;
+    x.x = static_cast<Real>(coords[i * 3 + 0]);
+    x.y = static_cast<Real>(coords[i * 3 + 1]);
+    x.z = static_cast<Real>(coords[i * 3 + 2]);
+    x.w = static_cast<Real>(params[i * 4 + P_W]);
+    p.x = static_cast<Real>(params[i * 4 + P_CHARGE]);
+    p.y = static_cast<Real>(params[i * 4 + P_SIG]);
+    p.z = static_cast<Real>(params[i * 4 + P_EPS]);
+    p.w = static_cast<Real>(0);
+    xr[i] = x;
+    pr[i] = p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// energies of all target molecules (reference k_compute_nonbonded_target_atom_energies + k_accumulate_..., brute force)
+// One thread per target atom, a slice of all atoms per blockIdx.y staged through shared memory, 128-bit atomics per
+// molecule.  out must be zeroed.
+constexpr int ME_THREADS = 128;
+template <typename Real>
+__global__ void __launch_bounds__(ME_THREADS) k_mol_energies(
+    int N, int num_targets, const int4 *__restrict__ targets, const Vec4<Real> *__restrict__ xr, const Vec4<Real> *__restrict__ pr,
+    const double *__restrict__ box, Real beta, Real cutoff2, i128 *__restrict__ out) {
+    __shared__ Vec4<Real> sx[ME_THREADS], sp[ME_THREADS];
+    const Box3<Real> b = load_box3<Real>(box);
+    const int t = blockIdx.x * ME_THREADS + threadIdx.x;
+    const bool live = t < num_targets;
+    int4 tg = make_int4(0, 0, 0, -1);
+    Vec4<Real> xi = {}, pi = {};
+    if (live) {
+        tg = targets[t];
+        xi = xr[tg.x];
+        pi = pr[tg.x];
+    }
+    const int per = (N + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y);
+    const int j0 = blockIdx.y * per;
+    const int j1 = min(N, j0 + per);
+    i128 acc = 0;
+    for (int base = j0; base < j1; base += ME_THREADS) {
+        const int j = base + threadIdx.x;
+        __syncthreads();
+        if (j < j1) {
+            sx[threadIdx.x] = xr[j];
+            sp[threadIdx.x] = pr[j];
+        }
+        __syncthreads();
+        const int n = min(ME_THREADS, j1 - base);
+        if (live) {
+            for (int k = 0; k < n; k++) {
+                const int jj = base + k;
+                if (jj >= tg.z && jj <= tg.w) {
+                    continue; // same molecule
+                }
+                acc += pair_e(xi, pi, sx[k], sp[k], b, cutoff2, beta);
+            }
+        }
+    }
+    if (live && acc != 0) {
+        atomic_add_i128(out + tg.y, acc);
+    }
+}
+
+// reference k_atom_by_atom_energies (k_nonbonded.cuh:604-700): [T, N] pair energies in Real
+template <typename Real>
+__global__ void k_atom_by_atom(
+    int N, int T, const int *__restrict__ target_atoms, const Vec4<Real> *__restrict__ xr, const Vec4<Real> *__restrict__ pr,
+    const double *__restrict__ box, Real beta, Real cutoff2, Real *__restrict__ out) {
+    const Box3<Real> b = load_box3<Real>(box);
+    const int row = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= T || j >= N) {
+        return;
+    }
+    const int i = target_atoms[row];
+    out[static_cast<size_t>(row) * N + j] = pair_u_or_zero(xr[i], pr[i], xr[j], pr[j], b, cutoff2, beta);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// block-level reductions (EX_THREADS threads).  No __restrict__ on their inputs: the persistent kernel rewrites those
+// buffers between grid barriers and the loads must stay ordinary (coherent) loads.  The order of the floating-point sum is fixed by the thread count and
+// the element count only, so a log-sum-exp is bitwise reproducible whichever batch slot computes it.
+constexpr int EX_THREADS = 256;
+
+template <typename Real> struct LseScratch {
+    Real v[EX_THREADS];
+    int i[EX_THREADS];
+};
+
+template <typename Real> __device__ Real block_max(const Real *vals, int n, LseScratch<Real> &s) {
+    Real m = -inf_<Real>();
+    for (int k = threadIdx.x; k < n; k += EX_THREADS) {
+        const Real v = vals[k];
+        m = (v > m) ? v : m;
+    }
+    s.v[threadIdx.x] = m;
+    __syncthreads();
+    for (int w = EX_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            const Real o = s.v[threadIdx.x + w];
+            if (o > s.v[threadIdx.x]) {
+                s.v[threadIdx.x] = o;
+            }
+        }
+        __syncthreads();
+    }
+    const Real r = s.v[0];
+    __syncthreads();
+    return r;
+}
+
+// (max, sum exp(x - max))  (reference SegmentedSumExp::sum_device)
+template <typename Real> __device__ void block_sumexp(const Real *vals, int n, LseScratch<Real> &s, Real &out_max, Real &out_sum) {
+    const Real m = block_max(vals, n, s);
+    Real acc = static_cast<Real>(0);
+    for (int k = threadIdx.x; k < n; k += EX_THREADS) {
+        acc = add_(acc, exp_(sub_(vals[k], m)));
+    }
+    s.v[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = EX_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            s.v[threadIdx.x] = add_(s.v[threadIdx.x], s.v[threadIdx.x + w]);
+        }
+        __syncthreads();
+    }
+    out_max = m;
+    out_sum = s.v[0];
+    __syncthreads();
+}
+
+// arg max of log_weights[k] - log(-log(noise[k])) with the lowest index on ties (Gumbel-max trick, reference
+// k_sampling.cu:10-75 + cub ArgMax)
+template <typename Real> __device__ int block_gumbel_argmax(const Real *logw, const Real *noise, int n, LseScratch<Real> &s) {
+    Real best = -inf_<Real>();
+    int best_i = 0x7fffffff;
+    for (int k = threadIdx.x; k < n; k += EX_THREADS) {
+        const Real g = -log_(-log_(noise[k]));
+        const Real v = add_(logw[k], g);
+        if (v > best || best_i == 0x7fffffff) {
+            best = v;
+            best_i = k;
+        }
+    }
+    s.v[threadIdx.x] = best;
+    s.i[threadIdx.x] = best_i;
+    __syncthreads();
+    for (int w = EX_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            const Real ov = s.v[threadIdx.x + w];
+            const int oi = s.i[threadIdx.x + w];
+            const Real mv = s.v[threadIdx.x];
+            const int mi = s.i[threadIdx.x];
+            if (oi != 0x7fffffff && (mi == 0x7fffffff || ov > mv || (ov == mv && oi < mi))) {
+                s.v[threadIdx.x] = ov;
+                s.i[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    const int r = s.i[0];
+    __syncthreads();
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rotation of (x, y, z) by the normalised quaternion q: q (0, v) q*   (reference k_rotations.cu:9-48)
+template <typename Real> __device__ __forceinline__ void rotate_by_quaternion(const Real *q_raw, Real &cx, Real &cy, Real &cz) {
+    const Real q0 = q_raw[0], q1 = q_raw[1], q2 = q_raw[2], q3 = q_raw[3];
+    const Real n2 = fmad_(q3, q3, fmad_(q2, q2, fmad_(q0, q0, mul_(q1, q1))));
+    const Real inv = rsqrt_(n2);
+    const Real w = mul_(q0, inv), x = mul_(q1, inv), y = mul_(q2, inv), z = mul_(q3, inv);
+    const Real zero = static_cast<Real>(0);
+    // q (0, c)
+    const Real i0 = fmad_(cz, -z, fmad_(cy, -y, fmad_(zero, w, -mul_(cx, x))));
+    const Real i1 = fmad_(cy, -z, fmad_(cz, y, fmad_(cx, w, mul_(zero, x))));
+    const Real i2 = fmad_(cx, z, fmad_(zero, y, fmad_(cy, w, -mul_(cz, x))));
+    const Real i3 = fmad_(zero, z, fmad_(cx, -y, fmad_(cz, w, mul_(cy, x))));
+    // (i) q*
+    cx = fmad_(y, i3, fmad_(-z, i2, fmad_(w, i1, -mul_(x, i0))));
+    cy = fmad_(-x, i3, fmad_(w, i2, fmad_(z, i1, -mul_(y, i0))));
+    cz = fmad_(w, i3, fmad_(x, i2, fmad_(-y, i1, -mul_(z, i0))));
+}
+
+// rotate a molecule about its centroid and put the centroid at the translation (imaged into the home box; scaled by the
+// box first when SCALE)   (reference k_rotate_and_translate_mols, k_rotations.cu:112-193)
+template <typename Real>
+__device__ void rotate_and_translate(
+    int num_atoms, const Vec4<Real> *mol_x, const Real *quat, const Real *trans, const Box3<Real> &b, bool scale, Vec4<Real> *out) {
+    Real tx = trans[0], ty = trans[1], tz = trans[2];
+    if (scale) {
+        tx = mul_(tx, b.x);
+        ty = mul_(ty, b.y);
+        tz = mul_(tz, b.z);
+    }
+    tx = fmad_(b.x, -floor_(mul_(tx, b.ix)), tx);
+    ty = fmad_(b.y, -floor_(mul_(ty, b.iy)), ty);
+    tz = fmad_(b.z, -floor_(mul_(tz, b.iz)), tz);
+    u64 ax = 0, ay = 0, az = 0;
+    for (int i = 0; i < num_atoms; i++) {
+        ax += to_fixed<FIXED_EXPONENT>(mol_x[i].x);
+        ay += to_fixed<FIXED_EXPONENT>(mol_x[i].y);
+        az += to_fixed<FIXED_EXPONENT>(mol_x[i].z);
+    }
+    const Real n = static_cast<Real>(num_atoms);
+    const Real gx = div_(fixed_to_real<Real>(ax), n);
+    const Real gy = div_(fixed_to_real<Real>(ay), n);
+    const Real gz = div_(fixed_to_real<Real>(az), n);
+    for (int i = 0; i < num_atoms; i++) {
+        Real cx = sub_(mol_x[i].x, gx);
+        Real cy = sub_(mol_x[i].y, gy);
+        Real cz = sub_(mol_x[i].z, gz);
+        rotate_by_quaternion(quat, cx, cy, cz);
+        Vec4<Real> o;
+        o.x = add_(cx, tx);
+        o.y = add_(cy, ty);
+        o.z = add_(cz, tz);
+        o.w = mol_x[i].w;
+        out[i] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the biased-deletion move, phase by phase
+enum { ST_OFFSET = 0, ST_SELECTED = 1, ST_ITER = 2, ST_WORDS = 4 };
+
+template <typename Real> struct BDDevice {
+    int N, M, S, B, P;   // atoms, target molecules, atoms per molecule, batch size, proposals per move
+    int first;           // first atom of molecule 0
+    int sample, scale;   // draw the molecule with the Gumbel-max trick / scale translations by the box
+    Real nb_beta, beta, cutoff2;
+    double *coords;      // [N, 3] the caller's coordinates (updated when a proposal is accepted)
+    const double *box;
+    Vec4<Real> *xr;      // [N] staged copy of coords (+ w), kept in step with coords
+    const Vec4<Real> *pr;
+    Vec4<Real> *prop;    // [B, S] proposed positions
+    i128 *before_E, *after_E, *total; // [M], [B, M], [B]
+    Real *logw_before, *logw_after;   // [M], [B, M]
+    Real *lse_before;                 // {max, sum}
+    Real *lse_after_max, *lse_after_sum; // [B]
+    int *samples;                     // [B]
+    int *state;                       // ST_*
+    u64 *num_accepted;
+    const Real *quat, *trans, *sample_noise, *mh; // [P, 4], [P, 3], [P, M], [P]
+};
+
+template <typename Real> struct BDShared {
+    LseScratch<Real> red;
+    unsigned long long tot[2]; // i128 partial of a block (two limbs)
+    int sel;
+};
+
+// phase S: choose the molecule of every live batch slot and build its proposal
+template <typename Real> __device__ void bd_phase_sample(const BDDevice<Real> &a, BDShared<Real> &sh, int off, int nblocks, int block) {
+    const Box3<Real> bx = load_box3<Real>(a.box);
+    const int live = min(a.B, a.P - off);
+    if (block == 0 && threadIdx.x == 0 && a.sample) {
+        // the previous batch's accepted proposal becomes the "before" state (reference k_store_accepted_log_probability)
+        const int sel = a.state[ST_SELECTED];
+        if (a.state[ST_ITER] > 0 && sel < a.B) {
+            a.lse_before[0] = a.lse_after_max[sel];
+            a.lse_before[1] = a.lse_after_sum[sel];
+        }
+    }
+    for (int b = block; b < live; b += nblocks) {
+        int s;
+        if (a.sample) {
+            s = block_gumbel_argmax(a.logw_before, a.sample_noise + static_cast<size_t>(off + b) * a.M, a.M, sh.red);
+        } else {
+            s = a.samples[b];
+        }
+        if (threadIdx.x == 0) {
+            a.samples[b] = s;
+            a.total[b] = 0;
+            rotate_and_translate(
+                a.S, a.xr + a.first + s * a.S, a.quat + static_cast<size_t>(off + b) * 4, a.trans + static_cast<size_t>(off + b) * 3, bx,
+                a.scale != 0, a.prop + static_cast<size_t>(b) * a.S);
+        }
+    }
+}
+
+// phase E: pair energies of the chosen molecule, at its old and at its proposed position, with every atom
+//   other molecule m:  E_after[b, m] = E_before[m] + sum_{i in s, j in m} (e_new(i, j) - e_old(i, j))
+//   chosen molecule:   total[b]      = sum_{i in s, j not in s} e_new(i, j)
+// (the reference's k_atom_by_atom_energies x 2 + k_adjust_energies x 2 + k_set_sampled_energy_block/_reduce)
+template <typename Real> __device__ void bd_phase_energies(const BDDevice<Real> &a, BDShared<Real> &sh, int off, int nblocks, int block) {
+    const Box3<Real> bx = load_box3<Real>(a.box);
+    const int live = min(a.B, a.P - off);
+    const int n_other = a.N - a.M * a.S;
+    const int items = a.M + n_other;
+    const int chunks = (items + EX_THREADS - 1) / EX_THREADS;
+    const long long tasks = static_cast<long long>(live) * chunks;
+    for (long long task = block; task < tasks; task += nblocks) {
+        const int b = static_cast<int>(task / chunks);
+        const int item = static_cast<int>(task % chunks) * EX_THREADS + threadIdx.x;
+        if (threadIdx.x == 0) {
+            sh.tot[0] = 0;
+            sh.tot[1] = 0;
+        }
+        __syncthreads();
+        const int s = a.samples[b];
+        const Vec4<Real> *xold = a.xr + a.first + s * a.S;
+        const Vec4<Real> *pmol = a.pr + a.first + s * a.S;
+        const Vec4<Real> *xnew = a.prop + static_cast<size_t>(b) * a.S;
+        i128 acc_new = 0;
+        if (item < a.M) {
+            if (item != s) {
+                i128 delta = 0;
+                const int j0 = a.first + item * a.S;
+                for (int i = 0; i < a.S; i++) {
+                    const Vec4<Real> xo = xold[i], xn = xnew[i], pi = pmol[i];
+                    for (int j = j0; j < j0 + a.S; j++) {
+                        const Vec4<Real> xj = a.xr[j], pj = a.pr[j];
+                        const i128 e_new = pair_e(xn, pi, xj, pj, bx, a.cutoff2, a.nb_beta);
+                        delta += e_new - pair_e(xo, pi, xj, pj, bx, a.cutoff2, a.nb_beta);
+                        acc_new += e_new;
+                    }
+                }
+                const i128 e = a.before_E[item] + delta;
+                a.after_E[static_cast<size_t>(b) * a.M + item] = e;
+                a.logw_after[static_cast<size_t>(b) * a.M + item] = log_weight<Real>(e, a.beta);
+            }
+        } else if (item < items) {
+            const int k = item - a.M;
+            const int j = k < a.first ? k : k + a.M * a.S;
+            const Vec4<Real> xj = a.xr[j], pj = a.pr[j];
+            for (int i = 0; i < a.S; i++) {
+                acc_new += pair_e(xnew[i], pmol[i], xj, pj, bx, a.cutoff2, a.nb_beta);
+            }
+        }
+        if (acc_new != 0) {
+            atomic_add_i128(reinterpret_cast<i128 *>(sh.tot), acc_new);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && (sh.tot[0] | sh.tot[1]) != 0) {
+            i128 v;
+            memcpy(&v, sh.tot, sizeof(v));
+            atomic_add_i128(a.total + b, v);
+        }
+        __syncthreads();
+    }
+}
+
+// phase L: energy and weight of the chosen molecule, log-sum-exp of the proposal's weights
+template <typename Real> __device__ void bd_phase_lse(const BDDevice<Real> &a, BDShared<Real> &sh, int off, int nblocks, int block) {
+    const int live = min(a.B, a.P - off);
+    for (int b = block; b < live; b += nblocks) {
+        if (threadIdx.x == 0) {
+            const int s = a.samples[b];
+            const i128 e = a.total[b];
+            a.after_E[static_cast<size_t>(b) * a.M + s] = e;
+            a.logw_after[static_cast<size_t>(b) * a.M + s] = log_weight<Real>(e, a.beta);
+        }
+        __syncthreads();
+        Real m, sum;
+        block_sumexp(a.logw_after + static_cast<size_t>(b) * a.M, a.M, sh.red, m, sum);
+        if (threadIdx.x == 0) {
+            a.lse_after_max[b] = m;
+            a.lse_after_sum[b] = sum;
+        }
+    }
+}
+
+// phase A: Metropolis test per slot, the first accepted slot wins; store its state (reference k_accept_first_valid_move
+// + k_store_exchange_move + k_convert_energies_to_log_weights).  Every block finds the winner for itself.
+template <typename Real> __device__ void bd_phase_accept(const BDDevice<Real> &a, BDShared<Real> &sh, int off, int nblocks, int block) {
+    const int live = min(a.B, a.P - off);
+    if (threadIdx.x == 0) {
+        sh.sel = a.B;
+    }
+    __syncthreads();
+    const Real before = nan_to_inf<Real>(add_(a.lse_before[0], log_(a.lse_before[1])));
+    for (int b = threadIdx.x; b < live; b += EX_THREADS) {
+        const Real after = nan_to_inf<Real>(add_(a.lse_after_max[b], log_(a.lse_after_sum[b])));
+        const Real log_acc = min_(sub_(before, after), static_cast<Real>(0));
+        if (a.mh[off + b] < exp_(log_acc)) {
+            atomicMin(&sh.sel, b);
+            break;
+        }
+    }
+    __syncthreads();
+    const int sel = sh.sel;
+    if (sel < a.B) {
+        for (int m = block * EX_THREADS + threadIdx.x; m < a.M; m += nblocks * EX_THREADS) {
+            a.before_E[m] = a.after_E[static_cast<size_t>(sel) * a.M + m];
+            a.logw_before[m] = a.logw_after[static_cast<size_t>(sel) * a.M + m];
+        }
+    }
+    if (block == 0 && threadIdx.x == 0) {
+        if (sel < a.B) {
+            const int s = a.samples[sel];
+            for (int i = 0; i < a.S; i++) {
+                const Vec4<Real> p = a.prop[static_cast<size_t>(sel) * a.S + i];
+                const int atom = a.first + s * a.S + i;
+                a.coords[atom * 3 + 0] = static_cast<double>(p.x);
+                a.coords[atom * 3 + 1] = static_cast<double>(p.y);
+                a.coords[atom * 3 + 2] = static_cast<double>(p.z);
+                a.xr[atom] = p;
+            }
+            a.state[ST_OFFSET] = off + sel + 1;
+            a.num_accepted[0] += 1;
+        } else {
+            a.state[ST_OFFSET] = off + a.B;
+        }
+        a.state[ST_SELECTED] = sel;
+        a.state[ST_ITER] += 1;
+    }
+    __syncthreads();
+}
+
+// one phase per launch (host-driven loop, and compute_incremental_log_weights)
+template <typename Real> __global__ void __launch_bounds__(EX_THREADS) k_bd_phase(BDDevice<Real> a, int phase) {
+    __shared__ BDShared<Real> sh;
+    const int off = a.state[ST_OFFSET];
+    if (off >= a.P) {
+        return;
+    }
+    switch (phase) {
+    case 0:
+        bd_phase_sample(a, sh, off, gridDim.x, blockIdx.x);
+        break;
+    case 1:
+        bd_phase_energies(a, sh, off, gridDim.x, blockIdx.x);
+        break;
+    case 2:
+        bd_phase_lse(a, sh, off, gridDim.x, blockIdx.x);
+        break;
+    default:
+        bd_phase_accept(a, sh, off, gridDim.x, blockIdx.x);
+        break;
+    }
+}
+
+// all batches of a move in one cooperative launch
+template <typename Real> __global__ void __launch_bounds__(EX_THREADS) k_bd_move(BDDevice<Real> a) {
+    __shared__ BDShared<Real> sh;
+    cg::grid_group grid = cg::this_grid();
+    // every pass consumes at least one proposal, so P passes is an upper bound that cannot be reached unless the state is corrupt
+    for (int pass = 0; pass < a.P; pass++) {
+        const int off = *reinterpret_cast<volatile int *>(a.state + ST_OFFSET);
+        if (off >= a.P) {
+            break;
+        }
+        bd_phase_sample(a, sh, off, gridDim.x, blockIdx.x);
+        grid.sync();
+        bd_phase_energies(a, sh, off, gridDim.x, blockIdx.x);
+        grid.sync();
+        bd_phase_lse(a, sh, off, gridDim.x, blockIdx.x);
+        grid.sync();
+        bd_phase_accept(a, sh, off, gridDim.x, blockIdx.x);
+        grid.sync();
+    }
+}
+
+// log weights of all molecules and their log-sum-exp (one block)
+template <typename Real>
+__global__ void __launch_bounds__(EX_THREADS) k_bd_initial_weights(int M, Real beta, const i128 *__restrict__ E, Real *__restrict__ logw, Real *__restrict__ lse) {
+    __shared__ LseScratch<Real> red;
+    for (int m = threadIdx.x; m < M; m += EX_THREADS) {
+        logw[m] = log_weight<Real>(E[m], beta);
+    }
+    __syncthreads();
+    Real mx, sum;
+    block_sumexp(logw, M, red, mx, sum);
+    if (threadIdx.x == 0) {
+        lse[0] = mx;
+        lse[1] = sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SegmentedSumExp / SegmentedWeightedRandomSampler kernels (one block per segment)
+template <typename Real>
+__global__ void __launch_bounds__(EX_THREADS) k_segmented_sumexp(int num_segments, const int *__restrict__ offsets, const Real *__restrict__ vals, Real *__restrict__ out_max, Real *__restrict__ out_sum) {
+    __shared__ LseScratch<Real> red;
+    for (int s = blockIdx.x; s < num_segments; s += gridDim.x) {
+        Real m, sum;
+        block_sumexp(vals + offsets[s], offsets[s + 1] - offsets[s], red, m, sum);
+        if (threadIdx.x == 0) {
+            out_max[s] = m;
+            out_sum[s] = sum;
+        }
+    }
+}
+template <typename Real>
+__global__ void __launch_bounds__(EX_THREADS) k_segmented_gumbel_argmax(int num_segments, const int *__restrict__ offsets, const Real *__restrict__ logw, const Real *__restrict__ noise, int *__restrict__ out) {
+    __shared__ LseScratch<Real> red;
+    for (int s = blockIdx.x; s < num_segments; s += gridDim.x) {
+        const int r = block_gumbel_argmax(logw + offsets[s], noise + offsets[s], offsets[s + 1] - offsets[s], red);
+        if (threadIdx.x == 0) {
+            out[s] = r;
+        }
+    }
+}
+
+template <typename Real> __global__ void k_rotate_coordinates(int N, int n_rot, const double *__restrict__ coords, const Real *__restrict__ quats, double *__restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (r >= n_rot || c >= N) {
+        return;
+    }
+    Real x = static_cast<Real>(coords[c * 3 + 0]), y = static_cast<Real>(coords[c * 3 + 1]), z = static_cast<Real>(coords[c * 3 + 2]);
+    rotate_by_quaternion(quats + r * 4, x, y, z);
+    double *o = out + (static_cast<size_t>(c) * n_rot + r) * 3;
+    o[0] = x;
+    o[1] = y;
+    o[2] = z;
+}
+template <typename Real>
+__global__ void k_rotate_and_translate_mol(int N, int batch, const Vec4<Real> *__restrict__ xr, const double *__restrict__ box, const Real *__restrict__ quats, const Real *__restrict__ trans, Vec4<Real> *__restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) {
+        return;
+    }
+    const Box3<Real> bx = load_box3<Real>(box);
+    rotate_and_translate(N, xr, quats + b * 4, trans + b * 3, bx, true, out + static_cast<size_t>(b) * N);
+}
+
+// ===============================================================================================================
+// host side
+template <typename Real>
+NonbondedMolEnergyPotential<Real>::NonbondedMolEnergyPotential(int N, const std::vector<std::vector<int>> &target_mols, double beta, double cutoff)
+    : N_(N), num_target_mols_(static_cast<int>(target_mols.size())), beta_(static_cast<Real>(beta)),
+      cutoff_squared_(static_cast<Real>(cutoff * cutoff)) {
+    verify_group_idxs(N_, target_mols);
+    if (num_target_mols_ <= 0) {
+        throw std::runtime_error("must provide at least one target mol");
+    }
+    const MolLayout l = flatten_mols(target_mols);
+    std::vector<int4> t(l.atom_idxs.size());
+    for (size_t k = 0; k < t.size(); k++) {
+        const int m = l.mol_idxs[k];
+        t[k] = make_int4(l.atom_idxs[k], m, l.atom_idxs[l.mol_offsets[m]], l.atom_idxs[l.mol_offsets[m + 1] - 1]);
+    }
+    num_target_atoms_ = static_cast<int>(t.size());
+    d_targets_.realloc(t.size());
+    d_targets_.copy_from(t.data());
+}
+
+template <typename Real>
+void NonbondedMolEnergyPotential<Real>::mol_energies_staged(const Vec4<Real> *d_xr, const Vec4<Real> *d_pr, const double *d_box, i128 *d_out, cudaStream_t stream) {
+    TMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(i128) * num_target_mols_, stream));
+    if (num_target_atoms_ == 0) {
+        return;
+    }
+    const int bx = ceil_div(num_target_atoms_, ME_THREADS);
+    // enough slices of the atom range to fill the machine a few times over
+    const int by = std::max(1, std::min(ceil_div(N_, ME_THREADS), ceil_div(4 * sm_count(), bx)));
+    TMB_LAUNCH(k_mol_energies<Real>, dim3(bx, by), ME_THREADS, 0, stream, N_, num_target_atoms_, d_targets_.data, d_xr, d_pr, d_box, beta_, cutoff_squared_, d_out);
+}
+
+template <typename Real>
+void NonbondedMolEnergyPotential<Real>::mol_energies_device(
+    int N, int target_mols, const double *d_coords, const double *d_params, const double *d_box, i128 *d_out, cudaStream_t stream) {
+    if (N != N_) {
+        throw std::runtime_error("N != N_");
+    }
+    if (target_mols != num_target_mols_) {
+        throw std::runtime_error("target_mols != num_target_mols_");
+    }
+    if (d_xr_.length != static_cast<size_t>(N_)) {
+        d_xr_.realloc(N_);
+        d_pr_.realloc(N_);
+    }
+    TMB_LAUNCH(k_stage_atoms<Real>, ceil_div(N_, 256), 256, 0, stream, N_, d_coords, d_params, d_xr_.data, d_pr_.data);
+    mol_energies_staged(d_xr_.data, d_pr_.data, d_box, d_out, stream);
+}
+
+template <typename Real>
+std::vector<i128> NonbondedMolEnergyPotential<Real>::mol_energies_host(int N, int P, const double *h_coords, const double *h_params, const double *h_box) {
+    DeviceBuffer<double> d_coords(static_cast<size_t>(N) * 3), d_params(P), d_box(9);
+    d_coords.copy_from(h_coords);
+    d_params.copy_from(h_params);
+    d_box.copy_from(h_box);
+    DeviceBuffer<i128> d_out(num_target_mols_);
+    cudaStream_t stream = main_stream();
+    mol_energies_device(N, num_target_mols_, d_coords.data, d_params.data, d_box.data, d_out.data, stream);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<i128> out(num_target_mols_);
+    d_out.copy_to(out.data());
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename Real>
+SegmentedSumExp<Real>::SegmentedSumExp(int max_vals_per_segment, int num_segments)
+    : max_vals_per_segment_(max_vals_per_segment), num_segments_(num_segments) {}
+
+struct FlatSegments {
+    std::vector<int> offsets;
+    int total = 0;
+};
+
+template <typename Real> std::vector<Real> SegmentedSumExp<Real>::logsumexp_host(const std::vector<std::vector<Real>> &vals) {
+    const int num_segments = static_cast<int>(vals.size());
+    std::vector<int> offsets(num_segments + 1, 0);
+    std::vector<Real> flat;
+    for (int i = 0; i < num_segments; i++) {
+        if (vals[i].empty()) {
+            throw std::runtime_error("empty array not allowed");
+        }
+        flat.insert(flat.end(), vals[i].begin(), vals[i].end());
+        offsets[i + 1] = static_cast<int>(flat.size());
+    }
+    const int total = offsets[num_segments];
+    if (total > max_vals_per_segment_ * num_segments_) {
+        throw std::runtime_error(
+            "SegmentedSumExp::total values is greater than buffer size:  total_values=" + std::to_string(total) +
+            ", buffer_size=" + std::to_string(max_vals_per_segment_ * num_segments_));
+    }
+    if (num_segments > num_segments_) {
+        throw std::runtime_error(
+            "SegmentedSumExp::number of segments must be less than or equal: num_segments=" + std::to_string(num_segments) +
+            ", num_segments_=" + std::to_string(num_segments_));
+    }
+    std::vector<Real> out(num_segments);
+    if (num_segments == 0) {
+        return out;
+    }
+    DeviceBuffer<Real> d_vals(flat.size()), d_max(num_segments), d_sum(num_segments);
+    DeviceBuffer<int> d_off(offsets.size());
+    d_vals.copy_from(flat.data());
+    d_off.copy_from(offsets.data());
+    cudaStream_t stream = main_stream();
+    TMB_LAUNCH(k_segmented_sumexp<Real>, std::min(num_segments, 4 * sm_count()), EX_THREADS, 0, stream, num_segments, d_off.data, d_vals.data, d_max.data, d_sum.data);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<Real> h_max(num_segments), h_sum(num_segments);
+    d_max.copy_to(h_max.data());
+    d_sum.copy_to(h_sum.data());
+    for (int i = 0; i < num_segments; i++) {
+        out[i] = h_max[i] + std::log(h_sum[i]);
+    }
+    return out;
+}
+
+template <typename Real>
+SegmentedWeightedRandomSampler<Real>::SegmentedWeightedRandomSampler(int max_vals_per_segment, int num_segments, int seed)
+    : max_vals_per_segment_(max_vals_per_segment), num_segments_(num_segments),
+      d_noise_(static_cast<size_t>(max_vals_per_segment) * num_segments) {
+    TMB_CURAND(curandCreateGenerator(&rng_, CURAND_RNG_PSEUDO_DEFAULT));
+    TMB_CURAND(curandSetPseudoRandomGeneratorSeed(rng_, seed));
+}
+template <typename Real> SegmentedWeightedRandomSampler<Real>::~SegmentedWeightedRandomSampler() {
+    if (rng_ != nullptr) {
+        curandDestroyGenerator(rng_);
+    }
+}
+
+template <typename Real> std::vector<int> SegmentedWeightedRandomSampler<Real>::sample_host(const std::vector<std::vector<Real>> &weights) {
+    const int num_segments = static_cast<int>(weights.size());
+    std::vector<int> offsets(num_segments + 1, 0);
+    std::vector<Real> log_probs;
+    const Real inf = std::numeric_limits<Real>::infinity();
+    for (int i = 0; i < num_segments; i++) {
+        if (weights[i].empty()) {
+            throw std::runtime_error("empty probability distribution not allowed");
+        }
+        for (Real w : weights[i]) {
+            if (w == inf) {
+                throw std::runtime_error("unable to use infinity as a weight");
+            } else if (std::isnan(w)) {
+                throw std::runtime_error("unable to use nan as a weight");
+            } else if (w < static_cast<Real>(0)) {
+                throw std::runtime_error("unable to use negative values as a weight");
+            }
+            log_probs.push_back(std::log(w));
+        }
+        offsets[i + 1] = static_cast<int>(log_probs.size());
+    }
+    const int total = offsets[num_segments];
+    if (total > max_vals_per_segment_ * num_segments_) {
+        throw std::runtime_error(
+            "SegmentedWeightedRandomerSampler::total values is greater than buffer size:  vals_per_segment * num_segments=" +
+            std::to_string(total) + ", buffer_size=" + std::to_string(max_vals_per_segment_ * num_segments_));
+    }
+    if (num_segments != num_segments_) {
+        throw std::runtime_error(
+            "SegmentedWeightedRandomerSampler::number of segments don't match: num_segments=" + std::to_string(num_segments) +
+            ", num_segments_=" + std::to_string(num_segments_));
+    }
+    DeviceBuffer<Real> d_logp(log_probs.size());
+    DeviceBuffer<int> d_off(offsets.size()), d_out(num_segments);
+    d_logp.copy_from(log_probs.data());
+    d_off.copy_from(offsets.data());
+    cudaStream_t stream = main_stream();
+    TMB_CURAND(curandSetStream(rng_, stream));
+    // the whole noise buffer is drawn per call, as in the reference (sample_device): same stream position afterwards
+    TMB_CURAND(gen_uniform(rng_, d_noise_.data, d_noise_.length));
+    TMB_LAUNCH(k_segmented_gumbel_argmax<Real>, std::min(num_segments, 4 * sm_count()), EX_THREADS, 0, stream, num_segments, d_off.data, d_logp.data, d_noise_.data, d_out.data);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<int> out(num_segments);
+    d_out.copy_to(out.data());
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static size_t round_up_even(size_t n) { return n + (n % 2); }
+
+template <typename Real>
+BDExchangeMove<Real>::BDExchangeMove(
+    int N, const std::vector<std::vector<int>> &target_mols, const std::vector<double> &params, double temperature, double nb_beta,
+    double cutoff, int seed, int num_proposals_per_move, int interval, int batch_size)
+    : Mover(interval), N_(N), mol_size_(static_cast<int>(target_mols[0].size())), num_proposals_per_move_(num_proposals_per_move),
+      num_target_mols_(static_cast<int>(target_mols.size())), nb_beta_(static_cast<Real>(nb_beta)),
+      beta_(static_cast<Real>(1.0 / (BOLTZ * temperature))), cutoff_squared_(static_cast<Real>(cutoff * cutoff)), batch_size_(batch_size),
+      first_atom_(target_mols[0].empty() ? 0 : *std::min_element(target_mols[0].begin(), target_mols[0].end())),
+      mol_potential_(N, target_mols, nb_beta, cutoff), d_params_(params.size()), d_xr_(N), d_pr_(N),
+      d_prop_(static_cast<size_t>(batch_size) * std::max(1, mol_size_)), d_before_E_(num_target_mols_),
+      d_after_E_(static_cast<size_t>(batch_size) * num_target_mols_), d_total_(batch_size), d_logw_before_(num_target_mols_),
+      d_logw_after_(static_cast<size_t>(batch_size) * num_target_mols_), d_lse_before_(2), d_lse_after_max_(batch_size),
+      d_lse_after_sum_(batch_size), d_samples_(batch_size), d_state_(ST_WORDS), d_num_accepted_(1),
+      d_quat_(round_up_even(static_cast<size_t>(4) * num_proposals_per_move)), d_trans_(static_cast<size_t>(3) * num_proposals_per_move),
+      d_sample_noise_(static_cast<size_t>(num_target_mols_) * num_proposals_per_move), d_mh_(num_proposals_per_move) {
+    if (num_proposals_per_move_ <= 0) {
+        throw std::runtime_error("proposals per move must be greater than 0");
+    }
+    if (mol_size_ == 0) {
+        throw std::runtime_error("must provide non-empty molecule indices");
+    }
+    verify_mols_contiguous(target_mols);
+    for (const auto &m : target_mols) {
+        if (static_cast<int>(m.size()) != mol_size_) {
+            throw std::runtime_error("only support running with mols with constant size, got mixed sizes");
+        }
+    }
+    if (static_cast<int>(params.size()) != N * P_PER_ATOM) {
+        throw std::runtime_error("Number of parameters must match N");
+    }
+    d_params_.copy_from(params.data());
+    d_lse_before_.zero();
+    d_lse_after_max_.zero();
+    d_lse_after_sum_.zero();
+    d_num_accepted_.zero();
+    d_state_.zero();
+    d_logw_before_.zero();
+    d_logw_after_.zero();
+    d_after_E_.zero();
+    // four generators so that the sequences do not depend on the batch size (reference bd_exchange_move.cu:96-108)
+    TMB_CURAND(curandCreateGenerator(&rng_quat_, CURAND_RNG_PSEUDO_DEFAULT));
+    TMB_CURAND(curandSetPseudoRandomGeneratorSeed(rng_quat_, seed));
+    TMB_CURAND(curandCreateGenerator(&rng_trans_, CURAND_RNG_PSEUDO_DEFAULT));
+    TMB_CURAND(curandSetPseudoRandomGeneratorSeed(rng_trans_, seed + 1));
+    TMB_CURAND(curandCreateGenerator(&rng_samples_, CURAND_RNG_PSEUDO_DEFAULT));
+    TMB_CURAND(curandSetPseudoRandomGeneratorSeed(rng_samples_, seed + 2));
+    TMB_CURAND(curandCreateGenerator(&rng_mh_, CURAND_RNG_PSEUDO_DEFAULT));
+    TMB_CURAND(curandSetPseudoRandomGeneratorSeed(rng_mh_, seed + 3));
+
+    const char *mode = std::getenv("TMB_BD_LOOP");
+    host_loop_ = mode != nullptr && std::strcmp(mode, "host") == 0;
+    int per_sm = 0;
+    TMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bd_move<Real>, EX_THREADS, 0));
+    if (per_sm < 1) {
+        throw std::runtime_error("BDExchangeMove: the move kernel does not fit on an SM");
+    }
+    coop_blocks_ = sm_count() * std::min(per_sm, 2);
+    TMB_CUDA(cudaDeviceSynchronize());
+}
+
+template <typename Real> BDExchangeMove<Real>::~BDExchangeMove() {
+    for (curandGenerator_t g : {rng_quat_, rng_trans_, rng_samples_, rng_mh_}) {
+        if (g != nullptr) {
+            curandDestroyGenerator(g);
+        }
+    }
+}
+
+template <typename Real> BDDevice<Real> BDExchangeMove<Real>::device_args(double *d_coords, const double *d_box, bool scale, bool sample) {
+    BDDevice<Real> a;
+    a.N = N_;
+    a.M = num_target_mols_;
+    a.S = mol_size_;
+    a.B = batch_size_;
+    a.P = num_proposals_per_move_;
+    a.first = first_atom_;
+    a.sample = sample ? 1 : 0;
+    a.scale = scale ? 1 : 0;
+    a.nb_beta = nb_beta_;
+    a.beta = beta_;
+    a.cutoff2 = cutoff_squared_;
+    a.coords = d_coords;
+    a.box = d_box;
+    a.xr = d_xr_.data;
+    a.pr = d_pr_.data;
+    a.prop = d_prop_.data;
+    a.before_E = d_before_E_.data;
+    a.after_E = d_after_E_.data;
+    a.total = d_total_.data;
+    a.logw_before = d_logw_before_.data;
+    a.logw_after = d_logw_after_.data;
+    a.lse_before = d_lse_before_.data;
+    a.lse_after_max = d_lse_after_max_.data;
+    a.lse_after_sum = d_lse_after_sum_.data;
+    a.samples = d_samples_.data;
+    a.state = d_state_.data;
+    a.num_accepted = d_num_accepted_.data;
+    a.quat = d_quat_.data;
+    a.trans = d_trans_.data;
+    a.sample_noise = d_sample_noise_.data;
+    a.mh = d_mh_.data;
+    return a;
+}
+
+template <typename Real> void BDExchangeMove<Real>::initial_log_weights_device(double *d_coords, const double *d_box, cudaStream_t stream) {
+    TMB_LAUNCH(k_stage_atoms<Real>, ceil_div(N_, 256), 256, 0, stream, N_, d_coords, d_params_.data, d_xr_.data, d_pr_.data);
+    mol_potential_.mol_energies_staged(d_xr_.data, d_pr_.data, d_box, d_before_E_.data, stream);
+    TMB_LAUNCH(k_bd_initial_weights<Real>, 1, EX_THREADS, 0, stream, num_target_mols_, beta_, d_before_E_.data, d_logw_before_.data, d_lse_before_.data);
+}
+
+template <typename Real> void BDExchangeMove<Real>::run_phase(int phase, const BDDevice<Real> &a, cudaStream_t stream) {
+    TMB_LAUNCH(k_bd_phase<Real>, coop_blocks_, EX_THREADS, 0, stream, a, phase);
+}
+
+template <typename Real> void BDExchangeMove<Real>::move(int N, double *d_coords, double *d_box, cudaStream_t stream) {
+    if (N != N_) {
+        throw std::runtime_error("N != N_");
+    }
+    step_++;
+    if (step_ % interval_ != 0) {
+        return;
+    }
+    TMB_CURAND(curandSetStream(rng_quat_, stream));
+    TMB_CURAND(curandSetStream(rng_trans_, stream));
+    TMB_CURAND(curandSetStream(rng_samples_, stream));
+    TMB_CURAND(curandSetStream(rng_mh_, stream));
+    TMB_CUDA(cudaMemsetAsync(d_state_.data, 0, d_state_.bytes(), stream));
+
+    initial_log_weights_device(d_coords, d_box, stream);
+
+    // all noise of the move up front, one draw per generator (reference bd_exchange_move.cu:197-201)
+    TMB_CURAND(gen_normal(rng_quat_, d_quat_.data, d_quat_.length));
+    TMB_CURAND(gen_uniform(rng_trans_, d_trans_.data, d_trans_.length));
+    TMB_CURAND(gen_uniform(rng_samples_, d_sample_noise_.data, d_sample_noise_.length));
+    TMB_CURAND(gen_uniform(rng_mh_, d_mh_.data, d_mh_.length));
+
+    BDDevice<Real> a = device_args(d_coords, d_box, true, true);
+    if (host_loop_) {
+        int off = 0;
+        while (off < num_proposals_per_move_) {
+            for (int phase = 0; phase < 4; phase++) {
+                run_phase(phase, a, stream);
+            }
+            TMB_CUDA(cudaMemcpyAsync(&off, d_state_.data + ST_OFFSET, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            TMB_CUDA(cudaStreamSynchronize(stream));
+        }
+    } else {
+        void *args[] = {&a};
+        TMB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_bd_move<Real>), dim3(coop_blocks_), dim3(EX_THREADS), args, 0, stream));
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    num_attempted_ += num_proposals_per_move_;
+}
+
+template <typename Real>
+std::vector<std::vector<Real>> BDExchangeMove<Real>::compute_incremental_log_weights_host(
+    int N, const double *h_coords, const double *h_box, const int *h_mol_idxs, const Real *h_quaternions, const Real *h_translations) {
+    if (N != N_) {
+        throw std::runtime_error("N != N_");
+    }
+    DeviceBuffer<double> d_coords(static_cast<size_t>(N) * 3), d_box(9);
+    d_coords.copy_from(h_coords);
+    d_box.copy_from(h_box);
+    // the caller's batch goes to the head of the noise buffers (P >= B)
+    TMB_CUDA(cudaMemcpy(d_quat_.data, h_quaternions, sizeof(Real) * 4 * batch_size_, cudaMemcpyHostToDevice));
+    TMB_CUDA(cudaMemcpy(d_trans_.data, h_translations, sizeof(Real) * 3 * batch_size_, cudaMemcpyHostToDevice));
+    TMB_CUDA(cudaMemcpy(d_samples_.data, h_mol_idxs, sizeof(int) * batch_size_, cudaMemcpyHostToDevice));
+    cudaStream_t stream = main_stream();
+    TMB_CUDA(cudaMemsetAsync(d_state_.data, 0, d_state_.bytes(), stream));
+    initial_log_weights_device(d_coords.data, d_box.data, stream);
+    // translations are used as given, the molecules are the caller's (reference bd_exchange_move.cu:437-487)
+    BDDevice<Real> a = device_args(d_coords.data, d_box.data, false, false);
+    for (int phase = 0; phase < 3; phase++) {
+        run_phase(phase, a, stream);
+    }
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<Real> flat = get_after_log_weights();
+    std::vector<std::vector<Real>> out(batch_size_);
+    for (int b = 0; b < batch_size_; b++) {
+        out[b].assign(flat.begin() + static_cast<size_t>(b) * num_target_mols_, flat.begin() + static_cast<size_t>(b + 1) * num_target_mols_);
+    }
+    return out;
+}
+
+template <typename Real> std::vector<Real> BDExchangeMove<Real>::compute_initial_log_weights_host(int N, const double *h_coords, const double *h_box) {
+    if (N != N_) {
+        throw std::runtime_error("N != N_");
+    }
+    DeviceBuffer<double> d_coords(static_cast<size_t>(N) * 3), d_box(9);
+    d_coords.copy_from(h_coords);
+    d_box.copy_from(h_box);
+    cudaStream_t stream = main_stream();
+    initial_log_weights_device(d_coords.data, d_box.data, stream);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    return get_before_log_weights();
+}
+
+template <typename Real> std::vector<Real> BDExchangeMove<Real>::get_before_log_weights() {
+    std::vector<Real> out(d_logw_before_.length);
+    d_logw_before_.copy_to(out.data());
+    return out;
+}
+template <typename Real> std::vector<Real> BDExchangeMove<Real>::get_after_log_weights() {
+    std::vector<Real> out(d_logw_after_.length);
+    d_logw_after_.copy_to(out.data());
+    return out;
+}
+
+template <typename Real> static Real host_nan_to_inf(Real v) { return std::isnan(v) ? std::numeric_limits<Real>::infinity() : v; }
+
+template <typename Real> double BDExchangeMove<Real>::raw_log_probability_host() {
+    Real before[2], after_max, after_sum;
+    d_lse_before_.copy_to(before);
+    TMB_CUDA(cudaMemcpy(&after_max, d_lse_after_max_.data, sizeof(Real), cudaMemcpyDeviceToHost));
+    TMB_CUDA(cudaMemcpy(&after_sum, d_lse_after_sum_.data, sizeof(Real), cudaMemcpyDeviceToHost));
+    const Real b = host_nan_to_inf<Real>(before[0] + std::log(before[1]));
+    const Real a = host_nan_to_inf<Real>(after_max + std::log(after_sum));
+    return static_cast<double>(b - a);
+}
+template <typename Real> double BDExchangeMove<Real>::log_probability_host() { return std::fmin(raw_log_probability_host(), 0.0); } // NaN-safe like the CUDA host min()
+
+template <typename Real> size_t BDExchangeMove<Real>::n_accepted() const {
+    u64 v = 0;
+    d_num_accepted_.copy_to(&v);
+    return static_cast<size_t>(v);
+}
+
+template <typename Real> std::vector<double> BDExchangeMove<Real>::get_params() {
+    std::vector<double> out(d_params_.length);
+    d_params_.copy_to(out.data());
+    return out;
+}
+template <typename Real> void BDExchangeMove<Real>::set_params(const std::vector<double> &params) {
+    if (d_params_.length != params.size()) {
+        throw std::runtime_error("number of params don't match");
+    }
+    d_params_.copy_from(params.data());
+}
+template <typename Real> void BDExchangeMove<Real>::set_params_device(int size, const double *d_p, cudaStream_t stream) {
+    if (d_params_.length != static_cast<size_t>(size)) {
+        throw std::runtime_error("number of params don't match");
+    }
+    TMB_CUDA(cudaMemcpyAsync(d_params_.data, d_p, d_params_.bytes(), cudaMemcpyDeviceToDevice, stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename Real>
+std::vector<Real> atom_by_atom_energies(
+    int N, const std::vector<int> &target_atoms, const double *coords, const double *params, const double *box, Real nb_beta, Real cutoff) {
+    const int T = static_cast<int>(target_atoms.size());
+    std::vector<Real> out(static_cast<size_t>(T) * N);
+    if (T == 0 || N == 0) {
+        return out;
+    }
+    for (int t : target_atoms) {
+        if (t < 0 || t >= N) {
+            throw std::runtime_error("target atoms must be between 0 and N");
+        }
+    }
+    DeviceBuffer<double> d_coords(static_cast<size_t>(N) * 3), d_params(static_cast<size_t>(N) * 4), d_box(9);
+    DeviceBuffer<int> d_t(T);
+    DeviceBuffer<Vec4<Real>> d_xr(N), d_pr(N);
+    DeviceBuffer<Real> d_out(out.size());
+    d_coords.copy_from(coords);
+    d_params.copy_from(params);
+    d_box.copy_from(box);
+    d_t.copy_from(target_atoms.data());
+    cudaStream_t stream = main_stream();
+    TMB_LAUNCH(k_stage_atoms<Real>, ceil_div(N, 256), 256, 0, stream, N, d_coords.data, d_params.data, d_xr.data, d_pr.data);
+    const Real cutoff2 = cutoff * cutoff; // formed in Real (reference all_atom_energies.cu:23)
+    TMB_LAUNCH(k_atom_by_atom<Real>, dim3(ceil_div(N, 256), T), 256, 0, stream, N, T, d_t.data, d_xr.data, d_pr.data, d_box.data, nb_beta, cutoff2, d_out.data);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    d_out.copy_to(out.data());
+    return out;
+}
+
+template <typename Real> void rotate_coordinates_host(int N, int n_rotations, const double *coords, const Real *quaternions, double *out) {
+    if (N == 0 || n_rotations == 0) {
+        return;
+    }
+    DeviceBuffer<double> d_coords(static_cast<size_t>(N) * 3), d_out(static_cast<size_t>(N) * n_rotations * 3);
+    DeviceBuffer<Real> d_q(static_cast<size_t>(n_rotations) * 4);
+    d_coords.copy_from(coords);
+    d_q.copy_from(quaternions);
+    cudaStream_t stream = main_stream();
+    TMB_LAUNCH(k_rotate_coordinates<Real>, dim3(ceil_div(n_rotations, 256), N), 256, 0, stream, N, n_rotations, d_coords.data, d_q.data, d_out.data);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    d_out.copy_to(out);
+}
+
+template <typename Real>
+void rotate_and_translate_mol_host(
+    int N, int batch_size, const double *mol_coords, const double *box, const Real *quaternions, const Real *translations, double *out) {
+    if (N == 0 || batch_size == 0) {
+        return;
+    }
+    std::vector<Vec4<Real>> h_x(N);
+    for (int i = 0; i < N; i++) {
+        h_x[i].x = static_cast<Real>(mol_coords[i * 3 + 0]);
+        h_x[i].y = static_cast<Real>(mol_coords[i * 3 + 1]);
+        h_x[i].z = static_cast<Real>(mol_coords[i * 3 + 2]);
+        h_x[i].w = 0;
+    }
+    DeviceBuffer<Vec4<Real>> d_x(N), d_out(static_cast<size_t>(N) * batch_size);
+    DeviceBuffer<double> d_box(9);
+    DeviceBuffer<Real> d_q(static_cast<size_t>(batch_size) * 4), d_t(static_cast<size_t>(batch_size) * 3);
+    d_x.copy_from(h_x.data());
+    d_box.copy_from(box);
+    d_q.copy_from(quaternions);
+    d_t.copy_from(translations);
+    cudaStream_t stream = main_stream();
+    TMB_LAUNCH(k_rotate_and_translate_mol<Real>, ceil_div(batch_size, 128), 128, 0, stream, N, batch_size, d_x.data, d_box.data, d_q.data, d_t.data, d_out.data);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<Vec4<Real>> h_out(d_out.length);
+    d_out.copy_to(h_out.data());
+    for (size_t k = 0; k < h_out.size(); k++) {
+        out[k * 3 + 0] = static_cast<double>(h_out[k].x);
+        out[k * 3 + 1] = static_cast<double>(h_out[k].y);
+        out[k * 3 + 2] = static_cast<double>(h_out[k].z);
+    }
+}
+
+template class NonbondedMolEnergyPotential<float>;
+template class NonbondedMolEnergyPotential<double>;
+template class SegmentedSumExp<float>;
+template class SegmentedSumExp<double>;
+template class SegmentedWeightedRandomSampler<float>;
+template class SegmentedWeightedRandomSampler<double>;
+template class BDExchangeMove<float>;
+template class BDExchangeMove<double>;
+template std::vector<float> atom_by_atom_energies<float>(int, const std::vector<int> &, const double *, const double *, const double *, float, float);
+template std::vector<double> atom_by_atom_energies<double>(int, const std::vector<int> &, const double *, const double *, const double *, double, double);
+template void rotate_coordinates_host<float>(int, int, const double *, const float *, double *);
+template void rotate_coordinates_host<double>(int, int, const double *, const double *, double *);
+template void rotate_and_translate_mol_host<float>(int, int, const double *, const double *, const float *, const float *, double *);
+template void rotate_and_translate_mol_host<double>(int, int, const double *, const double *, const double *, const double *, double *);
+
+} // namespace tmb

@@ -780,6 +780,340 @@ class MonteCarloBarostat(Mover):
         return int(out[0]), int(out[1])
 
 
+def _flatten_groups(group_idxs):
+    """list of index lists -> (flat int32, offsets int32, count), the layout the C ABI takes for molecules / groups."""
+    groups = [np.asarray(g, dtype=np.int32).reshape(-1) for g in group_idxs]
+    offsets = np.zeros(len(groups) + 1, dtype=np.int32)
+    if groups:
+        offsets[1:] = np.cumsum([len(g) for g in groups])
+    flat = np.ascontiguousarray(np.concatenate(groups) if groups else np.zeros(0, dtype=np.int32), dtype=np.int32)
+    return flat, offsets, len(groups)
+
+
+class _BDExchangeMove(Mover):
+    """BDExchangeMove_{f32,f64}(N, target_mols, params, temperature, nb_beta, cutoff, seed, num_proposals_per_move,
+    interval, batch_size=1): water exchange by biased deletion (wrap_kernels.cpp:1732-1900; bd_exchange_move.cu; the
+    Python reference is timemachine/md/exchange/exchange_mover.py::BDExchangeMove).  Same four cuRAND streams as the
+    reference: the same seed proposes and accepts the same moves."""
+
+    _precision = F32
+
+    def __init__(
+        self, N, target_mols, params, temperature, nb_beta, cutoff, seed, num_proposals_per_move, interval, batch_size=1
+    ):
+        params = np.asarray(params, dtype=np.float64)
+        if int(num_proposals_per_move) <= 0:
+            raise RuntimeError("proposals per move must be greater than 0")
+        if params.ndim != 2:
+            raise RuntimeError("parameters dimensions must be 2")
+        if params.shape[0] != int(N):
+            raise RuntimeError("Number of parameters must match N")
+        params = np.ascontiguousarray(params)
+        flat, offsets, n_mols = _flatten_groups(target_mols)
+        self._handle = None
+        h = _new_handle()
+        _check(
+            _L.tmb_bd_exchange_move_create(
+                self._precision, int(N), _ptr(flat, C.c_int32), _ptr(offsets, C.c_int32), n_mols, _ptr(params, C.c_double),
+                int(params.size), float(temperature), float(nb_beta), float(cutoff), int(seed), int(num_proposals_per_move),
+                int(interval), int(batch_size), C.byref(h),
+            )
+        )
+        self._handle = h
+        self._N = int(N)
+        self._real = np.float32 if self._precision == F32 else np.float64
+
+    def _num_target_mols(self) -> int:
+        n = C.c_int()
+        _check(_L.tmb_bd_exchange_move_num_target_mols(self._handle, C.byref(n)))
+        return n.value
+
+    def batch_size(self) -> int:
+        n = C.c_int()
+        _check(_L.tmb_bd_exchange_move_batch_size(self._handle, C.byref(n)))
+        return n.value
+
+    def compute_initial_log_weights(self, coords, box) -> list:
+        coords, box = _f64(coords), _f64(box)
+        _verify_coords_and_box(coords, box)
+        out = np.empty(self._num_target_mols(), dtype=np.float64)
+        _check(
+            _L.tmb_bd_exchange_move_initial_log_weights(
+                self._handle, coords.shape[0], _ptr(coords, C.c_double), _ptr(box, C.c_double), _ptr(out, C.c_double)
+            )
+        )
+        return list(out.astype(self._real))
+
+    def compute_incremental_log_weights(self, coords, box, mol_idxs, quaternions, translation) -> list:
+        coords, box = _f64(coords), _f64(box)
+        _verify_coords_and_box(coords, box)
+        mol_idxs = _i32(mol_idxs).reshape(-1)
+        quaternions = _f64(quaternions)
+        translation = _f64(translation)
+        B = self.batch_size()
+        if mol_idxs.size != B:
+            raise RuntimeError("number of mol idxs must match batch size")
+        if quaternions.shape[0] != B:
+            raise RuntimeError("number of quaternions must match batch size")
+        if quaternions.shape[1] != 4:
+            raise RuntimeError("each quaternion must be of length 4")
+        if translation.shape[0] != B:
+            raise RuntimeError("number of translations must match batch size")
+        if translation.shape[1] != 3:
+            raise RuntimeError("each translation must be of length 3")
+        M = self._num_target_mols()
+        out = np.empty((B, M), dtype=np.float64)
+        _check(
+            _L.tmb_bd_exchange_move_incremental_log_weights(
+                self._handle, coords.shape[0], _ptr(coords, C.c_double), _ptr(box, C.c_double), _ptr(mol_idxs, C.c_int32),
+                _ptr(quaternions, C.c_double), _ptr(translation, C.c_double), _ptr(out, C.c_double),
+            )
+        )
+        return [list(row.astype(self._real)) for row in out]
+
+    def get_params(self) -> np.ndarray:
+        out = np.empty((self._N, 4), dtype=np.float64)
+        _check(_L.tmb_bd_exchange_move_get_params(self._handle, _ptr(out, C.c_double), int(out.size)))
+        return out
+
+    def set_params(self, params) -> None:
+        params = _f64(params)
+        _check(_L.tmb_bd_exchange_move_set_params(self._handle, _ptr(params, C.c_double), int(params.size)))
+
+    def last_log_probability(self) -> float:
+        v = C.c_double()
+        _check(_L.tmb_bd_exchange_move_last_log_probability(self._handle, C.byref(v)))
+        return v.value
+
+    def last_raw_log_probability(self) -> float:
+        v = C.c_double()
+        _check(_L.tmb_bd_exchange_move_last_raw_log_probability(self._handle, C.byref(v)))
+        return v.value
+
+    def n_accepted(self) -> int:
+        v = C.c_ulonglong()
+        _check(_L.tmb_bd_exchange_move_n_accepted(self._handle, C.byref(v)))
+        return int(v.value)
+
+    def n_proposed(self) -> int:
+        v = C.c_ulonglong()
+        _check(_L.tmb_bd_exchange_move_n_proposed(self._handle, C.byref(v)))
+        return int(v.value)
+
+    def acceptance_fraction(self) -> float:
+        return self.n_accepted() / self.n_proposed()
+
+    def get_before_log_weights(self) -> list:
+        out = np.empty(self._num_target_mols(), dtype=np.float64)
+        _check(_L.tmb_bd_exchange_move_before_log_weights(self._handle, _ptr(out, C.c_double)))
+        return list(out.astype(self._real))
+
+    def get_after_log_weights(self) -> list:
+        out = np.empty(self._num_target_mols() * self.batch_size(), dtype=np.float64)
+        _check(_L.tmb_bd_exchange_move_after_log_weights(self._handle, _ptr(out, C.c_double)))
+        return list(out.astype(self._real))
+
+
+class BDExchangeMove_f32(_BDExchangeMove):
+    _precision = F32
+
+
+class BDExchangeMove_f64(_BDExchangeMove):
+    _precision = F64
+
+
+class _NonbondedMolEnergyPotential:
+    """NonbondedMolEnergyPotential_{f32,f64}(N, target_mols, beta, cutoff).execute(coords, params, box) -> energy of
+    every target molecule with all atoms outside it (wrap_kernels.cpp:234-294; nonbonded_mol_energy.cu)."""
+
+    _precision = F32
+
+    def __init__(self, N, target_mols, beta, cutoff):
+        self._N, self._beta, self._cutoff = int(N), float(beta), float(cutoff)
+        self._flat, self._offsets, self._n_mols = _flatten_groups(target_mols)
+        self._call(None, None, None, None)  # the constructor's argument checks
+
+    def _call(self, coords, params, box, out):
+        _check(
+            _L.tmb_nonbonded_mol_energies(
+                self._precision, self._N, _ptr(self._flat, C.c_int32), _ptr(self._offsets, C.c_int32), self._n_mols,
+                self._beta, self._cutoff, _ptr(coords, C.c_double), _ptr(params, C.c_double), _ptr(box, C.c_double), out,
+            )
+        )
+
+    def execute(self, coords, params, box) -> np.ndarray:
+        coords, params, box = _f64(coords), _f64(params), _f64(box)
+        _verify_coords_and_box(coords, box)
+        if coords.shape[0] != params.shape[0]:
+            raise RuntimeError("params N != coords N")
+        out = (I128 * self._n_mols)()
+        self._call(coords, params, box, out)
+        return _energies_to_float(out)
+
+
+class NonbondedMolEnergyPotential_f32(_NonbondedMolEnergyPotential):
+    _precision = F32
+
+
+class NonbondedMolEnergyPotential_f64(_NonbondedMolEnergyPotential):
+    _precision = F64
+
+
+def _atom_by_atom_energies(precision, target_atoms, coords, params, box, nb_beta, cutoff):
+    coords, params, box = _f64(coords), _f64(params), _f64(box)
+    _verify_coords_and_box(coords, box)
+    target_atoms = _i32(target_atoms).reshape(-1)
+    out = np.empty((target_atoms.size, coords.shape[0]), dtype=np.float64)
+    _check(
+        _L.tmb_atom_by_atom_energies(
+            precision, coords.shape[0], _ptr(target_atoms, C.c_int32), int(target_atoms.size), _ptr(coords, C.c_double),
+            _ptr(params, C.c_double), _ptr(box, C.c_double), float(nb_beta), float(cutoff), _ptr(out, C.c_double),
+        )
+    )
+    return out.astype(np.float32 if precision == F32 else np.float64)
+
+
+def atom_by_atom_energies_f32(target_atoms, coords, params, box, nb_beta, cutoff):
+    """Pair energies of the target atoms with every atom, [T, N] (wrap_kernels.cpp:2004-2030)."""
+    return _atom_by_atom_energies(F32, target_atoms, coords, params, box, nb_beta, cutoff)
+
+
+def atom_by_atom_energies_f64(target_atoms, coords, params, box, nb_beta, cutoff):
+    return _atom_by_atom_energies(F64, target_atoms, coords, params, box, nb_beta, cutoff)
+
+
+def _flatten_values(values):
+    rows = [np.asarray(v, dtype=np.float64).reshape(-1) for v in values]
+    offsets = np.zeros(len(rows) + 1, dtype=np.int32)
+    if rows:
+        offsets[1:] = np.cumsum([len(r) for r in rows])
+    flat = np.ascontiguousarray(np.concatenate(rows) if rows else np.zeros(0), dtype=np.float64)
+    return flat, offsets, len(rows)
+
+
+class _SegmentedSumExp:
+    """SegmentedSumExp_{f32,f64}(max_vals_per_segment, num_segments).logsumexp(values) (wrap_kernels.cpp:1693-1730)."""
+
+    _precision = F32
+
+    def __init__(self, max_vals_per_segment, num_segments):
+        self._max_vals, self._num_segments = int(max_vals_per_segment), int(num_segments)
+
+    def logsumexp(self, values) -> list:
+        flat, offsets, n = _flatten_values(values)
+        out = np.empty(n, dtype=np.float64)
+        _check(
+            _L.tmb_segmented_logsumexp(
+                self._precision, self._max_vals, self._num_segments, _ptr(flat, C.c_double), _ptr(offsets, C.c_int32), n,
+                _ptr(out, C.c_double),
+            )
+        )
+        return list(out.astype(np.float32 if self._precision == F32 else np.float64))
+
+
+class SegmentedSumExp_f32(_SegmentedSumExp):
+    _precision = F32
+
+
+class SegmentedSumExp_f64(_SegmentedSumExp):
+    _precision = F64
+
+
+class _SegmentedWeightedRandomSampler:
+    """SegmentedWeightedRandomSampler_{f32,f64}(max_vals_per_segment, segments, seed).sample(weights): one index per
+    segment, drawn with probability proportional to its weight (Gumbel-max trick; wrap_kernels.cpp:196-232)."""
+
+    _precision = F32
+    _handle = None
+
+    def __init__(self, max_vals_per_segment, segments, seed):
+        h = _new_handle()
+        _check(_L.tmb_weighted_sampler_create(self._precision, int(max_vals_per_segment), int(segments), int(seed), C.byref(h)))
+        self._handle = h
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _L.tmb_weighted_sampler_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def sample(self, weights) -> list:
+        flat, offsets, n = _flatten_values(weights)
+        out = np.empty(n, dtype=np.int32)
+        _check(_L.tmb_weighted_sampler_sample(self._handle, _ptr(flat, C.c_double), _ptr(offsets, C.c_int32), n, _ptr(out, C.c_int32)))
+        return [int(v) for v in out]
+
+
+class SegmentedWeightedRandomSampler_f32(_SegmentedWeightedRandomSampler):
+    _precision = F32
+
+
+class SegmentedWeightedRandomSampler_f64(_SegmentedWeightedRandomSampler):
+    _precision = F64
+
+
+def _rotate_coords(precision, coords, quaternions):
+    coords, quaternions = _f64(coords), _f64(quaternions)
+    _verify_coords(coords)
+    if quaternions.ndim != 2:
+        raise RuntimeError("quaternions dimensions must be 2")
+    if quaternions.shape[-1] != 4:
+        raise RuntimeError("quaternions must have a shape that is 4 dimensional")
+    out = np.empty((coords.shape[0], quaternions.shape[0], 3), dtype=np.float64)
+    _check(
+        _L.tmb_rotate_coords(
+            precision, coords.shape[0], quaternions.shape[0], _ptr(coords, C.c_double), _ptr(quaternions, C.c_double),
+            _ptr(out, C.c_double),
+        )
+    )
+    return out
+
+
+def rotate_coords_f32(coords, quaternions):
+    """Rotate every coordinate by every quaternion, [N, R, 3] (wrap_kernels.cpp:2050-2070)."""
+    return _rotate_coords(F32, coords, quaternions)
+
+
+def rotate_coords_f64(coords, quaternions):
+    return _rotate_coords(F64, coords, quaternions)
+
+
+def _rotate_and_translate_mol(precision, coords, box, quaternions, translations):
+    coords, box, quaternions, translations = _f64(coords), _f64(box), _f64(quaternions), _f64(translations)
+    _verify_coords_and_box(coords, box)
+    if quaternions.ndim != 2:
+        raise RuntimeError("quaternions dimensions must be 2")
+    if quaternions.shape[1] != 4:
+        raise RuntimeError("quaternions must be of length 4")
+    if translations.ndim != 2:
+        raise RuntimeError("translations dimensions must be 2")
+    if translations.shape[1] != 3:
+        raise RuntimeError("translations must be of size 3")
+    if quaternions.shape[0] != translations.shape[0]:
+        raise RuntimeError("Number of quaternions and translations must match")
+    out = np.empty((quaternions.shape[0], coords.shape[0], 3), dtype=np.float64)
+    _check(
+        _L.tmb_rotate_and_translate_mol(
+            precision, coords.shape[0], quaternions.shape[0], _ptr(coords, C.c_double), _ptr(box, C.c_double),
+            _ptr(quaternions, C.c_double), _ptr(translations, C.c_double), _ptr(out, C.c_double),
+        )
+    )
+    return out
+
+
+def rotate_and_translate_mol_f32(coords, box, quaternions, translations):
+    """Rotate a molecule about its centroid and move the centroid to translation * box, per (quaternion, translation)
+    pair, [B, N, 3] (wrap_kernels.cpp:2072-2115)."""
+    return _rotate_and_translate_mol(F32, coords, box, quaternions, translations)
+
+
+def rotate_and_translate_mol_f64(coords, box, quaternions, translations):
+    return _rotate_and_translate_mol(F64, coords, box, quaternions, translations)
+
+
 class Context:
     """Context(x0, v0, box, integrator, bps, movers=None) (wrap_kernels.cpp:296-689).  Movers run after every
     integrator step (context.cu:261-277); MonteCarloBarostat is the one implemented here."""
