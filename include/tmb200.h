@@ -211,6 +211,23 @@ int tmb_bd_exchange_move_n_accepted(tmb_mover m, unsigned long long *out);      
 int tmb_bd_exchange_move_n_proposed(tmb_mover m, unsigned long long *out);      /* :1895 */
 int tmb_bd_exchange_move_before_log_weights(tmb_mover m, double *out);          /* [num_target_mols]      :1897 */
 int tmb_bd_exchange_move_after_log_weights(tmb_mover m, double *out);           /* [B * num_target_mols]  :1898 */
+/* TIBDExchangeMove_{f32,f64}(N, ligand_idxs, target_mols, params, temperature, nb_beta, cutoff, radius, seed,
+ * num_proposals_per_move, interval, batch_size=1): targeted insertion / biased deletion between a sphere of `radius`
+ * around the ligand centroid and the rest of the box.  The tmb_bd_exchange_move_* accessors apply to it as well.
+ *                                                                    wrap_kernels.cpp:1902-1975, tibd_exchange_move.cu */
+int tmb_tibd_exchange_move_create(
+    int precision, int N, const int *ligand_idxs, int n_ligand, const int *mol_atoms, const int *mol_offsets, int n_mols,
+    const double *params, int n_params, double temperature, double nb_beta, double cutoff, double radius, int seed,
+    int num_proposals_per_move, int interval, int batch_size, tmb_mover *out);
+/* inner_and_outer_mols_{f32,f64}(center_atoms, coords, box, group_idxs, radius): flags[m] = 1 when the centroid of
+ * molecule m lies within `radius` of the centroid of center_atoms     wrap_kernels.cpp:2032-2048, exchange.cu:11-63 */
+int tmb_inner_and_outer_mols(
+    int precision, const int *center_atoms, int n_center, int N, const double *coords, const double *box, const int *mol_atoms,
+    const int *mol_offsets, int n_mols, double radius, int *flags);
+/* translations_inside_and_outside_sphere_host_{f32,f64}(n, box, center[3], radius, seed) -> [n, 2, 3]
+ *                                                                    wrap_kernels.cpp:2117-2141, translations.cu:8-42 */
+int tmb_translations_inside_and_outside_sphere(
+    int precision, int n_translations, const double *box, const double *center, double radius, int seed, double *out);
 /* NonbondedMolEnergyPotential_{f32,f64}(N, target_mols, beta, cutoff).execute(coords, params, box) -> [n_mols] fixed
  * point energies (int128, 2^36).  coords == NULL: construct and validate only.   wrap_kernels.cpp:234-294 */
 int tmb_nonbonded_mol_energies(

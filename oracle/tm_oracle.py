@@ -844,3 +844,28 @@ def rotate_and_translate_mol(coords, box, q, translation, scale=True):
     t = t - bd * np.floor(t / bd)
     c = np.mean(coords, axis=0, keepdims=True)
     return quaternion_rotate(coords - c, q) + t
+
+
+def water_groups(coords, box, center, mols, radius):
+    """exchange_mover.py:270-281 get_water_groups: molecules whose centroid lies within `radius` of `center` (minimum
+    image) and the rest."""
+    c = np.array([np.mean(coords[np.asarray(m)], axis=0) for m in mols])
+    d = np.linalg.norm(delta_r(c, np.asarray(center), box), axis=1)
+    return np.nonzero(d < radius)[0], np.nonzero(d >= radius)[0]
+
+
+def _proposal_probability(n_a, n_b):
+    """exchange_mover.py:283-296."""
+    assert n_a >= 0 and n_b >= 0 and (n_a > 0 or n_b > 0)
+    return 0.5 if (n_a > 0 and n_b > 0) else 1.0
+
+
+def tibd_raw_log_probability(log_weights_src_before, log_weights_dest_after, n_src, n_dest, vol_src, vol_dest):
+    """exchange_mover.py:298-323 compute_raw_ratio_given_weights: a molecule leaves a region of n_src molecules and
+    volume vol_src for a region of n_dest molecules and volume vol_dest; log_weights_dest_after includes the moved one."""
+    g_fwd = _proposal_probability(n_src, n_dest)
+    g_rev = _proposal_probability(n_src - 1, n_dest + 1)
+    return (
+        logsumexp(log_weights_src_before) - logsumexp(log_weights_dest_after) + np.log(vol_dest) - np.log(vol_src)
+        + np.log(g_rev) - np.log(g_fwd)
+    )

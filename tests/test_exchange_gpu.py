@@ -458,3 +458,200 @@ def test_bd_exchange_mover_in_context():
     # some water jumped further than thermal motion allows in 100 fs
     jump = np.linalg.norm(xs[-1][0::3] - x[0::3], axis=1)
     assert jump.max() > 0.5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# targeted insertion / biased deletion (reference tests/test_cuda_targeted_insertion_mover.py)
+def ligand_water_system(n_waters, n_ligand_waters=4, seed=2023):
+    """A water box whose `n_ligand_waters` molecules nearest to the box centre play the ligand (no clashes, so no
+    saturated energies, which the reference's device asserts reject); the ligand atoms come first."""
+    s = water_box(n_waters + n_ligand_waters, seed=seed)
+    x, params, box = s["x"], s["params"], s["box"]
+    c = x.reshape(-1, 3, 3).mean(1)
+    order = np.argsort(np.linalg.norm(c - np.diag(box) * 0.5, axis=1), kind="stable")
+    atoms = (order[:, None] * 3 + np.arange(3)[None, :]).reshape(-1)
+    x, params = x[atoms], params[atoms]
+    n_lig = 3 * n_ligand_waters
+    mols = [[n_lig + 3 * i, n_lig + 3 * i + 1, n_lig + 3 * i + 2] for i in range(n_waters)]
+    return x, params, box, mols, np.arange(n_lig, dtype=np.int32)
+
+
+@pytest.mark.parametrize("precision", [np.float64, np.float32])
+@pytest.mark.parametrize("radius", [0.4, 0.9, 2.0])
+def test_inner_and_outer_mols(precision, radius):
+    """test_cuda_targeted_insertion_mover.py:190-219: against the Python reference's get_water_groups."""
+    o = ops()
+    x, params, box, mols, lig = ligand_water_system(300)
+    x = x.copy()
+    x[3 * 50 + 12 :: 41] += box[0, 0]  # atoms in another image
+    inner, outer = klass(o, "inner_and_outer_mols", precision)(lig, x, box, mols, radius)
+    center = x[lig].mean(0)
+    ref_in, ref_out = O.water_groups(x, box, center, mols, radius)
+    # molecules within float rounding of the sphere may land on either side
+    c = np.array([x[m].mean(0) for m in mols])
+    d = np.linalg.norm(O.delta_r(c, center, box), axis=1)
+    sure = np.abs(d - radius) > 1e-5
+    assert set(np.array(inner)[sure[inner]]) == set(ref_in[sure[ref_in]])
+    assert set(np.array(outer)[sure[outer]]) == set(ref_out[sure[ref_out]])
+    assert sorted(inner + outer) == list(range(len(mols)))
+    ref = load_reference_ops()
+    if ref is not None:
+        r_in, r_out = klass(ref, "inner_and_outer_mols", precision)(lig, x, box, mols, radius)
+        assert list(r_in) == inner and list(r_out) == outer
+
+
+@pytest.mark.parametrize("precision", [np.float64, np.float32])
+@pytest.mark.parametrize("n_translations", [1, 33, 1000])
+def test_translations_inside_and_outside_sphere(precision, n_translations):
+    """test_cuda_targeted_insertion_mover.py:223-249: inner translations lie in the sphere, outer ones outside it (under
+    PBC); deterministic per seed; the same numbers as the compiled reference."""
+    o = ops()
+    box = np.diag([3.0, 3.5, 4.0])
+    center = np.array([1.4, 1.9, 2.2])
+    radius = 0.8
+    f = klass(o, "translations_inside_and_outside_sphere_host", precision)
+    t = f(n_translations, box, center, radius, 2023)
+    assert t.shape == (n_translations, 2, 3) and t.dtype == precision
+    d_in = np.linalg.norm(O.delta_r(t[:, 0].astype(np.float64), center, box), axis=1)
+    d_out = np.linalg.norm(O.delta_r(t[:, 1].astype(np.float64), center, box), axis=1)
+    assert np.all(d_in < radius + 1e-5) and np.all(d_out >= radius - 1e-5)
+    np.testing.assert_array_equal(t, f(n_translations, box, center, radius, 2023))
+    assert not np.array_equal(t, f(n_translations, box, center, radius, 2024))
+    if n_translations == 1000:  # uniform in the sphere: the radius^3 law
+        np.testing.assert_allclose(np.mean((d_in / radius) ** 3), 0.5, atol=0.04)
+    with pytest.raises(RuntimeError, match="Center must be of length 3"):
+        f(3, box, np.zeros(2), radius, 1)
+    ref = load_reference_ops()
+    if ref is not None:
+        r = klass(ref, "translations_inside_and_outside_sphere_host", precision)(n_translations, box, center, radius, 2023)
+        if precision == np.float32:
+            np.testing.assert_array_equal(t, r)
+        else:
+            np.testing.assert_allclose(t, r, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("precision", [np.float64, np.float32])
+def test_tibd_exchange_validation(precision):
+    """test_cuda_targeted_insertion_mover.py:253-340."""
+    o = ops()
+    k = klass(o, "TIBDExchangeMove", precision)
+    N, seed, ppm, radius = 10, 2023, 1, 1.0
+    params = np.random.default_rng(2023).random((N, 4))
+    lig = [0]
+    with pytest.raises(RuntimeError, match="must provide at least one molecule"):
+        k(N, lig, [], params, TEMP, BETA, CUTOFF, radius, seed, ppm, 1)
+    with pytest.raises(RuntimeError, match="must provide at least one atom for the ligand indices"):
+        k(N, [], [[1], [2]], params, TEMP, BETA, CUTOFF, radius, seed, ppm, 1)
+    with pytest.raises(RuntimeError, match="Molecules are not contiguous: mol 1"):
+        k(N, lig, [[1, 2, 3], [5, 6]], params, TEMP, BETA, CUTOFF, radius, seed, ppm, 1)
+    with pytest.raises(RuntimeError, match="only support running with mols with constant size, got mixed sizes"):
+        k(N, lig, [[1, 2, 3], [4, 5]], params, TEMP, BETA, CUTOFF, radius, seed, ppm, 1)
+    with pytest.raises(RuntimeError, match="must provide non-empty molecule indices"):
+        k(N, lig, [[]], params, TEMP, BETA, CUTOFF, radius, seed, ppm, 1)
+    with pytest.raises(RuntimeError, match="proposals per move must be greater than 0"):
+        k(N, lig, [[1], [2]], params, TEMP, BETA, CUTOFF, radius, seed, 0, 1)
+    with pytest.raises(RuntimeError, match="radius must be greater than 0.0"):
+        k(N, lig, [[1], [2]], params, TEMP, BETA, CUTOFF, 0.0, seed, ppm, 1)
+    with pytest.raises(RuntimeError, match="must provide interval greater than 0"):
+        k(N, lig, [[1], [2]], params, TEMP, BETA, CUTOFF, radius, seed, ppm, 0)
+    with pytest.raises(RuntimeError, match="must provide batch size greater than 0"):
+        k(N, lig, [[1], [2]], params, TEMP, BETA, CUTOFF, radius, seed, ppm, 1, batch_size=0)
+    with pytest.raises(RuntimeError, match="number of proposals per move must be greater than batch size"):
+        k(N, lig, [[1], [2]], params, TEMP, BETA, CUTOFF, radius, seed, ppm, 1, batch_size=2)
+    mover = k(N, lig, [[1], [2]], params, TEMP, BETA, CUTOFF, radius, seed, ppm, 1)
+    assert mover.last_log_probability() == 0.0 and mover.n_proposed() == 0
+    with pytest.raises(RuntimeError, match="volume of inner radius greater than box volume"):
+        mover.move(np.random.default_rng(1).random((N, 3)), np.eye(3) * 0.5)
+    np.testing.assert_array_equal(mover.get_params(), params)
+    with pytest.raises(RuntimeError, match="number of params don't match"):
+        mover.set_params(params[:3])
+
+
+@pytest.mark.parametrize("precision", [np.float64, np.float32])
+@pytest.mark.parametrize("radius,proposals_per_move,batch_size", [(0.5, 1, 1), (0.9, 50, 1), (0.9, 200, 64), (1.4, 120, 120)])
+def test_tibd_exchange_deterministic_moves(precision, radius, proposals_per_move, batch_size):
+    """test_cuda_targeted_insertion_mover.py:737-822: K moves of one proposal == one move of K proposals in batches,
+    bit for bit; every accepted move switches a molecule between the sphere and the bulk."""
+    o = ops()
+    x, params, box, mols, lig = ligand_water_system(600)
+    N = len(x)
+    k = klass(o, "TIBDExchangeMove", precision)
+    a = k(N, lig, mols, params, TEMP, BETA, CUTOFF, radius, 2023, 1, 1)
+    b = k(N, lig, mols, params, TEMP, BETA, CUTOFF, radius, 2023, proposals_per_move, 1, batch_size=batch_size)
+    inner_of = klass(o, "inner_and_outer_mols", precision)
+    xa = x.copy()
+    for _ in range(proposals_per_move):
+        before = set(inner_of(lig, xa, box, mols, radius)[0])
+        acc = a.n_accepted()
+        xa, _ = a.move(xa, box)
+        after = set(inner_of(lig, xa, box, mols, radius)[0])
+        if a.n_accepted() > acc:
+            assert len(before ^ after) == 1  # exactly one molecule changed region
+        else:
+            assert before == after
+    xb, _ = b.move(x, box)
+    assert a.n_proposed() == b.n_proposed() == proposals_per_move
+    assert a.n_accepted() == b.n_accepted()
+    np.testing.assert_array_equal(xa, xb)
+    np.testing.assert_array_equal(xa[: len(lig)], x[: len(lig)])  # the ligand never moves
+
+
+@pytest.mark.parametrize("precision", [np.float64, np.float32])
+@pytest.mark.parametrize("radius,proposals_per_move,batch_size", [(0.6, 1, 1), (0.9, 100, 1), (0.9, 400, 100), (1.5, 1000, 250)])
+def test_tibd_moves_against_compiled_reference(precision, radius, proposals_per_move, batch_size):
+    """Same seed, same system: the targeted moves of the compiled reference (f32: identical coordinates and counters)."""
+    ref = load_reference_ops()
+    if ref is None:
+        pytest.skip("compiled reference not present (oracle/_ref)")
+    o = ops()
+    x, params, box, mols, lig = ligand_water_system(700)
+    N = len(x)
+    args = (N, lig, mols, params, TEMP, BETA, CUTOFF, radius, 2023, proposals_per_move, 1)
+    mine = klass(o, "TIBDExchangeMove", precision)(*args, batch_size=batch_size)
+    theirs = klass(ref, "TIBDExchangeMove", precision)(*args, batch_size=batch_size)
+    xa, xb = x.copy(), x.copy()
+    for _ in range(6 if proposals_per_move < 200 else 3):
+        xa, _ = mine.move(xa, box)
+        xb, _ = theirs.move(xb, box)
+        assert mine.n_accepted() == theirs.n_accepted()
+        if precision == np.float32:
+            np.testing.assert_array_equal(xa, xb)
+        else:
+            np.testing.assert_allclose(xa, xb, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(mine.last_raw_log_probability(), theirs.last_raw_log_probability(), rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(mine.last_log_probability(), theirs.last_log_probability(), rtol=1e-4, atol=1e-4)
+    assert mine.n_proposed() == theirs.n_proposed()
+
+
+def test_tibd_log_probability_matches_oracle():
+    """One proposal per move in f64: the reported raw log acceptance equals compute_raw_ratio_given_weights of the Python
+    reference (exchange_mover.py:298-323) evaluated with the oracle's weights on the coordinates before / after."""
+    o = ops()
+    x, params, box, mols, lig = ligand_water_system(120)
+    N, radius = len(x), 0.7
+    mover = o.TIBDExchangeMove_f64(N, lig, mols, params, TEMP, BETA, CUTOFF, radius, 11, 1, 1)
+    vol_inner = 4.0 / 3.0 * np.pi * radius**3
+    vol_outer = np.prod(np.diag(box)) - vol_inner
+    checked = 0
+    for _ in range(12):
+        center = x[lig].mean(0)
+        inner, outer = O.water_groups(x, box, center, mols, radius)
+        w_before = O.bd_log_weights(x, params, box, mols, BETA, CUTOFF, TEMP)
+        acc = mover.n_accepted()
+        x_new, _ = mover.move(x, box)
+        raw = mover.last_raw_log_probability()
+        if mover.n_accepted() > acc:
+            new_inner, _ = O.water_groups(x_new, box, center, mols, radius)
+            moved = (set(inner) ^ set(new_inner)).pop()
+            to_inner = moved in set(new_inner)
+            src, dest = (outer, inner) if to_inner else (inner, outer)
+            w_after = O.bd_log_weights(x_new, params, box, mols, BETA, CUTOFF, TEMP)
+            want = O.tibd_raw_log_probability(
+                w_before[src], w_after[np.append(dest, moved)], len(src), len(dest), vol_outer if to_inner else vol_inner,
+                vol_inner if to_inner else vol_outer,
+            )
+            np.testing.assert_allclose(raw, want, rtol=1e-8, atol=1e-7)
+            checked += 1
+        assert mover.last_log_probability() == min(raw, 0.0)
+        x = x_new
+    assert checked >= 1

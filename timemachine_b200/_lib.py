@@ -99,6 +99,9 @@ SIGNATURES = {
     "tmb_barostat_last_uniforms": [_h, _p_f32],
     "tmb_barostat_counters": [_h, C.POINTER(C.c_int)],
     "tmb_bd_exchange_move_create": [_int, _int, _p_i32, _p_i32, _int, _p_f64, _int, _dbl, _dbl, _dbl, _int, _int, _int, _int, _ph],
+    "tmb_tibd_exchange_move_create": [_int, _int, _p_i32, _int, _p_i32, _p_i32, _int, _p_f64, _int, _dbl, _dbl, _dbl, _dbl, _int, _int, _int, _int, _ph],
+    "tmb_inner_and_outer_mols": [_int, _p_i32, _int, _int, _p_f64, _p_f64, _p_i32, _p_i32, _int, _dbl, _p_i32],
+    "tmb_translations_inside_and_outside_sphere": [_int, _int, _p_f64, _p_f64, _dbl, _int, _p_f64],
     "tmb_bd_exchange_move_num_target_mols": [_h, C.POINTER(C.c_int)],
     "tmb_bd_exchange_move_batch_size": [_h, C.POINTER(C.c_int)],
     "tmb_bd_exchange_move_initial_log_weights": [_h, _int, _p_f64, _p_f64, _p_f64],

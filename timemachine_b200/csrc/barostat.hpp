@@ -33,7 +33,7 @@ public:
     int get_interval() const { return interval_; }
     // May modify d_x and d_box.  Counts calls: acts on every interval-th one.
     virtual void move(int N, double *d_x, double *d_box, cudaStream_t stream) = 0;
-    std::array<std::vector<double>, 2> move_host(int N, const double *h_x, const double *h_box);
+    virtual std::array<std::vector<double>, 2> move_host(int N, const double *h_x, const double *h_box);
     // Number of upcoming move() calls that are guaranteed to do nothing but count (Context replays that many plain
     // MD steps from a CUDA graph and calls skip()).
     int idle_steps() const { return interval_ - 1 - (step_ % interval_); }

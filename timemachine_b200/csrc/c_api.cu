@@ -596,6 +596,79 @@ int tmb_bd_exchange_move_create(
         *out = new MoverPtr(mv);
     });
 }
+int tmb_tibd_exchange_move_create(
+    int precision, int N, const int *ligand_idxs, int n_ligand, const int *mol_atoms, const int *mol_offsets, int n_mols,
+    const double *params, int n_params, double temperature, double nb_beta, double cutoff, double radius, int seed,
+    int num_proposals_per_move, int interval, int batch_size, tmb_mover *out) {
+    return guarded([&] {
+        check_precision(precision);
+        // argument checks of the reference's binding, in its order (wrap_kernels.cpp:1922-1947)
+        if (num_proposals_per_move <= 0) {
+            throw std::runtime_error("proposals per move must be greater than 0");
+        }
+        if (n_params != N * P_PER_ATOM) {
+            throw std::runtime_error("Number of parameters must match N");
+        }
+        if (n_ligand <= 0) {
+            throw std::runtime_error("must provide at least one atom for the ligand indices");
+        }
+        if (n_mols <= 0) {
+            throw std::runtime_error("must provide at least one molecule");
+        }
+        if (interval <= 0) {
+            throw std::runtime_error("must provide interval greater than 0");
+        }
+        if (batch_size <= 0) {
+            throw std::runtime_error("must provide batch size greater than 0");
+        }
+        if (batch_size > num_proposals_per_move) {
+            throw std::runtime_error("number of proposals per move must be greater than batch size");
+        }
+        auto mols = unflatten_mols(mol_atoms, mol_offsets, n_mols);
+        std::vector<int> lig(ligand_idxs, ligand_idxs + n_ligand);
+        std::vector<double> p(params, params + n_params);
+        MoverPtr mv;
+        if (precision == TMB_F32) {
+            mv = std::make_shared<TIBDExchangeMove<float>>(N, lig, mols, p, temperature, nb_beta, cutoff, radius, seed, num_proposals_per_move, interval, batch_size);
+        } else {
+            mv = std::make_shared<TIBDExchangeMove<double>>(N, lig, mols, p, temperature, nb_beta, cutoff, radius, seed, num_proposals_per_move, interval, batch_size);
+        }
+        *out = new MoverPtr(mv);
+    });
+}
+int tmb_inner_and_outer_mols(
+    int precision, const int *center_atoms, int n_center, int N, const double *coords, const double *box, const int *mol_atoms,
+    const int *mol_offsets, int n_mols, double radius, int *flags) {
+    return guarded([&] {
+        check_precision(precision);
+        auto mols = unflatten_mols(mol_atoms, mol_offsets, n_mols);
+        std::vector<int> c(center_atoms, center_atoms + (n_center > 0 ? n_center : 0));
+        std::array<std::vector<int>, 2> r;
+        if (precision == TMB_F32) {
+            r = inner_and_outer_mols<float>(c, N, coords, box, mols, static_cast<float>(radius));
+        } else {
+            r = inner_and_outer_mols<double>(c, N, coords, box, mols, radius);
+        }
+        for (int m = 0; m < n_mols; m++) {
+            flags[m] = 0;
+        }
+        for (int m : r[0]) {
+            flags[m] = 1;
+        }
+    });
+}
+int tmb_translations_inside_and_outside_sphere(
+    int precision, int n_translations, const double *box, const double *center, double radius, int seed, double *out) {
+    return guarded([&] {
+        check_precision(precision);
+        if (precision == TMB_F32) {
+            const float c[3] = {static_cast<float>(center[0]), static_cast<float>(center[1]), static_cast<float>(center[2])};
+            widen(translations_inside_and_outside_sphere_host<float>(n_translations, box, c, static_cast<float>(radius), seed), out);
+        } else {
+            widen(translations_inside_and_outside_sphere_host<double>(n_translations, box, center, radius, seed), out);
+        }
+    });
+}
 int tmb_bd_exchange_move_num_target_mols(tmb_mover m, int *out) {
     return guarded([&] { *out = WITH_BD(m, mv.num_target_mols()); });
 }

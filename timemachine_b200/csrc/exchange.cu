@@ -14,6 +14,7 @@
 
 #include <cooperative_groups.h>
 #include <curand.h>
+#include <curand_kernel.h>
 
 #include <algorithm>
 #include <cmath>
@@ -463,7 +464,22 @@ __device__ void rotate_and_translate(
 
 // ---------------------------------------------------------------------------------------------------------------
 // the biased-deletion move, phase by phase
-enum { ST_OFFSET = 0, ST_SELECTED = 1, ST_ITER = 2, ST_WORDS = 4 };
+enum { ST_OFFSET = 0, ST_SELECTED = 1, ST_ITER = 2, ST_INNER_USED = 3, ST_WORDS = 4 };
+
+// targeted insertion (TIBDExchangeMove): molecules are split into those inside a sphere around the ligand centroid and
+// the rest; a proposal deletes from one region and inserts into the other.  enabled == 0 for plain biased deletion.
+template <typename Real> struct TIDevice {
+    int enabled;
+    Real inner_volume;
+    const Real *box_volume;   // [1]
+    const Real *uniform;      // [P] which region a proposal targets
+    int *inner_flags;         // [M] 1 inside the sphere
+    int *partition;           // [M] inner molecules ascending, then outer molecules descending (cub::DevicePartition::Flagged order)
+    int *inner_count;         // [1]
+    int *targeting;           // [B] 1: the proposal inserts into the sphere
+    Real *src_logw, *dest_logw;       // [B, M] weights of the region deleted from / inserted into
+    Real *lse_src_max, *lse_src_sum;  // [B]
+};
 
 template <typename Real> struct BDDevice {
     int N, M, S, B, P;   // atoms, target molecules, atoms per molecule, batch size, proposals per move
@@ -482,7 +498,8 @@ template <typename Real> struct BDDevice {
     int *samples;                     // [B]
     int *state;                       // ST_*
     u64 *num_accepted;
-    const Real *quat, *trans, *sample_noise, *mh; // [P, 4], [P, 3], [P, M], [P]
+    const Real *quat, *trans, *sample_noise, *mh; // [P, 4], [P, 3] ([P, 2, 3] targeted), [P, M], [P]
+    TIDevice<Real> ti;
 };
 
 template <typename Real> struct BDShared {
@@ -491,17 +508,85 @@ template <typename Real> struct BDShared {
     int sel;
 };
 
+// inner molecules in ascending order at the front, outer molecules in descending order behind them: the order
+// cub::DevicePartition::Flagged produces in the reference (tibd_exchange_move.cu:214-226); the proposals index into it
+template <typename Real> __device__ void ti_partition(const TIDevice<Real> &t, int M, int *scratch /* [EX_THREADS] */) {
+    const int per = (M + EX_THREADS - 1) / EX_THREADS;
+    const int lo = min(M, static_cast<int>(threadIdx.x) * per), hi = min(M, lo + per);
+    int mine = 0;
+    for (int m = lo; m < hi; m++) {
+        mine += t.inner_flags[m];
+    }
+    scratch[threadIdx.x] = mine;
+    __syncthreads();
+    int inner_before = 0;
+    for (int k = 0; k < static_cast<int>(threadIdx.x); k++) {
+        inner_before += scratch[k];
+    }
+    for (int m = lo; m < hi; m++) {
+        if (t.inner_flags[m]) {
+            t.partition[inner_before++] = m;
+        } else {
+            t.partition[M - 1 - (m - inner_before)] = m; // m - inner_before outer molecules precede m
+        }
+    }
+    if (threadIdx.x == EX_THREADS - 1) {
+        t.inner_count[0] = inner_before;
+    }
+    __syncthreads();
+}
+
 // phase S: choose the molecule of every live batch slot and build its proposal
 template <typename Real> __device__ void bd_phase_sample(const BDDevice<Real> &a, BDShared<Real> &sh, int off, int nblocks, int block) {
     const Box3<Real> bx = load_box3<Real>(a.box);
     const int live = min(a.B, a.P - off);
-    if (block == 0 && threadIdx.x == 0 && a.sample) {
+    if (block == 0 && threadIdx.x == 0 && a.sample && !a.ti.enabled) {
         // the previous batch's accepted proposal becomes the "before" state (reference k_store_accepted_log_probability)
         const int sel = a.state[ST_SELECTED];
         if (a.state[ST_ITER] > 0 && sel < a.B) {
             a.lse_before[0] = a.lse_after_max[sel];
             a.lse_before[1] = a.lse_after_sum[sel];
         }
+    }
+    if (a.ti.enabled) {
+        // (tibd_exchange_move.cu:228-307: k_decide_targeted_moves, k_separate_weights_for_targeted, the targeted Gumbel
+        // set-up, arg max, the source region's log-sum-exp, k_adjust_sample_idxs)
+        const int inner = a.ti.inner_count[0], outer = a.M - inner;
+        if (block == 0 && threadIdx.x == 0) {
+            a.state[ST_INNER_USED] = inner; // phases L and A read this copy: block 0 re-partitions while the others still test
+        }
+        for (int b = block; b < live; b += nblocks) {
+            int flag;
+            if (outer == 0) {
+                flag = 0;
+            } else if (inner == 0) {
+                flag = 1;
+            } else {
+                flag = a.ti.uniform[off + b] < static_cast<Real>(0.5) ? 1 : 0;
+            }
+            const int count = flag ? outer : inner, offset = flag ? inner : 0;
+            Real *src = a.ti.src_logw + static_cast<size_t>(b) * a.M;
+            for (int k = threadIdx.x; k < count; k += EX_THREADS) {
+                src[k] = a.logw_before[a.ti.partition[k + offset]];
+            }
+            __syncthreads();
+            const int pick = block_gumbel_argmax(src, a.sample_noise + static_cast<size_t>(off + b) * a.M, count, sh.red);
+            Real m, sum;
+            block_sumexp(src, count, sh.red, m, sum);
+            if (threadIdx.x == 0) {
+                const int s = a.ti.partition[pick + offset];
+                a.samples[b] = s;
+                a.total[b] = 0;
+                a.ti.targeting[b] = flag;
+                a.ti.lse_src_max[b] = m;
+                a.ti.lse_src_sum[b] = sum;
+                // first translation of the pair lies inside the sphere, the second outside; already absolute positions
+                rotate_and_translate(
+                    a.S, a.xr + a.first + s * a.S, a.quat + static_cast<size_t>(off + b) * 4,
+                    a.trans + static_cast<size_t>(off + b) * 6 + (flag ? 0 : 3), bx, false, a.prop + static_cast<size_t>(b) * a.S);
+            }
+        }
+        return;
     }
     for (int b = block; b < live; b += nblocks) {
         int s;
@@ -594,12 +679,46 @@ template <typename Real> __device__ void bd_phase_lse(const BDDevice<Real> &a, B
         }
         __syncthreads();
         Real m, sum;
-        block_sumexp(a.logw_after + static_cast<size_t>(b) * a.M, a.M, sh.red, m, sum);
+        if (a.ti.enabled) {
+            // weights of the region inserted into, plus the moved molecule's (k_setup_destination_weights_for_targeted)
+            const int inner = a.state[ST_INNER_USED];
+            const int flag = a.ti.targeting[b];
+            const int count = flag ? inner : a.M - inner, offset = flag ? 0 : inner;
+            const Real *after = a.logw_after + static_cast<size_t>(b) * a.M;
+            Real *dest = a.ti.dest_logw + static_cast<size_t>(b) * a.M;
+            for (int k = threadIdx.x; k < count; k += EX_THREADS) {
+                dest[k] = after[a.ti.partition[k + offset]];
+            }
+            if (threadIdx.x == 0) {
+                dest[count] = after[a.samples[b]];
+            }
+            __syncthreads();
+            block_sumexp(dest, count + 1, sh.red, m, sum);
+        } else {
+            block_sumexp(a.logw_after + static_cast<size_t>(b) * a.M, a.M, sh.red, m, sum);
+        }
         if (threadIdx.x == 0) {
             a.lse_after_max[b] = m;
             a.lse_after_sum[b] = sum;
         }
     }
+}
+
+// k_exchange.cuh:44-73 compute_raw_log_probability_targeted
+template <typename Real>
+__host__ __device__ inline Real ti_raw_log_probability(
+    int targeting_inner, Real inner_volume, Real outer_volume, int inner_count, int M, Real src_max, Real src_sum, Real dest_max, Real dest_sum) {
+    const Real log_vol = targeting_inner == 1 ? log(inner_volume) - log(outer_volume) : log(outer_volume) - log(inner_volume);
+    const int src = targeting_inner == 1 ? M - inner_count : inner_count;
+    const int dest = targeting_inner == 1 ? inner_count : M - inner_count;
+    const Real half = static_cast<Real>(log(0.5)), one = static_cast<Real>(0);
+    const Real log_fwd = (src > 0 && dest > 0) ? half : one;
+    const Real log_rev = (src - 1 > 0 && dest + 1 > 0) ? half : one;
+    Real before = src_max + log(src_sum);
+    Real after = dest_max + log(dest_sum);
+    before = isnan(before) ? static_cast<Real>(INFINITY) : before;
+    after = isnan(after) ? static_cast<Real>(INFINITY) : after;
+    return before - after + log_vol + (log_rev - log_fwd);
 }
 
 // phase A: Metropolis test per slot, the first accepted slot wins; store its state (reference k_accept_first_valid_move
@@ -610,13 +729,27 @@ template <typename Real> __device__ void bd_phase_accept(const BDDevice<Real> &a
         sh.sel = a.B;
     }
     __syncthreads();
-    const Real before = nan_to_inf<Real>(add_(a.lse_before[0], log_(a.lse_before[1])));
-    for (int b = threadIdx.x; b < live; b += EX_THREADS) {
-        const Real after = nan_to_inf<Real>(add_(a.lse_after_max[b], log_(a.lse_after_sum[b])));
-        const Real log_acc = min_(sub_(before, after), static_cast<Real>(0));
-        if (a.mh[off + b] < exp_(log_acc)) {
-            atomicMin(&sh.sel, b);
-            break;
+    if (a.ti.enabled) {
+        const int inner = a.state[ST_INNER_USED];
+        const Real outer_volume = a.ti.box_volume[0] - a.ti.inner_volume;
+        for (int b = threadIdx.x; b < live; b += EX_THREADS) {
+            const Real raw = ti_raw_log_probability<Real>(
+                a.ti.targeting[b], a.ti.inner_volume, outer_volume, inner, a.M, a.ti.lse_src_max[b], a.ti.lse_src_sum[b], a.lse_after_max[b],
+                a.lse_after_sum[b]);
+            if (a.mh[off + b] < exp_(min_(raw, static_cast<Real>(0)))) {
+                atomicMin(&sh.sel, b);
+                break;
+            }
+        }
+    } else {
+        const Real before = nan_to_inf<Real>(add_(a.lse_before[0], log_(a.lse_before[1])));
+        for (int b = threadIdx.x; b < live; b += EX_THREADS) {
+            const Real after = nan_to_inf<Real>(add_(a.lse_after_max[b], log_(a.lse_after_sum[b])));
+            const Real log_acc = min_(sub_(before, after), static_cast<Real>(0));
+            if (a.mh[off + b] < exp_(log_acc)) {
+                atomicMin(&sh.sel, b);
+                break;
+            }
         }
     }
     __syncthreads();
@@ -640,6 +773,9 @@ template <typename Real> __device__ void bd_phase_accept(const BDDevice<Real> &a
             }
             a.state[ST_OFFSET] = off + sel + 1;
             a.num_accepted[0] += 1;
+            if (a.ti.enabled) {
+                a.ti.inner_flags[s] ^= 1; // the molecule changed region
+            }
         } else {
             a.state[ST_OFFSET] = off + a.B;
         }
@@ -647,6 +783,9 @@ template <typename Real> __device__ void bd_phase_accept(const BDDevice<Real> &a
         a.state[ST_ITER] += 1;
     }
     __syncthreads();
+    if (a.ti.enabled && block == 0 && sel < a.B) {
+        ti_partition(a.ti, a.M, sh.red.i); // for the next batch; the other blocks do not touch it in this phase
+    }
 }
 
 // one phase per launch (host-driven loop, and compute_incremental_log_weights)
@@ -941,6 +1080,14 @@ template <typename Real>
 BDExchangeMove<Real>::BDExchangeMove(
     int N, const std::vector<std::vector<int>> &target_mols, const std::vector<double> &params, double temperature, double nb_beta,
     double cutoff, int seed, int num_proposals_per_move, int interval, int batch_size)
+    : BDExchangeMove(
+          N, target_mols, params, temperature, nb_beta, cutoff, seed, num_proposals_per_move, interval, batch_size,
+          static_cast<size_t>(3) * std::max(num_proposals_per_move, 0)) {}
+
+template <typename Real>
+BDExchangeMove<Real>::BDExchangeMove(
+    int N, const std::vector<std::vector<int>> &target_mols, const std::vector<double> &params, double temperature, double nb_beta,
+    double cutoff, int seed, int num_proposals_per_move, int interval, int batch_size, size_t translation_buffer_size)
     : Mover(interval), N_(N), mol_size_(static_cast<int>(target_mols[0].size())), num_proposals_per_move_(num_proposals_per_move),
       num_target_mols_(static_cast<int>(target_mols.size())), nb_beta_(static_cast<Real>(nb_beta)),
       beta_(static_cast<Real>(1.0 / (BOLTZ * temperature))), cutoff_squared_(static_cast<Real>(cutoff * cutoff)), batch_size_(batch_size),
@@ -950,8 +1097,8 @@ BDExchangeMove<Real>::BDExchangeMove(
       d_after_E_(static_cast<size_t>(batch_size) * num_target_mols_), d_total_(batch_size), d_logw_before_(num_target_mols_),
       d_logw_after_(static_cast<size_t>(batch_size) * num_target_mols_), d_lse_before_(2), d_lse_after_max_(batch_size),
       d_lse_after_sum_(batch_size), d_samples_(batch_size), d_state_(ST_WORDS), d_num_accepted_(1),
-      d_quat_(round_up_even(static_cast<size_t>(4) * num_proposals_per_move)), d_trans_(static_cast<size_t>(3) * num_proposals_per_move),
-      d_sample_noise_(static_cast<size_t>(num_target_mols_) * num_proposals_per_move), d_mh_(num_proposals_per_move) {
+      d_quat_(round_up_even(static_cast<size_t>(4) * std::max(num_proposals_per_move, 0))), d_trans_(translation_buffer_size),
+      d_sample_noise_(static_cast<size_t>(num_target_mols_) * std::max(num_proposals_per_move, 0)), d_mh_(std::max(num_proposals_per_move, 0)) {
     if (num_proposals_per_move_ <= 0) {
         throw std::runtime_error("proposals per move must be greater than 0");
     }
@@ -1038,6 +1185,7 @@ template <typename Real> BDDevice<Real> BDExchangeMove<Real>::device_args(double
     a.trans = d_trans_.data;
     a.sample_noise = d_sample_noise_.data;
     a.mh = d_mh_.data;
+    std::memset(&a.ti, 0, sizeof(a.ti));
     return a;
 }
 
@@ -1059,10 +1207,7 @@ template <typename Real> void BDExchangeMove<Real>::move(int N, double *d_coords
     if (step_ % interval_ != 0) {
         return;
     }
-    TMB_CURAND(curandSetStream(rng_quat_, stream));
-    TMB_CURAND(curandSetStream(rng_trans_, stream));
-    TMB_CURAND(curandSetStream(rng_samples_, stream));
-    TMB_CURAND(curandSetStream(rng_mh_, stream));
+    set_generator_streams(stream);
     TMB_CUDA(cudaMemsetAsync(d_state_.data, 0, d_state_.bytes(), stream));
 
     initial_log_weights_device(d_coords, d_box, stream);
@@ -1074,6 +1219,18 @@ template <typename Real> void BDExchangeMove<Real>::move(int N, double *d_coords
     TMB_CURAND(gen_uniform(rng_mh_, d_mh_.data, d_mh_.length));
 
     BDDevice<Real> a = device_args(d_coords, d_box, true, true);
+    run_proposals(a, stream);
+    num_attempted_ += num_proposals_per_move_;
+}
+
+template <typename Real> void BDExchangeMove<Real>::set_generator_streams(cudaStream_t stream) {
+    TMB_CURAND(curandSetStream(rng_quat_, stream));
+    TMB_CURAND(curandSetStream(rng_trans_, stream));
+    TMB_CURAND(curandSetStream(rng_samples_, stream));
+    TMB_CURAND(curandSetStream(rng_mh_, stream));
+}
+
+template <typename Real> void BDExchangeMove<Real>::run_proposals(BDDevice<Real> &a, cudaStream_t stream) {
     if (host_loop_) {
         int off = 0;
         while (off < num_proposals_per_move_) {
@@ -1088,7 +1245,6 @@ template <typename Real> void BDExchangeMove<Real>::move(int N, double *d_coords
         TMB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_bd_move<Real>), dim3(coop_blocks_), dim3(EX_THREADS), args, 0, stream));
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
-    num_attempted_ += num_proposals_per_move_;
 }
 
 template <typename Real>
@@ -1259,6 +1415,293 @@ void rotate_and_translate_mol_host(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// targeted insertion (reference tibd_exchange_move.cu, kernels/k_exchange.cu:440-545, k_translations.cuh, gpu_utils.cu:24-31)
+constexpr int TI_STATE_THREADS = 128; // the reference's DEFAULT_THREADS_PER_BLOCK: one cuRAND state per thread of one block
+
+__global__ void k_ti_init_states(int count, int seed, curandState_t *states) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < count) {
+        curand_init(seed + idx, 0, 0, &states[idx]);
+    }
+}
+
+// Pairs of translations: even slots uniformly inside the sphere (direction from three normals, radius^(1/3) law),
+// odd slots anywhere in the box but outside the sphere (rejection).  The state a thread ends with is written back
+// rotated so that the sequence does not depend on how many translations a call draws (k_translations.cuh:7-93).
+template <typename Real>
+__global__ void k_ti_translations(int num_translations, const double *__restrict__ box, const Real *__restrict__ center, Real radius, curandState_t *states, Real *__restrict__ out) {
+    const int stride = gridDim.x * blockDim.x;
+    const Real cx = center[0], cy = center[1], cz = center[2];
+    curandState_t local = states[threadIdx.x];
+    const Real bx = box[0], by = box[4], bz = box[8];
+    const Real ibx = 1 / bx, iby = 1 / by, ibz = 1 / bz;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < num_translations * 2; idx += stride) {
+        if (idx % 2 == 0) {
+            Real x = curand_normal(&local);
+            Real y = curand_normal(&local);
+            Real z = curand_normal(&local);
+            Real rad = curand_uniform(&local);
+            const Real norm = sqrt((x * x) + (y * y) + (z * z));
+            x /= norm;
+            y /= norm;
+            z /= norm;
+            rad = cbrt(rad);
+            out[idx * 3 + 0] = (x * rad * radius) + cx;
+            out[idx * 3 + 1] = (y * rad * radius) + cy;
+            out[idx * 3 + 2] = (z * rad * radius) + cz;
+        } else {
+            const Real r2 = radius * radius;
+            for (int it = 0; it < 1000; it++) {
+                const Real x = curand_normal(&local) * bx;
+                const Real y = curand_normal(&local) * by;
+                const Real z = curand_normal(&local) * bz;
+                Real dx = x - cx, dy = y - cy, dz = z - cz;
+                dx -= bx * nearbyint(dx * ibx);
+                dy -= by * nearbyint(dy * iby);
+                dz -= bz * nearbyint(dz * ibz);
+                const Real dist = (dx * dx) + (dy * dy) + (dz * dz);
+                if (dist >= r2) {
+                    out[idx * 3 + 0] = x;
+                    out[idx * 3 + 1] = y;
+                    out[idx * 3 + 2] = z;
+                    break;
+                }
+            }
+        }
+    }
+    int slot = static_cast<int>(threadIdx.x) - ((num_translations * 2) % stride);
+    slot = slot >= 0 ? slot : stride + slot;
+    states[slot] = local;
+}
+
+// centroid of the ligand atoms (fixed-point sum), box volume, inside/outside flag of every molecule and the partition
+// (k_compute_centroid_of_atoms, k_compute_box_volume, k_flag_mols_inner_outer; one block)
+template <typename Real>
+__global__ void __launch_bounds__(EX_THREADS) k_ti_setup(
+    int num_center_atoms, const int *__restrict__ center_atoms, int M, int S, int first, const int *__restrict__ mol_first /* or null */,
+    const int *__restrict__ mol_sizes /* or null */, const double *__restrict__ coords, const double *__restrict__ box, Real square_radius,
+    Real *center, Real *box_volume, TIDevice<Real> t) {
+    __shared__ unsigned long long acc[3];
+    __shared__ int scratch[EX_THREADS];
+    if (threadIdx.x < 3) {
+        acc[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < num_center_atoms; k += EX_THREADS) {
+        const int atom = center_atoms[k];
+        atomicAdd(acc + 0, to_fixed<FIXED_EXPONENT>(static_cast<Real>(coords[atom * 3 + 0])));
+        atomicAdd(acc + 1, to_fixed<FIXED_EXPONENT>(static_cast<Real>(coords[atom * 3 + 1])));
+        atomicAdd(acc + 2, to_fixed<FIXED_EXPONENT>(static_cast<Real>(coords[atom * 3 + 2])));
+    }
+    __syncthreads();
+    const Real n = static_cast<Real>(num_center_atoms);
+    const Real cx = fixed_to_real<Real>(acc[0]) / n, cy = fixed_to_real<Real>(acc[1]) / n, cz = fixed_to_real<Real>(acc[2]) / n;
+    if (threadIdx.x == 0) {
+        center[0] = cx;
+        center[1] = cy;
+        center[2] = cz;
+        if (box_volume != nullptr) {
+            const Real v = box[0] * box[4] * box[8]; // product in double, then rounded (k_exchange.cu:219-229)
+            box_volume[0] = v;
+        }
+    }
+    const Real bx = box[0], by = box[4], bz = box[8];
+    const Real ibx = 1 / bx, iby = 1 / by, ibz = 1 / bz;
+    for (int m = threadIdx.x; m < M; m += EX_THREADS) {
+        const int start = mol_first != nullptr ? mol_first[m] : first + m * S;
+        const int size = mol_sizes != nullptr ? mol_sizes[m] : S;
+        u64 ax = 0, ay = 0, az = 0;
+        for (int atom = start; atom < start + size; atom++) {
+            ax += to_fixed<FIXED_EXPONENT>(static_cast<Real>(coords[atom * 3 + 0]));
+            ay += to_fixed<FIXED_EXPONENT>(static_cast<Real>(coords[atom * 3 + 1]));
+            az += to_fixed<FIXED_EXPONENT>(static_cast<Real>(coords[atom * 3 + 2]));
+        }
+        const Real ns = static_cast<Real>(size);
+        Real dx = fixed_to_real<Real>(ax) / ns, dy = fixed_to_real<Real>(ay) / ns, dz = fixed_to_real<Real>(az) / ns;
+        dx -= cx;
+        dy -= cy;
+        dz -= cz;
+        dx -= bx * nearbyint(dx * ibx);
+        dy -= by * nearbyint(dy * iby);
+        dz -= bz * nearbyint(dz * ibz);
+        const Real dist = (dx * dx) + (dy * dy) + (dz * dz);
+        t.inner_flags[m] = dist < square_radius ? 1 : 0;
+    }
+    __syncthreads();
+    if (t.partition != nullptr) {
+        ti_partition(t, M, scratch);
+    }
+}
+
+template <typename Real>
+TIBDExchangeMove<Real>::TIBDExchangeMove(
+    int N, const std::vector<int> &ligand_idxs, const std::vector<std::vector<int>> &target_mols, const std::vector<double> &params,
+    double temperature, double nb_beta, double cutoff, double radius, int seed, int num_proposals_per_move, int interval, int batch_size)
+    : BDExchangeMove<Real>(
+          N, target_mols, params, temperature, nb_beta, cutoff, seed, num_proposals_per_move, interval, batch_size,
+          static_cast<size_t>(6) * std::max(num_proposals_per_move, 0)),
+      radius_(static_cast<Real>(radius)), inner_volume_(static_cast<Real>((4.0 / 3.0) * M_PI * std::pow(radius, 3))),
+      d_ligand_idxs_(ligand_idxs.size()), d_inner_flags_(this->num_target_mols_), d_partition_(this->num_target_mols_), d_inner_count_(1),
+      d_targeting_(batch_size), d_center_(3), d_box_volume_(1), d_uniform_(std::max(num_proposals_per_move, 0)),
+      d_src_logw_(static_cast<size_t>(batch_size) * this->num_target_mols_), d_dest_logw_(static_cast<size_t>(batch_size) * this->num_target_mols_),
+      d_lse_src_max_(batch_size), d_lse_src_sum_(batch_size) {
+    if (radius <= 0.0) {
+        throw std::runtime_error("radius must be greater than 0.0");
+    }
+    for (int idx : ligand_idxs) {
+        if (idx < 0 || idx >= N) {
+            throw std::runtime_error("ligand indices must be between 0 and N");
+        }
+    }
+    d_ligand_idxs_.copy_from(ligand_idxs.data());
+    d_box_volume_.zero();
+    d_lse_src_max_.zero();
+    d_lse_src_sum_.zero();
+    d_inner_count_.zero();
+    d_inner_flags_.zero();
+    d_src_logw_.zero();
+    d_dest_logw_.zero();
+    // targeting the sphere with nothing inside it: log probability 0 before the first move (tibd_exchange_move.cu:104-108)
+    std::vector<int> ones(batch_size, 1);
+    d_targeting_.copy_from(ones.data());
+    TMB_CUDA(cudaMalloc(&d_rand_states_, sizeof(curandState_t) * TI_STATE_THREADS));
+    // seed + 4: the first four seeds belong to the host generators (tibd_exchange_move.cu:66-71)
+    TMB_LAUNCH(k_ti_init_states, 1, TI_STATE_THREADS, 0, nullptr, TI_STATE_THREADS, seed + 4, reinterpret_cast<curandState_t *>(d_rand_states_));
+    TMB_CUDA(cudaDeviceSynchronize());
+}
+
+template <typename Real> TIBDExchangeMove<Real>::~TIBDExchangeMove() {
+    if (d_rand_states_ != nullptr) {
+        cudaFree(d_rand_states_);
+    }
+}
+
+template <typename Real> void TIBDExchangeMove<Real>::move(int N, double *d_coords, double *d_box, cudaStream_t stream) {
+    if (N != this->N_) {
+        throw std::runtime_error("N != N_");
+    }
+    this->step_++;
+    if (this->step_ % this->interval_ != 0) {
+        return;
+    }
+    this->set_generator_streams(stream);
+    TMB_CUDA(cudaMemsetAsync(this->d_state_.data, 0, this->d_state_.bytes(), stream));
+    this->initial_log_weights_device(d_coords, d_box, stream);
+
+    BDDevice<Real> a = this->device_args(d_coords, d_box, false, true);
+    a.ti.enabled = 1;
+    a.ti.inner_volume = inner_volume_;
+    a.ti.box_volume = d_box_volume_.data;
+    a.ti.uniform = d_uniform_.data;
+    a.ti.inner_flags = d_inner_flags_.data;
+    a.ti.partition = d_partition_.data;
+    a.ti.inner_count = d_inner_count_.data;
+    a.ti.targeting = d_targeting_.data;
+    a.ti.src_logw = d_src_logw_.data;
+    a.ti.dest_logw = d_dest_logw_.data;
+    a.ti.lse_src_max = d_lse_src_max_.data;
+    a.ti.lse_src_sum = d_lse_src_sum_.data;
+
+    TMB_LAUNCH(
+        k_ti_setup<Real>, 1, EX_THREADS, 0, stream, static_cast<int>(d_ligand_idxs_.length), d_ligand_idxs_.data, this->num_target_mols_,
+        this->mol_size_, this->first_atom_, static_cast<const int *>(nullptr), static_cast<const int *>(nullptr), d_coords, d_box,
+        radius_ * radius_, d_center_.data, d_box_volume_.data, a.ti);
+
+    // all noise of the move up front (tibd_exchange_move.cu:157-170); the region choice draws from the translations generator
+    TMB_CURAND(gen_uniform(this->rng_mh_, this->d_mh_.data, this->d_mh_.length));
+    TMB_CURAND(gen_uniform(this->rng_trans_, d_uniform_.data, d_uniform_.length));
+    TMB_CURAND(gen_normal(this->rng_quat_, this->d_quat_.data, this->d_quat_.length));
+    TMB_CURAND(gen_uniform(this->rng_samples_, this->d_sample_noise_.data, this->d_sample_noise_.length));
+    TMB_LAUNCH(
+        k_ti_translations<Real>, 1, TI_STATE_THREADS, 0, stream, this->num_proposals_per_move_, d_box, d_center_.data, radius_,
+        reinterpret_cast<curandState_t *>(d_rand_states_), this->d_trans_.data);
+
+    this->run_proposals(a, stream);
+    this->num_attempted_ += this->num_proposals_per_move_;
+}
+
+template <typename Real> std::array<std::vector<double>, 2> TIBDExchangeMove<Real>::move_host(int N, const double *h_x, const double *h_box) {
+    const double box_vol = h_box[0] * h_box[4] * h_box[8];
+    if (box_vol <= inner_volume_) {
+        throw std::runtime_error("volume of inner radius greater than box volume");
+    }
+    return Mover::move_host(N, h_x, h_box);
+}
+
+template <typename Real> double TIBDExchangeMove<Real>::raw_log_probability_host() {
+    Real src_max, src_sum, dest_max, dest_sum, box_vol;
+    int targeting, state[ST_WORDS];
+    TMB_CUDA(cudaMemcpy(&src_max, d_lse_src_max_.data, sizeof(Real), cudaMemcpyDeviceToHost));
+    TMB_CUDA(cudaMemcpy(&src_sum, d_lse_src_sum_.data, sizeof(Real), cudaMemcpyDeviceToHost));
+    TMB_CUDA(cudaMemcpy(&dest_max, this->d_lse_after_max_.data, sizeof(Real), cudaMemcpyDeviceToHost));
+    TMB_CUDA(cudaMemcpy(&dest_sum, this->d_lse_after_sum_.data, sizeof(Real), cudaMemcpyDeviceToHost));
+    TMB_CUDA(cudaMemcpy(&targeting, d_targeting_.data, sizeof(int), cudaMemcpyDeviceToHost));
+    d_box_volume_.copy_to(&box_vol);
+    this->d_state_.copy_to(state);
+    const Real outer_vol = box_vol - inner_volume_;
+    return static_cast<double>(ti_raw_log_probability<Real>(
+        targeting, inner_volume_, outer_vol, state[ST_INNER_USED], this->num_target_mols_, src_max, src_sum, dest_max, dest_sum));
+}
+
+template <typename Real>
+std::array<std::vector<int>, 2> inner_and_outer_mols(
+    const std::vector<int> &center_atoms, int N, const double *coords, const double *box, const std::vector<std::vector<int>> &group_idxs,
+    Real radius) {
+    const int M = static_cast<int>(group_idxs.size());
+    std::array<std::vector<int>, 2> out;
+    if (M == 0) {
+        return out;
+    }
+    const MolLayout l = flatten_mols(group_idxs);
+    std::vector<int> first(M), sizes(M);
+    for (int m = 0; m < M; m++) {
+        sizes[m] = l.mol_offsets[m + 1] - l.mol_offsets[m];
+        first[m] = sizes[m] > 0 ? l.atom_idxs[l.mol_offsets[m]] : 0;
+    }
+    DeviceBuffer<double> d_coords(static_cast<size_t>(N) * 3), d_box(9);
+    DeviceBuffer<int> d_center_atoms(center_atoms.size()), d_first(M), d_sizes(M), d_flags(M);
+    DeviceBuffer<Real> d_center(3);
+    d_coords.copy_from(coords);
+    d_box.copy_from(box);
+    d_center_atoms.copy_from(center_atoms.data());
+    d_first.copy_from(first.data());
+    d_sizes.copy_from(sizes.data());
+    TIDevice<Real> t;
+    std::memset(&t, 0, sizeof(t));
+    t.inner_flags = d_flags.data;
+    cudaStream_t stream = main_stream();
+    TMB_LAUNCH(
+        k_ti_setup<Real>, 1, EX_THREADS, 0, stream, static_cast<int>(center_atoms.size()), d_center_atoms.data, M, 0, 0, d_first.data,
+        d_sizes.data, d_coords.data, d_box.data, radius * radius, d_center.data, static_cast<Real *>(nullptr), t);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<int> flags(M);
+    d_flags.copy_to(flags.data());
+    for (int m = 0; m < M; m++) {
+        out[flags[m] == 1 ? 0 : 1].push_back(m);
+    }
+    return out;
+}
+
+template <typename Real>
+std::vector<Real> translations_inside_and_outside_sphere_host(int n_translations, const double *box, const Real *center, Real radius, int seed) {
+    std::vector<Real> out(static_cast<size_t>(n_translations) * 6);
+    if (n_translations <= 0) {
+        return out;
+    }
+    DeviceBuffer<double> d_box(9);
+    DeviceBuffer<Real> d_center(3), d_out(out.size());
+    DeviceBuffer<curandState_t> d_states(TI_STATE_THREADS);
+    d_box.copy_from(box);
+    d_center.copy_from(center);
+    cudaStream_t stream = main_stream();
+    TMB_LAUNCH(k_ti_init_states, 1, TI_STATE_THREADS, 0, stream, TI_STATE_THREADS, seed, d_states.data);
+    TMB_LAUNCH(k_ti_translations<Real>, 1, TI_STATE_THREADS, 0, stream, n_translations, d_box.data, d_center.data, radius, d_states.data, d_out.data);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    d_out.copy_to(out.data());
+    return out;
+}
+
 template class NonbondedMolEnergyPotential<float>;
 template class NonbondedMolEnergyPotential<double>;
 template class SegmentedSumExp<float>;
@@ -1267,6 +1710,12 @@ template class SegmentedWeightedRandomSampler<float>;
 template class SegmentedWeightedRandomSampler<double>;
 template class BDExchangeMove<float>;
 template class BDExchangeMove<double>;
+template class TIBDExchangeMove<float>;
+template class TIBDExchangeMove<double>;
+template std::array<std::vector<int>, 2> inner_and_outer_mols<float>(const std::vector<int> &, int, const double *, const double *, const std::vector<std::vector<int>> &, float);
+template std::array<std::vector<int>, 2> inner_and_outer_mols<double>(const std::vector<int> &, int, const double *, const double *, const std::vector<std::vector<int>> &, double);
+template std::vector<float> translations_inside_and_outside_sphere_host<float>(int, const double *, const float *, float, int);
+template std::vector<double> translations_inside_and_outside_sphere_host<double>(int, const double *, const double *, double, int);
 template std::vector<float> atom_by_atom_energies<float>(int, const std::vector<int> &, const double *, const double *, const double *, float, float);
 template std::vector<double> atom_by_atom_energies<double>(int, const std::vector<int> &, const double *, const double *, const double *, double, double);
 template void rotate_coordinates_host<float>(int, int, const double *, const float *, double *);

@@ -92,7 +92,7 @@ public:
     std::vector<Real> compute_initial_log_weights_host(int N, const double *h_coords, const double *h_box);
     std::vector<Real> get_before_log_weights();
     std::vector<Real> get_after_log_weights();
-    double raw_log_probability_host();
+    virtual double raw_log_probability_host();
     double log_probability_host();
     size_t n_accepted() const;
     size_t n_proposed() const { return num_attempted_; }
@@ -103,7 +103,11 @@ public:
     void set_params(const std::vector<double> &params);
     void set_params_device(int size, const double *d_p, cudaStream_t stream);
 
-private:
+protected:
+    BDExchangeMove(
+        int N, const std::vector<std::vector<int>> &target_mols, const std::vector<double> &params, double temperature,
+        double nb_beta, double cutoff, int seed, int num_proposals_per_move, int interval, int batch_size,
+        size_t translation_buffer_size);
     const int N_, mol_size_, num_proposals_per_move_, num_target_mols_;
     const Real nb_beta_, beta_, cutoff_squared_;
     const int batch_size_;
@@ -126,7 +130,41 @@ private:
     BDDevice<Real> device_args(double *d_coords, const double *d_box, bool scale, bool sample);
     void initial_log_weights_device(double *d_coords, const double *d_box, cudaStream_t stream);
     void run_phase(int phase, const BDDevice<Real> &a, cudaStream_t stream);
+    void run_proposals(BDDevice<Real> &a, cudaStream_t stream); // all batches of a move: device loop or host loop
+    void set_generator_streams(cudaStream_t stream);
 };
+
+struct curandStateXORWOW;
+
+// reference tibd_exchange_move.{hpp,cu}: targeted insertion / biased deletion between a sphere around the ligand
+// centroid and the rest of the box
+template <typename Real> class TIBDExchangeMove : public BDExchangeMove<Real> {
+public:
+    TIBDExchangeMove(
+        int N, const std::vector<int> &ligand_idxs, const std::vector<std::vector<int>> &target_mols, const std::vector<double> &params,
+        double temperature, double nb_beta, double cutoff, double radius, int seed, int num_proposals_per_move, int interval,
+        int batch_size);
+    ~TIBDExchangeMove() override;
+
+    void move(int N, double *d_coords, double *d_box, cudaStream_t stream) override;
+    std::array<std::vector<double>, 2> move_host(int N, const double *h_x, const double *h_box) override;
+    double raw_log_probability_host() override;
+
+private:
+    const Real radius_, inner_volume_;
+    DeviceBuffer<int> d_ligand_idxs_, d_inner_flags_, d_partition_, d_inner_count_, d_targeting_;
+    DeviceBuffer<Real> d_center_, d_box_volume_, d_uniform_, d_src_logw_, d_dest_logw_, d_lse_src_max_, d_lse_src_sum_;
+    curandStateXORWOW *d_rand_states_ = nullptr; // [TI_STATE_THREADS]
+};
+
+// reference exchange.cu:11-63 (molecules inside / outside a sphere around the centroid of center_atoms) and
+// translations.cu:8-42 (n pairs of translations: inside the sphere, outside it)
+template <typename Real>
+std::array<std::vector<int>, 2> inner_and_outer_mols(
+    const std::vector<int> &center_atoms, int N, const double *coords, const double *box, const std::vector<std::vector<int>> &group_idxs,
+    Real radius);
+template <typename Real>
+std::vector<Real> translations_inside_and_outside_sphere_host(int n_translations, const double *box, const Real *center, Real radius, int seed);
 
 // reference all_atom_energies.cu:8-48 (pair energies of target atoms with every atom, [T, N])
 template <typename Real>

@@ -922,6 +922,97 @@ class BDExchangeMove_f64(_BDExchangeMove):
     _precision = F64
 
 
+class _TIBDExchangeMove(_BDExchangeMove):
+    """TIBDExchangeMove_{f32,f64}(N, ligand_idxs, target_mols, params, temperature, nb_beta, cutoff, radius, seed,
+    num_proposals_per_move, interval, batch_size=1): targeted insertion / biased deletion between a sphere around the
+    ligand centroid and the bulk (wrap_kernels.cpp:1902-1975; tibd_exchange_move.cu; the Python reference is
+    timemachine/md/exchange/exchange_mover.py::TIBDExchangeMove)."""
+
+    def __init__(
+        self, N, ligand_idxs, target_mols, params, temperature, nb_beta, cutoff, radius, seed, num_proposals_per_move,
+        interval, batch_size=1,
+    ):
+        params = np.asarray(params, dtype=np.float64)
+        if int(num_proposals_per_move) <= 0:
+            raise RuntimeError("proposals per move must be greater than 0")
+        if params.ndim != 2:
+            raise RuntimeError("parameters dimensions must be 2")
+        if params.shape[0] != int(N):
+            raise RuntimeError("Number of parameters must match N")
+        params = np.ascontiguousarray(params)
+        ligand_idxs = _i32(ligand_idxs).reshape(-1)
+        flat, offsets, n_mols = _flatten_groups(target_mols)
+        self._handle = None
+        h = _new_handle()
+        _check(
+            _L.tmb_tibd_exchange_move_create(
+                self._precision, int(N), _ptr(ligand_idxs, C.c_int32), int(ligand_idxs.size), _ptr(flat, C.c_int32),
+                _ptr(offsets, C.c_int32), n_mols, _ptr(params, C.c_double), int(params.size), float(temperature), float(nb_beta),
+                float(cutoff), float(radius), int(seed), int(num_proposals_per_move), int(interval), int(batch_size), C.byref(h),
+            )
+        )
+        self._handle = h
+        self._N = int(N)
+        self._real = np.float32 if self._precision == F32 else np.float64
+
+
+class TIBDExchangeMove_f32(_TIBDExchangeMove):
+    _precision = F32
+
+
+class TIBDExchangeMove_f64(_TIBDExchangeMove):
+    _precision = F64
+
+
+def _inner_and_outer_mols(precision, center_atoms, coords, box, group_idxs, radius):
+    coords, box = _f64(coords), _f64(box)
+    _verify_coords_and_box(coords, box)
+    center_atoms = _i32(center_atoms).reshape(-1)
+    flat, offsets, n_mols = _flatten_groups(group_idxs)
+    flags = np.zeros(n_mols, dtype=np.int32)
+    _check(
+        _L.tmb_inner_and_outer_mols(
+            precision, _ptr(center_atoms, C.c_int32), int(center_atoms.size), coords.shape[0], _ptr(coords, C.c_double),
+            _ptr(box, C.c_double), _ptr(flat, C.c_int32), _ptr(offsets, C.c_int32), n_mols, float(radius), _ptr(flags, C.c_int32),
+        )
+    )
+    idx = np.arange(n_mols)
+    return [int(i) for i in idx[flags == 1]], [int(i) for i in idx[flags != 1]]
+
+
+def inner_and_outer_mols_f32(center_atoms, coords, box, group_idxs, radius):
+    """(inner, outer) molecule indices: centroid within `radius` of the centroid of center_atoms, minimum image
+    (wrap_kernels.cpp:2032-2048)."""
+    return _inner_and_outer_mols(F32, center_atoms, coords, box, group_idxs, radius)
+
+
+def inner_and_outer_mols_f64(center_atoms, coords, box, group_idxs, radius):
+    return _inner_and_outer_mols(F64, center_atoms, coords, box, group_idxs, radius)
+
+
+def _translations_inside_and_outside_sphere_host(precision, num_translations, box, center, radius, seed):
+    box, center = _f64(box), _f64(center).reshape(-1)
+    if center.size != 3:
+        raise RuntimeError("Center must be of length 3")
+    out = np.empty((int(num_translations), 2, 3), dtype=np.float64)
+    _check(
+        _L.tmb_translations_inside_and_outside_sphere(
+            precision, int(num_translations), _ptr(box, C.c_double), _ptr(center, C.c_double), float(radius), int(seed),
+            _ptr(out, C.c_double),
+        )
+    )
+    return out.astype(np.float32 if precision == F32 else np.float64)
+
+
+def translations_inside_and_outside_sphere_host_f32(num_translations, box, center, radius, seed):
+    """[n, 2, 3]: a translation inside the sphere around `center` and one outside it, per row (wrap_kernels.cpp:2117-2141)."""
+    return _translations_inside_and_outside_sphere_host(F32, num_translations, box, center, radius, seed)
+
+
+def translations_inside_and_outside_sphere_host_f64(num_translations, box, center, radius, seed):
+    return _translations_inside_and_outside_sphere_host(F64, num_translations, box, center, radius, seed)
+
+
 class _NonbondedMolEnergyPotential:
     """NonbondedMolEnergyPotential_{f32,f64}(N, target_mols, beta, cutoff).execute(coords, params, box) -> energy of
     every target molecule with all atoms outside it (wrap_kernels.cpp:234-294; nonbonded_mol_energy.cu)."""
