@@ -212,6 +212,15 @@ pair_e(const Vec4<Real> &xi, const Vec4<Real> &pi, const Vec4<Real> &xj, const V
     return energy_to_fixed<Real>(pair_u(pi.x, pj.x, pi.y, pj.y, pi.z, pj.z, d2, beta));
 }
 
+// squared minimum-image distance in 3-D, for skip decisions only (plain arithmetic: compared against a padded bound)
+template <typename Real> __device__ __forceinline__ Real anchor_d2(const Vec4<Real> &p, const Vec4<Real> &q, const Box3<Real> &b) {
+    Real dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+    dx -= b.x * rint_(dx * b.ix);
+    dy -= b.y * rint_(dy * b.iy);
+    dz -= b.z * rint_(dz * b.iz);
+    return dx * dx + dy * dy + dz * dz;
+}
+
 // 128-bit accumulate through two 64-bit atomics; the final value does not depend on the order of the adds
 __device__ __forceinline__ void atomic_add_i128(i128 *addr, i128 v) {
     u64 *p = reinterpret_cast<u64 *>(addr);
@@ -496,6 +505,8 @@ template <typename Real> struct BDDevice {
     Real *lse_before;                 // {max, sum}
     Real *lse_after_max, *lse_after_sum; // [B]
     int *samples;                     // [B]
+    const unsigned int *mol_order;    // [M] first atoms of the molecules in Hilbert order (work order of the pair phase)
+    const Real *r_bound;              // [1] no atom of a target molecule is further than this from the molecule's first atom
     int *state;                       // ST_*
     u64 *num_accepted;
     const Real *quat, *trans, *sample_noise, *mh; // [P, 4], [P, 3] ([P, 2, 3] targeted), [P, M], [P]
@@ -614,56 +625,67 @@ template <typename Real> __device__ void bd_phase_energies(const BDDevice<Real> 
     const int live = min(a.B, a.P - off);
     const int n_other = a.N - a.M * a.S;
     const int items = a.M + n_other;
-    const int chunks = (items + EX_THREADS - 1) / EX_THREADS;
+    // Work is handed out per warp (32 consecutive items of one proposal) with no block-level step in between: the few
+    // warps whose molecules lie near the moved molecule run long, latency-bound pair evaluations and must not hold up
+    // the others.  Molecules are visited in Hilbert order, so a warp is either near or far as a whole.
+    const int chunks = (items + WARP - 1) / WARP;
     const long long tasks = static_cast<long long>(live) * chunks;
-    for (long long task = block; task < tasks; task += nblocks) {
+    const int warps_per_block = EX_THREADS / WARP;
+    const int lane = threadIdx.x % WARP;
+    const Real reach_mol = sqrt(a.cutoff2) + 2 * a.r_bound[0], reach_atom = sqrt(a.cutoff2) + a.r_bound[0];
+    for (long long task = static_cast<long long>(block) * warps_per_block + threadIdx.x / WARP; task < tasks;
+         task += static_cast<long long>(nblocks) * warps_per_block) {
         const int b = static_cast<int>(task / chunks);
-        const int item = static_cast<int>(task % chunks) * EX_THREADS + threadIdx.x;
-        if (threadIdx.x == 0) {
-            sh.tot[0] = 0;
-            sh.tot[1] = 0;
-        }
-        __syncthreads();
+        const int item = static_cast<int>(task % chunks) * WARP + lane;
         const int s = a.samples[b];
         const Vec4<Real> *xold = a.xr + a.first + s * a.S;
         const Vec4<Real> *pmol = a.pr + a.first + s * a.S;
         const Vec4<Real> *xnew = a.prop + static_cast<size_t>(b) * a.S;
         i128 acc_new = 0;
+        // Anchor test: a pair of atoms is at least (distance of the molecules' first atoms) - 2 r_bound apart, so a
+        // molecule whose anchor is further than cutoff + 2 r_bound from the moved molecule's anchor contributes exact
+        // zeros and is skipped (pairs outside the cutoff are exact zeros anyway: the result is bit-identical).
         if (item < a.M) {
-            if (item != s) {
+            const int j0 = static_cast<int>(a.mol_order[item]);
+            const int mol = (j0 - a.first) / a.S;
+            if (mol != s) {
                 i128 delta = 0;
-                const int j0 = a.first + item * a.S;
-                for (int i = 0; i < a.S; i++) {
-                    const Vec4<Real> xo = xold[i], xn = xnew[i], pi = pmol[i];
-                    for (int j = j0; j < j0 + a.S; j++) {
-                        const Vec4<Real> xj = a.xr[j], pj = a.pr[j];
-                        const i128 e_new = pair_e(xn, pi, xj, pj, bx, a.cutoff2, a.nb_beta);
-                        delta += e_new - pair_e(xo, pi, xj, pj, bx, a.cutoff2, a.nb_beta);
-                        acc_new += e_new;
+                const Vec4<Real> anchor = a.xr[j0];
+                const bool near_old = anchor_d2(xold[0], anchor, bx) < reach_mol * reach_mol;
+                const bool near_new = anchor_d2(xnew[0], anchor, bx) < reach_mol * reach_mol;
+                if (near_old || near_new) {
+                    for (int i = 0; i < a.S; i++) {
+                        const Vec4<Real> xo = xold[i], xn = xnew[i], pi = pmol[i];
+                        for (int j = j0; j < j0 + a.S; j++) {
+                            const Vec4<Real> xj = a.xr[j], pj = a.pr[j];
+                            if (near_new) {
+                                const i128 e_new = pair_e(xn, pi, xj, pj, bx, a.cutoff2, a.nb_beta);
+                                delta += e_new;
+                                acc_new += e_new;
+                            }
+                            if (near_old) {
+                                delta -= pair_e(xo, pi, xj, pj, bx, a.cutoff2, a.nb_beta);
+                            }
+                        }
                     }
                 }
-                const i128 e = a.before_E[item] + delta;
-                a.after_E[static_cast<size_t>(b) * a.M + item] = e;
-                a.logw_after[static_cast<size_t>(b) * a.M + item] = log_weight<Real>(e, a.beta);
+                const i128 e = a.before_E[mol] + delta;
+                a.after_E[static_cast<size_t>(b) * a.M + mol] = e;
+                a.logw_after[static_cast<size_t>(b) * a.M + mol] = log_weight<Real>(e, a.beta);
             }
         } else if (item < items) {
             const int k = item - a.M;
             const int j = k < a.first ? k : k + a.M * a.S;
             const Vec4<Real> xj = a.xr[j], pj = a.pr[j];
-            for (int i = 0; i < a.S; i++) {
-                acc_new += pair_e(xnew[i], pmol[i], xj, pj, bx, a.cutoff2, a.nb_beta);
+            if (anchor_d2(xnew[0], xj, bx) < reach_atom * reach_atom) {
+                for (int i = 0; i < a.S; i++) {
+                    acc_new += pair_e(xnew[i], pmol[i], xj, pj, bx, a.cutoff2, a.nb_beta);
+                }
             }
         }
         if (acc_new != 0) {
-            atomic_add_i128(reinterpret_cast<i128 *>(sh.tot), acc_new);
+            atomic_add_i128(a.total + b, acc_new); // a few hundred per proposal: the atoms inside the cutoff of the new position
         }
-        __syncthreads();
-        if (threadIdx.x == 0 && (sh.tot[0] | sh.tot[1]) != 0) {
-            i128 v;
-            memcpy(&v, sh.tot, sizeof(v));
-            atomic_add_i128(a.total + b, v);
-        }
-        __syncthreads();
     }
 }
 
@@ -832,12 +854,34 @@ template <typename Real> __global__ void __launch_bounds__(EX_THREADS) k_bd_move
     }
 }
 
-// log weights of all molecules and their log-sum-exp (one block)
+// log weights of all molecules, their log-sum-exp, and the bound on the size of a molecule (one block)
 template <typename Real>
-__global__ void __launch_bounds__(EX_THREADS) k_bd_initial_weights(int M, Real beta, const i128 *__restrict__ E, Real *__restrict__ logw, Real *__restrict__ lse) {
+__global__ void __launch_bounds__(EX_THREADS) k_bd_initial_weights(
+    int M, int S, int first, Real beta, const i128 *__restrict__ E, const Vec4<Real> *__restrict__ xr, Real *__restrict__ logw,
+    Real *__restrict__ lse, Real *__restrict__ r_bound) {
     __shared__ LseScratch<Real> red;
+    Real r2 = 0;
     for (int m = threadIdx.x; m < M; m += EX_THREADS) {
         logw[m] = log_weight<Real>(E[m], beta);
+        const Vec4<Real> a0 = xr[first + m * S];
+        for (int i = 1; i < S; i++) {
+            const Vec4<Real> ai = xr[first + m * S + i];
+            const Real dx = ai.x - a0.x, dy = ai.y - a0.y, dz = ai.z - a0.z;
+            const Real d2 = dx * dx + dy * dy + dz * dz;
+            r2 = d2 > r2 ? d2 : r2; // a NaN coordinate never raises the bound; its pairs are outside every cutoff test too
+        }
+    }
+    red.v[threadIdx.x] = r2;
+    __syncthreads();
+    for (int w = EX_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w && red.v[threadIdx.x + w] > red.v[threadIdx.x]) {
+            red.v[threadIdx.x] = red.v[threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        // padded for the f32 rounding of the staged coordinates and of the rigid rotations applied during the move
+        r_bound[0] = sqrt(red.v[0]) * static_cast<Real>(1.001) + static_cast<Real>(1e-4);
     }
     __syncthreads();
     Real mx, sum;
@@ -1092,7 +1136,8 @@ BDExchangeMove<Real>::BDExchangeMove(
       num_target_mols_(static_cast<int>(target_mols.size())), nb_beta_(static_cast<Real>(nb_beta)),
       beta_(static_cast<Real>(1.0 / (BOLTZ * temperature))), cutoff_squared_(static_cast<Real>(cutoff * cutoff)), batch_size_(batch_size),
       first_atom_(target_mols[0].empty() ? 0 : *std::min_element(target_mols[0].begin(), target_mols[0].end())),
-      mol_potential_(N, target_mols, nb_beta, cutoff), d_params_(params.size()), d_xr_(N), d_pr_(N),
+      mol_potential_(N, target_mols, nb_beta, cutoff), sorter_(N), d_anchor_atoms_(num_target_mols_), d_mol_order_(num_target_mols_),
+      d_r_bound_(1), d_params_(params.size()), d_xr_(N), d_pr_(N),
       d_prop_(static_cast<size_t>(batch_size) * std::max(1, mol_size_)), d_before_E_(num_target_mols_),
       d_after_E_(static_cast<size_t>(batch_size) * num_target_mols_), d_total_(batch_size), d_logw_before_(num_target_mols_),
       d_logw_after_(static_cast<size_t>(batch_size) * num_target_mols_), d_lse_before_(2), d_lse_after_max_(batch_size),
@@ -1115,6 +1160,15 @@ BDExchangeMove<Real>::BDExchangeMove(
         throw std::runtime_error("Number of parameters must match N");
     }
     d_params_.copy_from(params.data());
+    {
+        std::vector<unsigned int> anchors(num_target_mols_);
+        for (int m = 0; m < num_target_mols_; m++) {
+            anchors[m] = static_cast<unsigned int>(first_atom_ + m * mol_size_);
+        }
+        d_anchor_atoms_.copy_from(anchors.data());
+        d_mol_order_.copy_from(anchors.data());
+    }
+    d_r_bound_.zero();
     d_lse_before_.zero();
     d_lse_after_max_.zero();
     d_lse_after_sum_.zero();
@@ -1140,7 +1194,8 @@ BDExchangeMove<Real>::BDExchangeMove(
     if (per_sm < 1) {
         throw std::runtime_error("BDExchangeMove: the move kernel does not fit on an SM");
     }
-    coop_blocks_ = sm_count() * std::min(per_sm, 2);
+    const char *bps = std::getenv("TMB_BD_BLOCKS_PER_SM"); // measurement knob
+    coop_blocks_ = sm_count() * std::min(per_sm, bps != nullptr ? std::max(1, std::atoi(bps)) : 2);
     TMB_CUDA(cudaDeviceSynchronize());
 }
 
@@ -1179,6 +1234,8 @@ template <typename Real> BDDevice<Real> BDExchangeMove<Real>::device_args(double
     a.lse_after_max = d_lse_after_max_.data;
     a.lse_after_sum = d_lse_after_sum_.data;
     a.samples = d_samples_.data;
+    a.mol_order = d_mol_order_.data;
+    a.r_bound = d_r_bound_.data;
     a.state = d_state_.data;
     a.num_accepted = d_num_accepted_.data;
     a.quat = d_quat_.data;
@@ -1192,7 +1249,12 @@ template <typename Real> BDDevice<Real> BDExchangeMove<Real>::device_args(double
 template <typename Real> void BDExchangeMove<Real>::initial_log_weights_device(double *d_coords, const double *d_box, cudaStream_t stream) {
     TMB_LAUNCH(k_stage_atoms<Real>, ceil_div(N_, 256), 256, 0, stream, N_, d_coords, d_params_.data, d_xr_.data, d_pr_.data);
     mol_potential_.mol_energies_staged(d_xr_.data, d_pr_.data, d_box, d_before_E_.data, stream);
-    TMB_LAUNCH(k_bd_initial_weights<Real>, 1, EX_THREADS, 0, stream, num_target_mols_, beta_, d_before_E_.data, d_logw_before_.data, d_lse_before_.data);
+    TMB_LAUNCH(
+        k_bd_initial_weights<Real>, 1, EX_THREADS, 0, stream, num_target_mols_, mol_size_, first_atom_, beta_, d_before_E_.data, d_xr_.data,
+        d_logw_before_.data, d_lse_before_.data, d_r_bound_.data);
+    // work order of the pair phase: molecules along the Hilbert curve of their first atoms (stale entries of molecules moved
+    // during the move only cost coherence)
+    sorter_.sort_device(num_target_mols_, d_anchor_atoms_.data, d_coords, d_box, d_mol_order_.data, stream);
 }
 
 template <typename Real> void BDExchangeMove<Real>::run_phase(int phase, const BDDevice<Real> &a, cudaStream_t stream) {

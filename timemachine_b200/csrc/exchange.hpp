@@ -117,6 +117,9 @@ protected:
     int coop_blocks_ = 0;
 
     NonbondedMolEnergyPotential<Real> mol_potential_;
+    HilbertSort sorter_;                                  // molecules in Hilbert order: spatially coherent warps in the pair phase
+    DeviceBuffer<unsigned int> d_anchor_atoms_, d_mol_order_; // first atom of every molecule; the same, Hilbert-sorted
+    DeviceBuffer<Real> d_r_bound_;                        // [1] bound on the distance of a molecule's atoms from its first atom
     DeviceBuffer<double> d_params_;
     DeviceBuffer<Vec4<Real>> d_xr_, d_pr_, d_prop_;
     DeviceBuffer<i128> d_before_E_, d_after_E_, d_total_;
