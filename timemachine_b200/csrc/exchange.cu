@@ -312,6 +312,130 @@ __global__ void __launch_bounds__(ME_THREADS) k_mol_energies(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// all-molecule energies in Hilbert order: the brute-force row x column sweep above, but rows and columns are visited
+// along the Hilbert curve of the molecules, 128 atoms per chunk with a bounding box each, and a row chunk skips every
+// column chunk whose box is further than the cutoff away (exact zeros).  Same integers as k_mol_energies.
+template <typename Real>
+__global__ void __launch_bounds__(ME_THREADS) k_me_chunks(
+    int N, int M, int S, int first, const unsigned int *__restrict__ mol_order, const Vec4<Real> *__restrict__ xr, const Vec4<Real> *__restrict__ pr,
+    const double *__restrict__ box, Vec4<Real> *__restrict__ xs, Vec4<Real> *__restrict__ ps, int *__restrict__ col_atom,
+    Vec4<Real> *__restrict__ chunk_ctr, Vec4<Real> *__restrict__ chunk_ext) {
+    __shared__ Real lo[3][ME_THREADS], hi[3][ME_THREADS];
+    const Box3<Real> b = load_box3<Real>(box);
+    const int c = blockIdx.x * ME_THREADS + threadIdx.x;
+    Real w[3] = {0, 0, 0};
+    const bool live = c < N;
+    if (live) {
+        int atom;
+        if (c < M * S) {
+            atom = static_cast<int>(mol_order[c / S]) + c % S;
+        } else {
+            const int k = c - M * S;
+            atom = k < first ? k : k + M * S;
+        }
+        const Vec4<Real> x = xr[atom];
+        xs[c] = x;
+        ps[c] = pr[atom];
+        col_atom[c] = atom;
+        // home-box image, for the bounding box only
+        w[0] = x.x - b.x * floor_(x.x * b.ix);
+        w[1] = x.y - b.y * floor_(x.y * b.iy);
+        w[2] = x.z - b.z * floor_(x.z * b.iz);
+    }
+    for (int d = 0; d < 3; d++) {
+        // a NaN coordinate poisons nothing here: the comparisons below drop it, and its pairs fail every cutoff test
+        lo[d][threadIdx.x] = live ? w[d] : inf_<Real>();
+        hi[d][threadIdx.x] = live ? w[d] : -inf_<Real>();
+    }
+    __syncthreads();
+    for (int s2 = ME_THREADS / 2; s2 > 0; s2 >>= 1) {
+        if (threadIdx.x < s2) {
+            for (int d = 0; d < 3; d++) {
+                if (lo[d][threadIdx.x + s2] < lo[d][threadIdx.x]) {
+                    lo[d][threadIdx.x] = lo[d][threadIdx.x + s2];
+                }
+                if (hi[d][threadIdx.x + s2] > hi[d][threadIdx.x]) {
+                    hi[d][threadIdx.x] = hi[d][threadIdx.x + s2];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Vec4<Real> ctr, ext;
+        const Real half = static_cast<Real>(0.5), pad = static_cast<Real>(1e-4);
+        ctr.x = half * (lo[0][0] + hi[0][0]);
+        ctr.y = half * (lo[1][0] + hi[1][0]);
+        ctr.z = half * (lo[2][0] + hi[2][0]);
+        ctr.w = 0;
+        ext.x = half * (hi[0][0] - lo[0][0]) + pad;
+        ext.y = half * (hi[1][0] - lo[1][0]) + pad;
+        ext.z = half * (hi[2][0] - lo[2][0]) + pad;
+        ext.w = 0;
+        chunk_ctr[blockIdx.x] = ctr;
+        chunk_ext[blockIdx.x] = ext;
+    }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(ME_THREADS) k_mol_energies_sorted(
+    int N, int M, int S, int first, const Vec4<Real> *__restrict__ xs, const Vec4<Real> *__restrict__ ps, const int *__restrict__ col_atom,
+    const Vec4<Real> *__restrict__ chunk_ctr, const Vec4<Real> *__restrict__ chunk_ext, const double *__restrict__ box, Real beta, Real cutoff2,
+    i128 *__restrict__ out) {
+    __shared__ Vec4<Real> sx[ME_THREADS], sp[ME_THREADS];
+    __shared__ int sa[ME_THREADS];
+    const Box3<Real> b = load_box3<Real>(box);
+    const int r = blockIdx.x * ME_THREADS + threadIdx.x; // row = one of the first M * S sorted atoms
+    const bool live = r < M * S;
+    Vec4<Real> xi = {}, pi = {};
+    int lo_atom = 0, hi_atom = -1, mol = 0;
+    if (live) {
+        xi = xs[r];
+        pi = ps[r];
+        lo_atom = col_atom[r] - r % S;
+        hi_atom = lo_atom + S - 1;
+        mol = (lo_atom - first) / S;
+    }
+    const Vec4<Real> rc = chunk_ctr[blockIdx.x], re = chunk_ext[blockIdx.x];
+    const int n_chunks = (N + ME_THREADS - 1) / ME_THREADS;
+    i128 acc = 0;
+    for (int c = blockIdx.y; c < n_chunks; c += gridDim.y) {
+        const Vec4<Real> cc = chunk_ctr[c], ce = chunk_ext[c];
+        Real dx = rc.x - cc.x, dy = rc.y - cc.y, dz = rc.z - cc.z;
+        dx -= b.x * rint_(dx * b.ix);
+        dy -= b.y * rint_(dy * b.iy);
+        dz -= b.z * rint_(dz * b.iz);
+        const Real gx = fmax(fabs(dx) - re.x - ce.x, static_cast<Real>(0));
+        const Real gy = fmax(fabs(dy) - re.y - ce.y, static_cast<Real>(0));
+        const Real gz = fmax(fabs(dz) - re.z - ce.z, static_cast<Real>(0));
+        if (gx * gx + gy * gy + gz * gz >= cutoff2) {
+            continue; // block-uniform: no atom of the column chunk is within the cutoff of any row atom
+        }
+        const int base = c * ME_THREADS;
+        const int n = min(ME_THREADS, N - base);
+        __syncthreads();
+        if (static_cast<int>(threadIdx.x) < n) {
+            sx[threadIdx.x] = xs[base + threadIdx.x];
+            sp[threadIdx.x] = ps[base + threadIdx.x];
+            sa[threadIdx.x] = col_atom[base + threadIdx.x];
+        }
+        __syncthreads();
+        if (live) {
+            for (int k = 0; k < n; k++) {
+                const int jj = sa[k];
+                if (jj >= lo_atom && jj <= hi_atom) {
+                    continue; // same molecule
+                }
+                acc += pair_e(xi, pi, sx[k], sp[k], b, cutoff2, beta);
+            }
+        }
+    }
+    if (live && acc != 0) {
+        atomic_add_i128(out + mol, acc);
+    }
+}
+
 // reference k_atom_by_atom_energies (k_nonbonded.cuh:604-700): [T, N] pair energies in Real
 template <typename Real>
 __global__ void k_atom_by_atom(
@@ -500,7 +624,8 @@ template <typename Real> struct BDDevice {
     Vec4<Real> *xr;      // [N] staged copy of coords (+ w), kept in step with coords
     const Vec4<Real> *pr;
     Vec4<Real> *prop;    // [B, S] proposed positions
-    i128 *before_E, *after_E, *total; // [M], [B, M], [B]
+    Vec4<Real> *prop_old; // [B, S] positions the proposal moves away from (a copy: xr changes when a proposal is accepted)
+    i128 *before_E, *total;           // [M], [B]: molecule energies of the current state; energy of the moved molecule per proposal
     Real *logw_before, *logw_after;   // [M], [B, M]
     Real *lse_before;                 // {max, sum}
     Real *lse_after_max, *lse_after_sum; // [B]
@@ -545,6 +670,44 @@ template <typename Real> __device__ void ti_partition(const TIDevice<Real> &t, i
         t.inner_count[0] = inner_before;
     }
     __syncthreads();
+}
+
+// Most molecules are out of reach of a proposal and keep their weight: the proposal's row starts as a copy of the current
+// weights (coalesced) and the pair phase rewrites only the molecules near the old or the new position.
+template <typename Real> __device__ __forceinline__ void bd_seed_after_weights(const BDDevice<Real> &a, int b) {
+    Real *row = a.logw_after + static_cast<size_t>(b) * a.M;
+    for (int m = threadIdx.x; m < a.M; m += EX_THREADS) {
+        row[m] = a.logw_before[m];
+    }
+}
+
+// energy change of molecule `mol` (first atom j0) when molecule s goes from xold to xnew; *e_new_out: its energy with the
+// new position alone.  Exact zeros when the first atoms are further apart than reach (see the pair phase).
+template <typename Real>
+__device__ __forceinline__ bool bd_mol_delta(
+    const BDDevice<Real> &a, const Box3<Real> &bx, const Vec4<Real> *xold, const Vec4<Real> *xnew, const Vec4<Real> *pmol, int j0,
+    Real reach2, i128 &delta, i128 &e_new_out) {
+    const Vec4<Real> anchor = a.xr[j0];
+    const bool near_old = anchor_d2(xold[0], anchor, bx) < reach2;
+    const bool near_new = anchor_d2(xnew[0], anchor, bx) < reach2;
+    if (!(near_old || near_new)) {
+        return false;
+    }
+    for (int i = 0; i < a.S; i++) {
+        const Vec4<Real> xo = xold[i], xn = xnew[i], pi = pmol[i];
+        for (int j = j0; j < j0 + a.S; j++) {
+            const Vec4<Real> xj = a.xr[j], pj = a.pr[j];
+            if (near_new) {
+                const i128 e_new = pair_e(xn, pi, xj, pj, bx, a.cutoff2, a.nb_beta);
+                delta += e_new;
+                e_new_out += e_new;
+            }
+            if (near_old) {
+                delta -= pair_e(xo, pi, xj, pj, bx, a.cutoff2, a.nb_beta);
+            }
+        }
+    }
+    return true;
 }
 
 // phase S: choose the molecule of every live batch slot and build its proposal
@@ -595,7 +758,11 @@ template <typename Real> __device__ void bd_phase_sample(const BDDevice<Real> &a
                 rotate_and_translate(
                     a.S, a.xr + a.first + s * a.S, a.quat + static_cast<size_t>(off + b) * 4,
                     a.trans + static_cast<size_t>(off + b) * 6 + (flag ? 0 : 3), bx, false, a.prop + static_cast<size_t>(b) * a.S);
+                for (int i = 0; i < a.S; i++) {
+                    a.prop_old[static_cast<size_t>(b) * a.S + i] = a.xr[a.first + s * a.S + i];
+                }
             }
+            bd_seed_after_weights(a, b);
         }
         return;
     }
@@ -612,7 +779,11 @@ template <typename Real> __device__ void bd_phase_sample(const BDDevice<Real> &a
             rotate_and_translate(
                 a.S, a.xr + a.first + s * a.S, a.quat + static_cast<size_t>(off + b) * 4, a.trans + static_cast<size_t>(off + b) * 3, bx,
                 a.scale != 0, a.prop + static_cast<size_t>(b) * a.S);
+            for (int i = 0; i < a.S; i++) {
+                a.prop_old[static_cast<size_t>(b) * a.S + i] = a.xr[a.first + s * a.S + i];
+            }
         }
+        bd_seed_after_weights(a, b);
     }
 }
 
@@ -638,7 +809,7 @@ template <typename Real> __device__ void bd_phase_energies(const BDDevice<Real> 
         const int b = static_cast<int>(task / chunks);
         const int item = static_cast<int>(task % chunks) * WARP + lane;
         const int s = a.samples[b];
-        const Vec4<Real> *xold = a.xr + a.first + s * a.S;
+        const Vec4<Real> *xold = a.prop_old + static_cast<size_t>(b) * a.S;
         const Vec4<Real> *pmol = a.pr + a.first + s * a.S;
         const Vec4<Real> *xnew = a.prop + static_cast<size_t>(b) * a.S;
         i128 acc_new = 0;
@@ -650,28 +821,9 @@ template <typename Real> __device__ void bd_phase_energies(const BDDevice<Real> 
             const int mol = (j0 - a.first) / a.S;
             if (mol != s) {
                 i128 delta = 0;
-                const Vec4<Real> anchor = a.xr[j0];
-                const bool near_old = anchor_d2(xold[0], anchor, bx) < reach_mol * reach_mol;
-                const bool near_new = anchor_d2(xnew[0], anchor, bx) < reach_mol * reach_mol;
-                if (near_old || near_new) {
-                    for (int i = 0; i < a.S; i++) {
-                        const Vec4<Real> xo = xold[i], xn = xnew[i], pi = pmol[i];
-                        for (int j = j0; j < j0 + a.S; j++) {
-                            const Vec4<Real> xj = a.xr[j], pj = a.pr[j];
-                            if (near_new) {
-                                const i128 e_new = pair_e(xn, pi, xj, pj, bx, a.cutoff2, a.nb_beta);
-                                delta += e_new;
-                                acc_new += e_new;
-                            }
-                            if (near_old) {
-                                delta -= pair_e(xo, pi, xj, pj, bx, a.cutoff2, a.nb_beta);
-                            }
-                        }
-                    }
+                if (bd_mol_delta(a, bx, xold, xnew, pmol, j0, reach_mol * reach_mol, delta, acc_new)) {
+                    a.logw_after[static_cast<size_t>(b) * a.M + mol] = log_weight<Real>(a.before_E[mol] + delta, a.beta);
                 }
-                const i128 e = a.before_E[mol] + delta;
-                a.after_E[static_cast<size_t>(b) * a.M + mol] = e;
-                a.logw_after[static_cast<size_t>(b) * a.M + mol] = log_weight<Real>(e, a.beta);
             }
         } else if (item < items) {
             const int k = item - a.M;
@@ -695,9 +847,7 @@ template <typename Real> __device__ void bd_phase_lse(const BDDevice<Real> &a, B
     for (int b = block; b < live; b += nblocks) {
         if (threadIdx.x == 0) {
             const int s = a.samples[b];
-            const i128 e = a.total[b];
-            a.after_E[static_cast<size_t>(b) * a.M + s] = e;
-            a.logw_after[static_cast<size_t>(b) * a.M + s] = log_weight<Real>(e, a.beta);
+            a.logw_after[static_cast<size_t>(b) * a.M + s] = log_weight<Real>(a.total[b], a.beta);
         }
         __syncthreads();
         Real m, sum;
@@ -777,14 +927,30 @@ template <typename Real> __device__ void bd_phase_accept(const BDDevice<Real> &a
     __syncthreads();
     const int sel = sh.sel;
     if (sel < a.B) {
-        for (int m = block * EX_THREADS + threadIdx.x; m < a.M; m += nblocks * EX_THREADS) {
-            a.before_E[m] = a.after_E[static_cast<size_t>(sel) * a.M + m];
-            a.logw_before[m] = a.logw_after[static_cast<size_t>(sel) * a.M + m];
+        // the accepted proposal becomes the state: energies of the molecules it touches are re-derived (the same integers the
+        // pair phase formed; no [B, M] energy matrix is kept), the weights are its row
+        const Box3<Real> bx = load_box3<Real>(a.box);
+        const int s = a.samples[sel];
+        const Vec4<Real> *xold = a.prop_old + static_cast<size_t>(sel) * a.S;
+        const Vec4<Real> *xnew = a.prop + static_cast<size_t>(sel) * a.S;
+        const Vec4<Real> *pmol = a.pr + a.first + s * a.S;
+        const Real reach_mol = sqrt(a.cutoff2) + 2 * a.r_bound[0];
+        for (int item = block * EX_THREADS + threadIdx.x; item < a.M; item += nblocks * EX_THREADS) {
+            const int j0 = static_cast<int>(a.mol_order[item]);
+            const int mol = (j0 - a.first) / a.S;
+            if (mol != s) {
+                i128 delta = 0, unused = 0;
+                if (bd_mol_delta(a, bx, xold, xnew, pmol, j0, reach_mol * reach_mol, delta, unused)) {
+                    a.before_E[mol] += delta;
+                }
+            }
+            a.logw_before[item] = a.logw_after[static_cast<size_t>(sel) * a.M + item];
         }
     }
     if (block == 0 && threadIdx.x == 0) {
         if (sel < a.B) {
             const int s = a.samples[sel];
+            a.before_E[s] = a.total[sel];
             for (int i = 0; i < a.S; i++) {
                 const Vec4<Real> p = a.prop[static_cast<size_t>(sel) * a.S + i];
                 const int atom = a.first + s * a.S + i;
@@ -1137,9 +1303,10 @@ BDExchangeMove<Real>::BDExchangeMove(
       beta_(static_cast<Real>(1.0 / (BOLTZ * temperature))), cutoff_squared_(static_cast<Real>(cutoff * cutoff)), batch_size_(batch_size),
       first_atom_(target_mols[0].empty() ? 0 : *std::min_element(target_mols[0].begin(), target_mols[0].end())),
       mol_potential_(N, target_mols, nb_beta, cutoff), sorter_(N), d_anchor_atoms_(num_target_mols_), d_mol_order_(num_target_mols_),
-      d_r_bound_(1), d_params_(params.size()), d_xr_(N), d_pr_(N),
-      d_prop_(static_cast<size_t>(batch_size) * std::max(1, mol_size_)), d_before_E_(num_target_mols_),
-      d_after_E_(static_cast<size_t>(batch_size) * num_target_mols_), d_total_(batch_size), d_logw_before_(num_target_mols_),
+      d_r_bound_(1), d_xs_(N), d_ps_(N), d_col_atom_(N), d_chunk_ctr_(ceil_div(std::max(N, 1), ME_THREADS)),
+      d_chunk_ext_(ceil_div(std::max(N, 1), ME_THREADS)), d_params_(params.size()), d_xr_(N), d_pr_(N),
+      d_prop_(static_cast<size_t>(batch_size) * std::max(1, mol_size_)), d_prop_old_(static_cast<size_t>(batch_size) * std::max(1, mol_size_)), d_before_E_(num_target_mols_),
+      d_total_(batch_size), d_logw_before_(num_target_mols_),
       d_logw_after_(static_cast<size_t>(batch_size) * num_target_mols_), d_lse_before_(2), d_lse_after_max_(batch_size),
       d_lse_after_sum_(batch_size), d_samples_(batch_size), d_state_(ST_WORDS), d_num_accepted_(1),
       d_quat_(round_up_even(static_cast<size_t>(4) * std::max(num_proposals_per_move, 0))), d_trans_(translation_buffer_size),
@@ -1176,7 +1343,6 @@ BDExchangeMove<Real>::BDExchangeMove(
     d_state_.zero();
     d_logw_before_.zero();
     d_logw_after_.zero();
-    d_after_E_.zero();
     // four generators so that the sequences do not depend on the batch size (reference bd_exchange_move.cu:96-108)
     TMB_CURAND(curandCreateGenerator(&rng_quat_, CURAND_RNG_PSEUDO_DEFAULT));
     TMB_CURAND(curandSetPseudoRandomGeneratorSeed(rng_quat_, seed));
@@ -1226,7 +1392,7 @@ template <typename Real> BDDevice<Real> BDExchangeMove<Real>::device_args(double
     a.pr = d_pr_.data;
     a.prop = d_prop_.data;
     a.before_E = d_before_E_.data;
-    a.after_E = d_after_E_.data;
+    a.prop_old = d_prop_old_.data;
     a.total = d_total_.data;
     a.logw_before = d_logw_before_.data;
     a.logw_after = d_logw_after_.data;
@@ -1248,13 +1414,22 @@ template <typename Real> BDDevice<Real> BDExchangeMove<Real>::device_args(double
 
 template <typename Real> void BDExchangeMove<Real>::initial_log_weights_device(double *d_coords, const double *d_box, cudaStream_t stream) {
     TMB_LAUNCH(k_stage_atoms<Real>, ceil_div(N_, 256), 256, 0, stream, N_, d_coords, d_params_.data, d_xr_.data, d_pr_.data);
-    mol_potential_.mol_energies_staged(d_xr_.data, d_pr_.data, d_box, d_before_E_.data, stream);
+    // molecules along the Hilbert curve of their first atoms: the order of the all-molecule energy sweep below and of the pair
+    // phase of the move (entries of molecules moved during the move go stale, which only costs coherence)
+    sorter_.sort_device(num_target_mols_, d_anchor_atoms_.data, d_coords, d_box, d_mol_order_.data, stream);
+    const int n_chunks = ceil_div(N_, ME_THREADS);
+    const int row_chunks = ceil_div(num_target_mols_ * mol_size_, ME_THREADS);
+    TMB_LAUNCH(
+        k_me_chunks<Real>, n_chunks, ME_THREADS, 0, stream, N_, num_target_mols_, mol_size_, first_atom_, d_mol_order_.data, d_xr_.data,
+        d_pr_.data, d_box, d_xs_.data, d_ps_.data, d_col_atom_.data, d_chunk_ctr_.data, d_chunk_ext_.data);
+    TMB_CUDA(cudaMemsetAsync(d_before_E_.data, 0, d_before_E_.bytes(), stream));
+    const int by = std::max(1, std::min(n_chunks, ceil_div(6 * sm_count(), row_chunks)));
+    TMB_LAUNCH(
+        k_mol_energies_sorted<Real>, dim3(row_chunks, by), ME_THREADS, 0, stream, N_, num_target_mols_, mol_size_, first_atom_, d_xs_.data,
+        d_ps_.data, d_col_atom_.data, d_chunk_ctr_.data, d_chunk_ext_.data, d_box, nb_beta_, cutoff_squared_, d_before_E_.data);
     TMB_LAUNCH(
         k_bd_initial_weights<Real>, 1, EX_THREADS, 0, stream, num_target_mols_, mol_size_, first_atom_, beta_, d_before_E_.data, d_xr_.data,
         d_logw_before_.data, d_lse_before_.data, d_r_bound_.data);
-    // work order of the pair phase: molecules along the Hilbert curve of their first atoms (stale entries of molecules moved
-    // during the move only cost coherence)
-    sorter_.sort_device(num_target_mols_, d_anchor_atoms_.data, d_coords, d_box, d_mol_order_.data, stream);
 }
 
 template <typename Real> void BDExchangeMove<Real>::run_phase(int phase, const BDDevice<Real> &a, cudaStream_t stream) {

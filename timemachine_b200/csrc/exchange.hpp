@@ -120,9 +120,12 @@ protected:
     HilbertSort sorter_;                                  // molecules in Hilbert order: spatially coherent warps in the pair phase
     DeviceBuffer<unsigned int> d_anchor_atoms_, d_mol_order_; // first atom of every molecule; the same, Hilbert-sorted
     DeviceBuffer<Real> d_r_bound_;                        // [1] bound on the distance of a molecule's atoms from its first atom
+    DeviceBuffer<Vec4<Real>> d_xs_, d_ps_;                // atoms in sweep order (Hilbert-sorted molecules, then the other atoms)
+    DeviceBuffer<int> d_col_atom_;                        // atom index of every sweep slot
+    DeviceBuffer<Vec4<Real>> d_chunk_ctr_, d_chunk_ext_;  // bounding box of every 128 sweep slots (home-box images)
     DeviceBuffer<double> d_params_;
-    DeviceBuffer<Vec4<Real>> d_xr_, d_pr_, d_prop_;
-    DeviceBuffer<i128> d_before_E_, d_after_E_, d_total_;
+    DeviceBuffer<Vec4<Real>> d_xr_, d_pr_, d_prop_, d_prop_old_;
+    DeviceBuffer<i128> d_before_E_, d_total_;
     DeviceBuffer<Real> d_logw_before_, d_logw_after_;
     DeviceBuffer<Real> d_lse_before_, d_lse_after_max_, d_lse_after_sum_;
     DeviceBuffer<int> d_samples_, d_state_;
