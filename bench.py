@@ -326,6 +326,67 @@ def npt_arm(args, s, ops, impl, flat, x_eq, v_eq, dev, torch):
     return out
 
 
+def water_sampling_arm(args, s, ops, impl, flat, lam, x_eq, v_eq, dev, torch):
+    """Side measurement, not the headline metric: the same leg with the reference's production water sampling (targeted
+    insertion / biased deletion around the ligand: 1000 proposals in batches of 250 every 400 steps, radius 1 nm,
+    timemachine/fe/free_energy.py:119-147, 640-657) with this repo's TIBDExchangeMove, and with the compiled reference's
+    where oracle/_ref is present."""
+    n_env = s["n_env"]
+    mols = [[i, i + 1, i + 2] for i in range(0, n_env, 3)]
+    lig = s["lig_idx"].astype(np.int32)
+    proposals, batch, radius, reps = 1000, 250, 1.0, 3
+
+    def time_ctx(make):
+        ctx, mover = make()
+        ctx.multiple_steps(args.md_steps, args.md_steps + 1)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.multiple_steps(args.md_steps, args.md_steps + 1)
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / (reps * args.md_steps), mover
+
+    def ours():
+        bp = ops.BoundPotential(impl, flat)
+        intg = ops.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 4321)
+        mover = ops.TIBDExchangeMove_f32(
+            s["N"], lig, mols, params_at_lambda(s, lam), TEMPERATURE, BETA, CUTOFF, radius, 77, proposals, args.md_steps, batch_size=batch
+        )
+        return ops.Context(x_eq, v_eq, s["box"], intg, [bp], movers=[mover]), mover
+
+    out = {"mover": "TIBDExchangeMove_f32", "proposals_per_move": proposals, "batch_size": batch, "interval": args.md_steps, "radius_nm": radius,
+           "unit": "ns/day", "timing": f"wall clock around {reps} x {args.md_steps} steps, synchronised both sides"}
+    try:
+        t, mover = time_ctx(ours)
+        out.update(value=86400.0 / t * DT * 1e-3, us_per_md_step=t * 1e6, accepted=mover.n_accepted(), proposed=mover.n_proposed())
+    except Exception as e:
+        out["error"] = repr(e)[:200]
+        return out
+    if not args.no_ref_gpu:
+        try:
+            from tests.common import load_reference_ops
+
+            ref = load_reference_ops()
+            if ref is not None:
+                with stdout_to_stderr():
+
+                    def theirs():
+                        rbp = ref.BoundPotential(make_reference_potential(ref, s), flat)
+                        rintg = ref.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 4321)
+                        rmover = ref.TIBDExchangeMove_f32(
+                            s["N"], lig.tolist(), mols, params_at_lambda(s, lam), TEMPERATURE, BETA, CUTOFF, radius, 77, proposals,
+                            args.md_steps, batch_size=batch,
+                        )
+                        return ref.Context(x_eq, v_eq, s["box"], rintg, [rbp], [rmover]), rmover
+
+                    rt, rmover = time_ctx(theirs)
+                out["reference_gpu"] = {"value": 86400.0 / rt * DT * 1e-3, "us_per_md_step": rt * 1e6, "accepted": rmover.n_accepted(),
+                                        "proposed": rmover.n_proposed()}
+        except Exception as e:
+            out["reference_gpu"] = {"unavailable": repr(e)[:200]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -338,6 +399,7 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the compiled reference custom_ops on the GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-npt", action="store_true", help="skip the NPT (barostat) side measurement")
+    ap.add_argument("--no-water-sampling", action="store_true", help="skip the water-exchange (TIBD mover) side measurement")
     args = ap.parse_args()
 
     # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner, the
@@ -582,6 +644,9 @@ def main():
     npt = None
     if rank == 0 and world == 1 and not args.no_npt:
         npt = npt_arm(args, s, ops, impl, flats[my_state], x_eq, v_eq, dev, torch)
+    water_sampling = None
+    if rank == 0 and world == 1 and not args.no_water_sampling:
+        water_sampling = water_sampling_arm(args, s, ops, impl, flats[my_state], float(lambdas[my_state]), x_eq, v_eq, dev, torch)
 
     if rank == 0:
         out = {
@@ -591,7 +656,7 @@ def main():
                                                 timing="CUDA events on the MD stream per bench step, summed; max over ranks"),
             "clocks": clocks, "gpu_launches": int(gpu_launches), "nblist_rebuilds": int(nblist_rebuilds), "md_steps_timed": int(args.md_steps * args.steps), "wall_s": wall,
             "e2e": {"value": e2e_ns_day, "unit": "ns/day", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": ref_gpu, "npt": npt,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": ref_gpu, "npt": npt, "water_sampling": water_sampling,
             "us_per_md_step": total_ms * 1e3 / (args.md_steps * args.steps),
         }
         print(json.dumps(out), file=json_out, flush=True)
