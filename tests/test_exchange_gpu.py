@@ -657,3 +657,40 @@ def test_tibd_log_probability_matches_oracle():
         assert mover.last_log_probability() == min(raw, 0.0)
         x = x_new
     assert checked >= 1
+
+
+@pytest.mark.parametrize("precision", [np.float64, np.float32])
+@pytest.mark.parametrize("radius", [0.2, 2.2])
+def test_tibd_empty_region_edge_cases(precision, radius):
+    """test_cuda_targeted_insertion_mover.py:419-488 (the buckyball edge cases): one of the two regions starts empty - a
+    droplet in a large box with a sphere too small to hold any water, or large enough to hold them all - so the first
+    proposals can only go one way; later ones choose by the noise.  Against the compiled reference where present."""
+    o = ops()
+    x, params, box, mols, lig = ligand_water_system(150)
+    box = np.eye(3) * 12.0
+    N = len(x)
+    inner, outer = klass(o, "inner_and_outer_mols", precision)(lig, x, box, mols, radius)
+    assert (len(inner) == 0) if radius < 1.0 else (len(outer) == 0)
+    args = (N, lig, mols, params, TEMP, BETA, CUTOFF, radius, 2025, 60, 1)
+    mine = klass(o, "TIBDExchangeMove", precision)(*args, batch_size=20)
+    single = klass(o, "TIBDExchangeMove", precision)(*args[:-2], 1, 1)
+    ref = load_reference_ops()
+    theirs = klass(ref, "TIBDExchangeMove", precision)(*args, batch_size=20) if ref is not None else None
+    xa, xb, xc = x.copy(), x.copy(), x.copy()
+    for _ in range(3):
+        xa, _ = mine.move(xa, box)
+        for _ in range(60):
+            xc, _ = single.move(xc, box)
+        np.testing.assert_array_equal(xa, xc)  # batch-size independence through the edge cases
+        if theirs is not None:
+            xb, _ = theirs.move(xb, box)
+            assert mine.n_accepted() == theirs.n_accepted()
+            if precision == np.float32:
+                np.testing.assert_array_equal(xa, xb)
+            else:
+                np.testing.assert_allclose(xa, xb, rtol=0, atol=1e-12)
+    assert mine.n_accepted() == single.n_accepted()
+    assert mine.n_proposed() == single.n_proposed() == 180
+    if mine.n_accepted() > 0:
+        new_inner, new_outer = klass(o, "inner_and_outer_mols", precision)(lig, xa, box, mols, radius)
+        assert len(new_inner) > 0 and len(new_outer) > 0  # the empty region got populated
