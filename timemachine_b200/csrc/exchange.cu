@@ -640,7 +640,6 @@ template <typename Real> struct BDDevice {
 
 template <typename Real> struct BDShared {
     LseScratch<Real> red;
-    unsigned long long tot[2]; // i128 partial of a block (two limbs)
     int sel;
 };
 
@@ -1248,11 +1247,6 @@ std::vector<i128> NonbondedMolEnergyPotential<Real>::mol_energies_host(int N, in
 template <typename Real>
 SegmentedSumExp<Real>::SegmentedSumExp(int max_vals_per_segment, int num_segments)
     : max_vals_per_segment_(max_vals_per_segment), num_segments_(num_segments) {}
-
-struct FlatSegments {
-    std::vector<int> offsets;
-    int total = 0;
-};
 
 template <typename Real> std::vector<Real> SegmentedSumExp<Real>::logsumexp_host(const std::vector<std::vector<Real>> &vals) {
     const int num_segments = static_cast<int>(vals.size());
