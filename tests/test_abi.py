@@ -79,3 +79,44 @@ def test_host_side_validation_without_gpu():
     bad[0, 1] = 0.1
     with pytest.raises(RuntimeError, match="box must be ortholinear"):
         ops._verify_coords_and_box(np.zeros((2, 3)), bad)
+
+
+def test_exchange_surface_and_host_side_validation_without_gpu():
+    """the exchange movers and their helpers are exported under the reference's names
+    (timemachine/lib/custom_ops.pyi), and the argument checks that precede any CUDA call keep its messages
+    (wrap_kernels.cpp:1749-1755, 2055-2100, 2124-2126)."""
+    import numpy as np
+
+    from timemachine_b200 import custom_ops as ops
+
+    for base in ("BDExchangeMove", "TIBDExchangeMove", "NonbondedMolEnergyPotential", "SegmentedSumExp", "SegmentedWeightedRandomSampler",
+                 "atom_by_atom_energies", "rotate_coords", "rotate_and_translate_mol", "inner_and_outer_mols",
+                 "translations_inside_and_outside_sphere_host"):
+        for suffix in ("f32", "f64"):
+            assert hasattr(ops, f"{base}_{suffix}"), f"{base}_{suffix}"
+    assert issubclass(ops.BDExchangeMove_f32, ops.Mover) and issubclass(ops.TIBDExchangeMove_f64, ops.BDExchangeMove_f64)
+    for m in ("move", "compute_initial_log_weights", "compute_incremental_log_weights", "get_params", "set_params", "last_log_probability",
+              "last_raw_log_probability", "n_accepted", "n_proposed", "acceptance_fraction", "get_before_log_weights",
+              "get_after_log_weights", "batch_size", "set_interval", "get_interval", "set_step"):
+        assert hasattr(ops.BDExchangeMove_f32, m), m
+    params = np.zeros((10, 4))
+    mols = [[0, 1, 2], [3, 4, 5]]
+    for k, extra in ((ops.BDExchangeMove_f32, ()), (ops.TIBDExchangeMove_f32, ([9],))):
+        lead = (10, *extra, mols)
+        tail = (300.0, 2.0, 1.2) + ((1.0,) if extra else ())
+        with pytest.raises(RuntimeError, match="proposals per move must be greater than 0"):
+            k(*lead, params, *tail, 1, 0, 1)
+        with pytest.raises(RuntimeError, match="parameters dimensions must be 2"):
+            k(*lead, params.reshape(-1), *tail, 1, 1, 1)
+        with pytest.raises(RuntimeError, match="Number of parameters must match N"):
+            k(*lead, params[:9], *tail, 1, 1, 1)
+    with pytest.raises(RuntimeError, match="quaternions must have a shape that is 4 dimensional"):
+        ops.rotate_coords_f32(np.zeros((3, 3)), np.zeros((2, 3)))
+    with pytest.raises(RuntimeError, match="quaternions dimensions must be 2"):
+        ops.rotate_and_translate_mol_f64(np.zeros((3, 3)), np.eye(3), np.zeros(4), np.zeros((1, 3)))
+    with pytest.raises(RuntimeError, match="translations must be of size 3"):
+        ops.rotate_and_translate_mol_f64(np.zeros((3, 3)), np.eye(3), np.zeros((1, 4)), np.zeros((1, 2)))
+    with pytest.raises(RuntimeError, match="Number of quaternions and translations must match"):
+        ops.rotate_and_translate_mol_f64(np.zeros((3, 3)), np.eye(3), np.zeros((2, 4)), np.zeros((1, 3)))
+    with pytest.raises(RuntimeError, match="Center must be of length 3"):
+        ops.translations_inside_and_outside_sphere_host_f32(4, np.eye(3), np.zeros(2), 1.0, 1)

@@ -922,7 +922,7 @@ class BDExchangeMove_f64(_BDExchangeMove):
     _precision = F64
 
 
-class _TIBDExchangeMove(_BDExchangeMove):
+class _TIBDExchangeMove:
     """TIBDExchangeMove_{f32,f64}(N, ligand_idxs, target_mols, params, temperature, nb_beta, cutoff, radius, seed,
     num_proposals_per_move, interval, batch_size=1): targeted insertion / biased deletion between a sphere around the
     ligand centroid and the bulk (wrap_kernels.cpp:1902-1975; tibd_exchange_move.cu; the Python reference is
@@ -956,11 +956,11 @@ class _TIBDExchangeMove(_BDExchangeMove):
         self._real = np.float32 if self._precision == F32 else np.float64
 
 
-class TIBDExchangeMove_f32(_TIBDExchangeMove):
+class TIBDExchangeMove_f32(_TIBDExchangeMove, BDExchangeMove_f32):  # custom_ops.pyi: TIBDExchangeMove_f32(BDExchangeMove_f32)
     _precision = F32
 
 
-class TIBDExchangeMove_f64(_TIBDExchangeMove):
+class TIBDExchangeMove_f64(_TIBDExchangeMove, BDExchangeMove_f64):
     _precision = F64
 
 
