@@ -1545,8 +1545,13 @@ template <typename Real> void BDExchangeMove<Real>::run_proposals(BDDevice<Real>
             TMB_CUDA(cudaStreamSynchronize(stream));
         }
     } else {
+        // a grid barrier costs in proportion to the CTAs that meet at it: small batches get a grid sized for their pair phase
+        // (about two 32-molecule tasks per warp) instead of the whole machine
+        const int chunks = ceil_div(num_target_mols_ + (N_ - num_target_mols_ * mol_size_), WARP);
+        const long long want = std::max<long long>(batch_size_, ceil_div<long long>(static_cast<long long>(batch_size_) * chunks, 2 * (EX_THREADS / WARP)));
+        const int blocks = static_cast<int>(std::min<long long>(coop_blocks_, std::max<long long>(want, 8)));
         void *args[] = {&a};
-        TMB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_bd_move<Real>), dim3(coop_blocks_), dim3(EX_THREADS), args, 0, stream));
+        TMB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_bd_move<Real>), dim3(blocks), dim3(EX_THREADS), args, 0, stream));
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
 }
