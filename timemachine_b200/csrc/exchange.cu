@@ -464,6 +464,7 @@ template <typename Real> struct LseScratch {
 
 template <typename Real> __device__ Real block_max(const Real *vals, int n, LseScratch<Real> &s) {
     Real m = -inf_<Real>();
+#pragma unroll 8
     for (int k = threadIdx.x; k < n; k += EX_THREADS) {
         const Real v = vals[k];
         m = (v > m) ? v : m;
@@ -488,7 +489,8 @@ template <typename Real> __device__ Real block_max(const Real *vals, int n, LseS
 template <typename Real> __device__ void block_sumexp(const Real *vals, int n, LseScratch<Real> &s, Real &out_max, Real &out_sum) {
     const Real m = block_max(vals, n, s);
     Real acc = static_cast<Real>(0);
-    for (int k = threadIdx.x; k < n; k += EX_THREADS) {
+#pragma unroll 8
+    for (int k = threadIdx.x; k < n; k += EX_THREADS) { // loads and exps overlap; the adds stay in order
         acc = add_(acc, exp_(sub_(vals[k], m)));
     }
     s.v[threadIdx.x] = acc;
@@ -509,6 +511,7 @@ template <typename Real> __device__ void block_sumexp(const Real *vals, int n, L
 template <typename Real> __device__ int block_gumbel_argmax(const Real *logw, const Real *noise, int n, LseScratch<Real> &s) {
     Real best = -inf_<Real>();
     int best_i = 0x7fffffff;
+#pragma unroll 8
     for (int k = threadIdx.x; k < n; k += EX_THREADS) {
         const Real g = -log_(-log_(noise[k]));
         const Real v = add_(logw[k], g);
@@ -675,7 +678,20 @@ template <typename Real> __device__ void ti_partition(const TIDevice<Real> &t, i
 // weights (coalesced) and the pair phase rewrites only the molecules near the old or the new position.
 template <typename Real> __device__ __forceinline__ void bd_seed_after_weights(const BDDevice<Real> &a, int b) {
     Real *row = a.logw_after + static_cast<size_t>(b) * a.M;
-    for (int m = threadIdx.x; m < a.M; m += EX_THREADS) {
+    // eight loads in flight per thread (the two arrays never overlap, which the compiler cannot know)
+    int m = threadIdx.x;
+    for (; m + 7 * EX_THREADS < a.M; m += 8 * EX_THREADS) {
+        Real v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            v[u] = a.logw_before[m + u * EX_THREADS];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            row[m + u * EX_THREADS] = v[u];
+        }
+    }
+    for (; m < a.M; m += EX_THREADS) {
         row[m] = a.logw_before[m];
     }
 }
