@@ -2,6 +2,9 @@
 1000 proposals per move in batches of 250, timemachine/fe/free_energy.py:130-131) for this repo and, when present, the
 compiled reference (oracle/_ref).  Wall clock around the blocking call, median of `reps` after warm-up.
 
+Measurement script (like bench.py's `reference_gpu` leg): the compiled reference is only the thing timed next to this repo,
+nothing under timemachine_b200/ depends on it.
+
     python profiles/bench_exchange.py [n_waters] [proposals] [batch] [reps]
 """
 
