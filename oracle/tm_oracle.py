@@ -779,9 +779,11 @@ def nonbonded_precomputed(x, params, box, pair_idxs, beta, cutoff):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # water exchange by biased deletion (timemachine/md/exchange/exchange_mover.py:64-234) - test oracle for
-# timemachine_b200/csrc/exchange.cu.  PINNING: the per-molecule energies are the interaction-group energies of the
-# oracle above (pinned to the reference's `nonbonded` through tests/golden/nonbonded_*.npz); the rest restates the
-# reference's Python line by line and is cross-checked on the GPU against the compiled reference (tests/test_exchange_gpu.py).
+# timemachine_b200/csrc/exchange.cu.  PINNING: tests/golden/exchange.npz holds outputs of the reference's own Python
+# (make_golden_exchange.py executes nonbonded_block_unsummed per molecule as BDExchangeMove.batch_log_weights does, and
+# get_water_groups / compute_raw_ratio_given_weights / delta_r_np from exchange_mover.py); tests/test_oracle_exchange.py
+# holds the functions below to it at 1e-11.  The rotation is checked against the Hamilton-product definition, and the
+# whole movers are cross-checked on the GPU against the compiled reference (tests/test_exchange_gpu.py).
 def pair_energy_matrix(x, params, box, rows, cols, beta, cutoff):
     """u_ij for i in rows, j in cols (0 outside the cutoff, NaN on a coincident pair), like
     nonbonded_block_unsummed (nonbonded.py:82-150) / k_atom_by_atom_energies (k_nonbonded.cuh:604-700)."""

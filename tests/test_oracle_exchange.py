@@ -76,3 +76,29 @@ def test_mol_energies_are_interaction_group_energies_and_incremental_weights_are
         np.testing.assert_allclose(w1[m], w0[m] + beta * (new - old), rtol=1e-9, atol=1e-9)
     assert O.bd_log_acceptance(w0, w0) == 0.0
     np.testing.assert_allclose(O.logsumexp([1000.0, 1000.0]), 1000.0 + np.log(2.0))
+
+
+def test_exchange_oracle_matches_the_references_own_python():
+    """tests/golden/exchange.npz was written by executing the reference's Python (make_golden_exchange.py):
+    nonbonded_block_unsummed per molecule as BDExchangeMove.batch_log_weights uses it, get_water_groups,
+    compute_raw_ratio_given_weights, delta_r_np.  The oracle's restatements must reproduce it."""
+    from pathlib import Path
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "exchange.npz")
+    x, params, box, mols = g["x"], g["params"], g["box"], g["mols"]
+    beta, cutoff, temperature = float(g["beta"]), float(g["cutoff"]), float(g["temperature"])
+    np.testing.assert_allclose(O.mol_energies(x, params, box, mols, beta, cutoff), g["mol_energy"], rtol=1e-11, atol=1e-10)
+    np.testing.assert_allclose(O.bd_log_weights(x, params, box, mols, beta, cutoff, temperature), g["log_weights"], rtol=1e-11, atol=1e-10)
+    others = np.delete(np.arange(len(x)), mols[4])
+    np.testing.assert_allclose(O.pair_energy_matrix(x, params, box, mols[4], others, beta, cutoff), g["pair_rows_mol4"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(O.delta_r(x[:10], x[10:20], box), g["delta_r"], rtol=0, atol=1e-15)
+    inner, outer = O.water_groups(x, box, g["center"], mols, float(g["radius"]))
+    np.testing.assert_array_equal(inner, g["inner"])
+    np.testing.assert_array_equal(outer, g["outer"])
+    lw, after, moved = g["log_weights"], g["after"], int(g["moved"])
+    vi, vo = float(g["vol_inner"]), float(g["vol_outer"])
+    raw_in = O.tibd_raw_log_probability(lw[outer], after[np.append(inner, moved)], len(outer), len(inner), vo, vi)
+    raw_out = O.tibd_raw_log_probability(lw[inner], after[np.append(outer, inner[0])], len(inner), len(outer), vi, vo)
+    np.testing.assert_allclose([raw_in, raw_out], [g["raw_in"], g["raw_out"]], rtol=1e-13)
+    np.testing.assert_allclose(O.tibd_raw_log_probability(lw[:5], after[:1], 5, 0, 2.0, 3.0), g["raw_empty_dest"], rtol=1e-13)
+    np.testing.assert_allclose(O.tibd_raw_log_probability(lw[:1], after[:4], 1, 3, 2.0, 3.0), g["raw_single_src"], rtol=1e-13)
