@@ -183,3 +183,41 @@ def test_two_state_identity_move_and_context_sampler_contract():
     out, scale = s.sample(H.CoordsVelBox(np.zeros((2, 3)), np.zeros((2, 3)), np.eye(3)), replica_idx=2, state_idx=1, steps_done=5, n_steps=4)
     assert calls == ["x", "v", "box", ("params", [2.0, 3.0]), ("step", (2 << 40) + 5)] and scale is None
     assert out.velocities.shape == (2, 3)
+
+
+def test_context_sampler_drives_the_water_sampler_like_the_reference():
+    """fe/free_energy.py:1497-1528: before a replica is sampled the exchange mover gets the nonbonded parameters of the
+    replica's state and the replica's step count; the proposals / acceptances of the call are recorded per state."""
+    calls = []
+    counts = {"p": 0, "a": 0}
+
+    def run(n):
+        counts["p"] += 1000
+        counts["a"] += 7
+        return np.zeros((1, 2, 3)), np.eye(3)[None]
+
+    mover = types.SimpleNamespace(
+        set_params=lambda p: calls.append(("water_params", np.asarray(p).tolist())), set_step=lambda s: calls.append(("water_step", s)),
+        n_proposed=lambda: counts["p"], n_accepted=lambda: counts["a"],
+    )
+    baro = types.SimpleNamespace(set_step=lambda s: calls.append(("baro_step", s)), get_volume_scale_factor=lambda: 0.5)
+    bp = types.SimpleNamespace(get_potential=lambda: "pot", set_params=lambda p: calls.append(("params", p.tolist())))
+    intg = types.SimpleNamespace(set_step=lambda s: calls.append(("step", s)))
+    ctx = types.SimpleNamespace(
+        get_potentials=lambda: [bp], get_integrator=lambda: intg, get_barostat=lambda: baro, get_movers=lambda: [baro, mover],
+        set_x_t=lambda x: None, set_v_t=lambda v: None, set_box=lambda b: None, multiple_steps=run, get_v_t=lambda: np.ones((2, 3)),
+    )
+    water = np.arange(3 * 2 * 4, dtype=float).reshape(3, 2, 4)
+    s = H.ContextSampler(ctx, np.arange(6.0).reshape(3, 2), water_params_by_state=water)
+    assert s.water_sampler is mover
+    xvb = H.CoordsVelBox(np.zeros((2, 3)), np.zeros((2, 3)), np.eye(3))
+    _, scale = s.sample(xvb, replica_idx=1, state_idx=2, steps_done=800, n_steps=400)
+    assert scale == 0.5
+    assert calls == [
+        ("params", [4.0, 5.0]), ("step", (1 << 40) + 800), ("baro_step", 800), ("water_params", water[2].tolist()), ("water_step", 800),
+    ]
+    s.sample(xvb, replica_idx=0, state_idx=0, steps_done=800, n_steps=400)
+    assert s.water_sampling_counts == {2: (7, 1000), 0: (7, 1000)}
+    with pytest.raises(AssertionError, match="no exchange mover"):
+        ctx2 = types.SimpleNamespace(**{**ctx.__dict__, "get_movers": lambda: [baro]})
+        H.ContextSampler(ctx2, np.arange(6.0).reshape(3, 2), water_params_by_state=water)

@@ -295,7 +295,7 @@ class ContextSampler:
 
     SUBSTREAM_BITS = 40  # noise counter = (replica << 40) + steps taken by that replica: 2^40 steps per replica
 
-    def __init__(self, context, params_by_state):
+    def __init__(self, context, params_by_state, water_params_by_state=None):
         self.context = context
         bps = context.get_potentials()
         assert len(bps) == 1, "HREX expects the whole system in one SummedPotential (fe/free_energy.py:1436-1438)"
@@ -304,6 +304,15 @@ class ContextSampler:
         self.params_by_state = np.ascontiguousarray(params_by_state, dtype=np.float64)
         self.integrator = context.get_integrator()
         self.barostat = context.get_barostat()
+        # water sampling (fe/free_energy.py:1448-1466, 1497-1528): the exchange mover among the context's movers gets the
+        # nonbonded parameters of the state a replica is sampled under, [n_states, N, 4] (get_water_sampler_params)
+        movers = context.get_movers() if hasattr(context, "get_movers") else []
+        self.water_sampler = next((m for m in movers if hasattr(m, "n_proposed") and hasattr(m, "set_params")), None)
+        self.water_params_by_state = None if water_params_by_state is None else np.ascontiguousarray(water_params_by_state, dtype=np.float64)
+        if self.water_params_by_state is not None:
+            assert self.water_sampler is not None, "water parameters given but the context has no exchange mover"
+            assert len(self.water_params_by_state) == len(self.params_by_state)
+        self.water_sampling_counts = {}  # state -> (accepted, proposed) during the most recent sample() under that state
 
     def sample(self, xvb: CoordsVelBox, replica_idx: int, state_idx: int, steps_done: int, n_steps: int):
         ctx = self.context
@@ -314,7 +323,16 @@ class ContextSampler:
         self.integrator.set_step((replica_idx << self.SUBSTREAM_BITS) + steps_done)
         if self.barostat is not None:
             self.barostat.set_step(steps_done)
+        if self.water_sampler is not None:
+            if self.water_params_by_state is not None:
+                self.water_sampler.set_params(self.water_params_by_state[state_idx])
+            self.water_sampler.set_step(steps_done)
+            proposed0, accepted0 = self.water_sampler.n_proposed(), self.water_sampler.n_accepted()
         xs, boxes = ctx.multiple_steps(n_steps)
+        if self.water_sampler is not None:
+            self.water_sampling_counts[state_idx] = (
+                self.water_sampler.n_accepted() - accepted0, self.water_sampler.n_proposed() - proposed0,
+            )
         scale = self.barostat.get_volume_scale_factor() if self.barostat is not None else None
         return CoordsVelBox(xs[-1], ctx.get_v_t(), boxes[-1]), scale
 
