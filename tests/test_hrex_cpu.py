@@ -114,6 +114,8 @@ class ToySampler:
         x = xvb.coords
         for _ in range(n_steps):
             x = x + 0.2 * (self.centers[state_idx] - x) + 0.08 * rng.normal(size=x.shape)
+        # a pretend water sampler: counts keyed like the trajectory, so they cannot depend on the layout either
+        self.water_sampling_counts = {state_idx: (int(rng.integers(0, 5)), 10 * n_steps)}
         return H.CoordsVelBox(x, xvb.velocities + 1.0, xvb.box), None
 
     def energies(self, xvbs, cidx, pidx):
@@ -132,6 +134,7 @@ def _summarise(trajs, diag, hx):
         history=np.array(diag.replica_idx_by_state_by_iter), frac=np.array(diag.fraction_accepted_by_pair_by_iter),
         final=np.array(hx.replica_idx_by_state), frames=np.array([[f for f in t.frames] for t in trajs]),
         boxes=np.array([t.boxes for t in trajs]), vels=np.array([t.final_velocities for t in trajs]),
+        water=diag.water_sampling_diagnostics.proposals_by_state_by_iter,
     )
 
 
@@ -159,6 +162,7 @@ def test_replica_per_rank_layout_equals_sequential(tmp_path, world, n_states):
 
     ref = _summarise(*_toy_run(n_states))  # world_size 1: the reference's sequential algorithm
     assert ref["history"].shape == (12, n_states) and ref["frames"].shape == (n_states, 12, 5, 3)
+    assert ref["water"].shape == (12, n_states, 2) and np.all(ref["water"][1:, :, 1] == 30) and np.all(ref["water"][0, :, 1] == 50)
     assert len({tuple(p) for p in ref["history"]}) > 1, "no swap was ever accepted: the test would prove nothing"
     mp.spawn(_worker, args=(world, _free_port(), n_states, str(tmp_path)), nprocs=world, join=True)
     for rank in range(world):

@@ -206,9 +206,22 @@ def get_samples_by_iter_by_replica(samples_by_state_by_iter, replica_idx_by_stat
 
 
 @dataclass
+class WaterSamplingDiagnostics:
+    """timemachine/md/exchange/exchange_mover.py:55-61: (accepted, proposed) water-exchange moves, [n_iters, n_states, 2]."""
+
+    proposals_by_state_by_iter: np.ndarray
+
+    @property
+    def cumulative_proposals_by_state(self) -> np.ndarray:
+        return np.sum(self.proposals_by_state_by_iter, axis=0)
+
+
+@dataclass
 class HREXDiagnostics:
     replica_idx_by_state_by_iter: list
     fraction_accepted_by_pair_by_iter: list
+    # set when the sampler drives a water-exchange mover (SimulationResult.water_sampling_diagnostics, fe/free_energy.py:320,1615)
+    water_sampling_diagnostics: Optional[WaterSamplingDiagnostics] = None
 
     @property
     def cumulative_swap_acceptance_rates(self) -> np.ndarray:
@@ -415,6 +428,7 @@ def run_sims_hrex(
     box_dirs = [out_dir / f"state_{s}_boxes" for s in range(n_states)]
     for d in box_dirs:
         d.mkdir(parents=True, exist_ok=True)
+    water_dirs = [out_dir / f"state_{s}_water_sampling" for s in range(n_states)]  # created on first use
     replica_idx_by_state_by_iter, fraction_accepted_by_pair_by_iter = [], []
     kT = BOLTZ * temperature
     t_begin = t_last = time.perf_counter()
@@ -431,6 +445,10 @@ def run_sims_hrex(
             # one chunk per (state, iteration), written by whoever sampled it: the reference's StoredArrays layout
             np.save(StoredArrays.get_chunk_path(state_dirs[s], frame), xvb.coords[None])
             np.save(StoredArrays.get_chunk_path(box_dirs[s], frame), xvb.box[None])
+            water_counts = getattr(sampler, "water_sampling_counts", None)
+            if water_counts is not None and s in water_counts:  # (accepted, proposed) of this call (fe/free_energy.py:1521-1528)
+                water_dirs[s].mkdir(parents=True, exist_ok=True)
+                np.save(StoredArrays.get_chunk_path(water_dirs[s], frame), np.asarray(water_counts[s], dtype=np.int32)[None])
             if frame == md_params.n_frames - 1:
                 np.savez(out_dir / f"final_state_{s}.npz", velocities=xvb.velocities, scale=np.nan if scale is None else scale)
         hrex = HREX(local, hrex.replica_idx_by_state)
@@ -473,6 +491,9 @@ def run_sims_hrex(
         scale = float(final["scale"])
         trajectories.append(Trajectory(frames, boxes, final["velocities"], None if np.isnan(scale) else scale))
     diagnostics = HREXDiagnostics(replica_idx_by_state_by_iter, fraction_accepted_by_pair_by_iter)
+    if all(d.is_dir() for d in water_dirs):
+        per_state = [np.array(list(StoredArrays.load(d)), dtype=np.int32) for d in water_dirs]  # [n_iters, 2] each
+        diagnostics.water_sampling_diagnostics = WaterSamplingDiagnostics(np.stack(per_state, axis=1))
     if tmp is not None:
         for t in trajectories:
             t.frames._tmp = tmp  # keep the temporary directory alive as long as any trajectory is
