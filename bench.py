@@ -69,7 +69,11 @@ def build_system(n_waters: int, n_lig: int, seed: int):
     q = rng.normal(0, 0.15, n_lig)
     q -= q.mean()
     params[n_env:, 0] = q * np.sqrt(ONE_4PI_EPS0)
-    params[n_env:, 1] = 0.17
+    # sigma/2 = 0.09 nm: the chain above only keeps non-bonded ligand atoms 0.2 nm apart, so a carbon-sized sigma (0.34 nm)
+    # made the ligand a bundle of LJ clashes (pair forces of 3e4-5e4 kJ/mol/nm between atoms four bonds apart) that the
+    # 2.5 fs integrator survives only by luck: round 1's 4- and 8-window runs died of exactly that ("simulation
+    # unstable" in a window near lambda = 1, same forces from the compiled reference; profiles/r2_summary.md)
+    params[n_env:, 1] = 0.09
     params[n_env:, 2] = np.sqrt(0.4)
     o = np.arange(0, n_env, 3, dtype=np.int32)
     lig_idx = np.arange(n_env, N, dtype=np.int32)
@@ -250,6 +254,7 @@ def cpu_arm(args, s, x0, v0, lam):
     from oracle import build_oracle as OC
     from oracle import tm_oracle as O
 
+    OC.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     params = params_at_lambda(s, lam)
     x = np.ascontiguousarray(x0, dtype=np.float64).copy()
     v = np.ascontiguousarray(v0, dtype=np.float64).copy()
@@ -267,6 +272,7 @@ def cpu_arm(args, s, x0, v0, lam):
 
 
 BAROSTAT_INTERVAL, PRESSURE_BAR = 25, 1.013
+NCU_SUMMARY = "r2_nb_tiles_cq_ncu.json"  # profiles/: dram bytes, L1 data pipe and issue-slot figures of the ncu --set full capture
 
 
 def npt_arm(args, s, ops, impl, flat, x_eq, v_eq, dev, torch):
@@ -400,6 +406,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-npt", action="store_true", help="skip the NPT (barostat) side measurement")
     ap.add_argument("--no-water-sampling", action="store_true", help="skip the water-exchange (TIBD mover) side measurement")
+    ap.add_argument("--single-device", action="store_true",
+                    help="debugging: every rank uses cuda:0 and the collective runs over gloo (reproduces N>1 runs on a 1-GPU box)")
     args = ap.parse_args()
 
     # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner, the
@@ -446,56 +454,38 @@ def main():
     import torch
     import torch.distributed as dist
 
+    if args.single_device:
+        local_rank = 0
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if args.single_device:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from timemachine_b200 import custom_ops as ops
+    from timemachine_b200 import hrex as H
     from timemachine_b200 import potentials as P
-    from timemachine_b200 import replica
 
     dev = torch.device("cuda", local_rank)
-    my_state = rank
+    coll_dev = None if args.single_device else dev  # where the all-gather of the energy rows runs (NCCL: on the GPU)
+    the_dist = dist if world > 1 else None
     pot = make_potential(P, s)
     gpu_impl = pot.to_gpu(np.float32)
     impl = gpu_impl.unbound_impl
     all_pairs_impl = impl.get_potentials()[3].get_potentials()[0]
     flats = [flat_params(s, float(l)) for l in lambdas]
-    x_eq, v_eq = equilibrate(ops, impl, flats[my_state], s, seed=100 + rank)
+    params_by_state = np.stack(flats)
+    x_eq, v_eq = equilibrate(ops, impl, flats[rank], s, seed=100 + rank)
 
-    stream = torch.cuda.Stream(device=dev)
-    bp = ops.BoundPotential(impl, flats[my_state])
-    intg = ops.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 1234 + rank)
+    # One replica (lambda window) per rank, driven by the HREX driver with the reference's interface
+    # (timemachine_b200/hrex.py: run_sims_hrex, reference fe/free_energy.py:1383-1618).
+    bp = ops.BoundPotential(impl, flats[rank])
+    intg = ops.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 1234)
     ctx = ops.Context(x_eq, v_eq, s["box"], intg, [bp])
-    ctx.set_stream(stream.cuda_stream)
-    d_x, d_v, d_box = ctx.device_state()
-    d_params = [torch.from_numpy(f).to(dev) for f in flats]
-    d_u = torch.zeros(2 * max(3, world), dtype=torch.int64, device=dev)  # int128 slots
+    sampler = H.DeviceResidentSampler(ctx, params_by_state, dev)
+    stream = sampler.stream
+    replicas = [H.CoordsVelBox(x_eq, v_eq, s["box"]) if k % world == rank else None for k in range(world)]
     P_total = flats[0].size
-    kT = 0.008314462618 * TEMPERATURE
-    swap_rng = np.random.default_rng(2024)
-    states = np.arange(world)
-
-    def exchange():
-        """Energies of this replica under neighbouring windows' parameters -> all-gather -> deterministic swap."""
-        nonlocal states, my_state
-        mine = int(states[rank])
-        cand = replica.candidate_states(mine, world)
-        for slot, k in enumerate(cand):
-            impl.execute_device(N, P_total, d_x, d_params[k].data_ptr(), d_box, 0, 0, d_u.data_ptr() + 16 * slot, stream.cuda_stream)
-        with torch.cuda.stream(stream):
-            host = d_u[: 2 * len(cand)].cpu().numpy()
-        row = replica.energy_row(
-            world, cand, [replica.i128_to_energy(int(host[2 * i]), int(host[2 * i + 1])) for i in range(len(cand))]
-        )
-        if world > 1:
-            with torch.cuda.stream(stream):
-                u_matrix = replica.all_gather_rows(row, dist, dev)  # NCCL all-gather of K doubles per rank
-            new_states = replica.neighbour_swaps(u_matrix, states, TEMPERATURE, swap_rng)
-            if new_states[rank] != states[rank]:
-                k = int(new_states[rank])
-                bp.set_params_device(d_params[k].data_ptr(), P_total, stream.cuda_stream)
-            states = new_states
-        return row
 
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -504,69 +494,119 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def one_step():
-        ctx.multiple_steps(args.md_steps, args.md_steps + 1)  # device-resident: no frame is copied out
-        return exchange()
-
-    for _ in range(max(args.warmup, 3)):
-        one_step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches_before = ops.kernel_launch_count()
-    rebuilds_before = all_pairs_impl.get_num_rebuilds()
+    warm = max(args.warmup, 3)
+    n_frames = warm + args.steps
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    wall0 = time.perf_counter()
-    torch.cuda.profiler.start()  # `ncu --profile-from-start off python bench.py ...` captures exactly the timed region
-    for i in range(args.steps):
+    clock_sampler = ClockSampler(local_rank)
+    marks = {}
+
+    def begin_frame(i):
         l2_flush.zero_()  # evict L2 between timed iterations (outside the event pair)
         torch.cuda.synchronize(dev)
         starts[i].record(stream)
-        one_step()
-        stops[i].record(stream)
+
+    def on_iteration(frame, U_kl, hx):
+        """Called by the driver when a frame's MD and energy exchange are done, before its swaps are drawn."""
+        if os.environ.get("TMB_BENCH_DEBUG"):
+            xx, vv = ctx.get_x_t(), ctx.get_v_t()
+            ke = 0.5 * float(np.sum(s["masses"][:, None] * vv * vv))
+            sys.stderr.write(
+                f"[dbg rank {rank}] frame {frame} perm={hx.replica_idx_by_state} row={np.array2string(U_kl[rank], precision=1)} "
+                f"x in [{xx.min():.2f}, {xx.max():.2f}] T={2 * ke / (3 * N * 0.008314462618):.1f}\n")
+        if frame >= warm:
+            stops[frame - warm].record(stream)
+        if frame == warm - 1:
+            barrier()
+            clock_sampler.start()
+            marks["launches"] = ops.kernel_launch_count()
+            marks["rebuilds"] = all_pairs_impl.get_num_rebuilds()
+            marks["wall"] = time.perf_counter()
+            torch.cuda.profiler.start()  # `ncu --profile-from-start off python bench.py ...` captures exactly the timed region
+        if warm - 1 <= frame < n_frames - 1:
+            begin_frame(frame + 1 - warm)
+
+    md = H.HREXMDParams(n_frames=n_frames, steps_per_frame=args.md_steps, n_eq_steps=0, seed=2024, max_delta_states=1)
+    _, diag, hx_final = H.run_sims_hrex(
+        sampler, replicas, TEMPERATURE, md, dist=the_dist, device=coll_dev, on_iteration=on_iteration, store_frames=False
+    )
     barrier()
     torch.cuda.profiler.stop()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
-    gpu_launches = ops.kernel_launch_count() - launches_before
-    nblist_rebuilds = all_pairs_impl.get_num_rebuilds() - rebuilds_before
+    wall = time.perf_counter() - marks["wall"]
+    clocks = clock_sampler.stop()
+    gpu_launches = ops.kernel_launch_count() - marks["launches"]
+    nblist_rebuilds = all_pairs_impl.get_num_rebuilds() - marks["rebuilds"]
     total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
-    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device="cpu" if args.single_device else dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     total_ms = float(t_ms.item())
     md_steps_total = args.md_steps * args.steps * world
     ns_day = md_steps_total / (total_ms * 1e-3) * 86400.0 * DT * 1e-3
+    swaps = np.sum(np.array(diag.fraction_accepted_by_pair_by_iter, dtype=float).reshape(n_frames, -1, 2), axis=0) if world > 1 else np.zeros((0, 2))
 
     # ---------------- end-to-end through the public (host-buffer) API ---------------------------------------------------
-    pin = lambda shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()  # noqa: E731
-    hx, hv, hbox = pin((N, 3)), pin((N, 3)), pin((3, 3))
-    hx[:], hv[:], hbox[:] = ctx.get_x_t(), ctx.get_v_t(), ctx.get_box()
-    bound = gpu_impl.bind(flats[int(states[rank])])
+    # The same driver with the reference's own sampler semantics (ContextSampler: the replica's coordinates, velocities,
+    # box and parameters are host arrays loaded into the Context every frame, the frame comes back to the host, U_kl goes
+    # through execute_batch_sparse on host arrays, frames are stored in the reference's StoredArrays layout).
+    import shutil
+    import tempfile
 
-    def e2e_step():
-        ctx.set_x_t(hx)
-        ctx.set_v_t(hv)
-        ctx.set_box(hbox)
-        xs, boxes = ctx.multiple_steps(args.md_steps)  # returns the last frame on the host
-        hx[:], hbox[:] = xs[-1], boxes[-1]
-        hv[:] = ctx.get_v_t()
-        return bound.bound_impl.execute(hx, hbox, compute_du_dx=False, compute_u=True)[1]
+    out_dir = [tempfile.mkdtemp(prefix="tmb_bench_e2e_") if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(out_dir, src=0)
+    last = hx_final.replicas[rank]
+    e2e_replicas = [H.CoordsVelBox(np.array(last.coords), np.array(last.velocities), np.array(last.box)) if k % world == rank else None
+                    for k in range(world)]
+    ctx.set_stream(0)
+    host_sampler = H.ContextSampler(ctx, params_by_state)
+    if os.environ.get("TMB_BENCH_DEBUG"):  # where an end-to-end frame goes
+        acc = {}
 
-    e2e_step()
+        def timed(obj, name):
+            fn = getattr(obj, name)
+
+            def wrapper(*a, **k):
+                t0 = time.perf_counter()
+                r = fn(*a, **k)
+                acc[name] = acc.get(name, 0.0) + time.perf_counter() - t0
+                return r
+
+            setattr(obj, name, wrapper)
+
+        timed(host_sampler, "sample")
+        timed(host_sampler, "energies")
+        for nm in ("set_x_t", "set_v_t", "set_box", "multiple_steps", "get_v_t"):
+            timed(ctx, nm)
+        timed(host_sampler.bound, "set_params")
+        timed(np, "save")
+    e2e_marks = {}
+
+    def on_iteration_e2e(frame, U_kl, hx):
+        if frame == 0:  # frame 0 is the warm-up of this path
+            barrier()
+            e2e_marks["t0"] = time.perf_counter()
+
+    md_e2e = H.HREXMDParams(n_frames=args.steps + 1, steps_per_frame=args.md_steps, n_eq_steps=0, seed=4048, max_delta_states=1)
+    H.run_sims_hrex(
+        host_sampler, e2e_replicas, TEMPERATURE, md_e2e, out_dir=out_dir[0], dist=the_dist, device=coll_dev,
+        on_iteration=on_iteration_e2e, replica_idx_by_state=list(hx_final.replica_idx_by_state),
+    )
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_s = time.perf_counter() - e2e_marks["t0"]
+    if os.environ.get("TMB_BENCH_DEBUG"):
+        sys.stderr.write(f"[dbg rank {rank}] e2e {e2e_s:.3f} s over {args.steps} frames; seconds by call (all {args.steps + 1} frames): "
+                         + ", ".join(f"{k}={v:.3f}" for k, v in sorted(acc.items())) + "\n")
+    if rank == 0:
+        shutil.rmtree(out_dir[0], ignore_errors=True)
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cpu" if args.single_device else dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_ns_day = md_steps_total / float(t_e2e.item()) * 86400.0 * DT * 1e-3
-    h2d = 2 * N * 3 * 8 + 72 + (N * 3 * 8 + 72)  # x, v, box for the MD call + x, box for the energy call
-    d2h = 2 * N * 3 * 8 + 72 + 16
+    n_cand = 3 if world > 2 else world
+    # per frame and replica: x, v, box, parameters in for the MD call; x, box, all K parameter sets in for the U_kl row
+    h2d = (2 * N * 3 * 8 + 72 + P_total * 8) + (N * 3 * 8 + 72 + world * P_total * 8)
+    d2h = (2 * N * 3 * 8 + 72) + 16 * n_cand
 
     # ---------------- roofline of the dominant kernel (k_nb_tiles of NonbondedAllPairs), rank 0 ----------------------------
     roofline = None
@@ -587,22 +627,42 @@ def main():
             except Exception:
                 pass
         achieved = algo_bytes / t_kernel / 1e9
-        traffic, traffic_src = None, None
-        traffic_file = ROOT / "profiles" / "r1s2_nb_tiles_cq_traffic.json"
-        if traffic_file.exists():  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per launch
+        # what only a profiler can see comes from the committed ncu capture of this same kernel on this same system
+        ncu = {}
+        ncu_file = ROOT / "profiles" / NCU_SUMMARY
+        if ncu_file.exists():
             try:
-                tj = json.loads(traffic_file.read_text())
-                traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
-                traffic_src = tj["source"]
+                ncu = json.loads(ncu_file.read_text())
             except Exception:
-                pass
-        pair_slots = 1024.0 * T
+                ncu = {}
+        traffic = (float(ncu["dram_bytes_read"]) + float(ncu["dram_bytes_write"])) if "dram_bytes_read" in ncu else None
+        # flops_nb = 1024 T * 22 (distance + PBC + cutoff test per slot) + pairs_in_cutoff * 95
+        try:
+            from scipy.spatial import cKDTree
+
+            L = float(s["box"][0, 0])
+            xe = np.mod(ctx.get_x_t()[: s["n_env"]], L)
+            xe[xe >= L] = 0.0
+            pairs_in_cutoff = int(cKDTree(xe, boxsize=L).count_neighbors(cKDTree(xe, boxsize=L), CUTOFF) - s["n_env"]) // 2
+        except Exception:
+            pairs_in_cutoff = int(361 * s["n_env"])
+        flops_nb = 1024.0 * T * 22.0 + pairs_in_cutoff * 95.0
+        sm_mhz = clocks.get("sm_max_mhz") or 1965.0
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s: 148 SMs x 128 FP32 lanes x 2 (FMA) x SM clock
         roofline = {
-            "kernel": "k_nb_tiles_cq<U=0,X=1,P=0> (NonbondedAllPairs, env-env)", "bound": "hbm", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_us": t_kernel * 1e6,
+            "kernel": "k_nb_tiles_cq<U=0,X=1,P=0> (NonbondedAllPairs, env-env)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": ncu.get("source"), "peak_source": peak_src, "kernel_us": t_kernel * 1e6,
             "launches_timed": int(len(times_ms)), "tiles": int(T), "algorithmic_bytes": algo_bytes,
-            "pair_slots_per_s": pair_slots / t_kernel,
-            "note": "the working set (tile list + 32 B/atom) is L2-resident, DRAM sees it about once per launch (54 GB/s); the kernel is bound by the L1 data pipe (shared-memory atomics of the fixed-point accumulation: ncu 81 % of peak) together with instruction issue (72 %), see DESIGN.md and profiles/r1_summary.md",
+            "measured_bound": "l1_data_pipe (shared-memory atomics of the fixed-point accumulation), instruction issue second",
+            "l1_pipe_pct": ncu.get("l1_data_pipe_lsu_wavefronts_pct"), "issue_slots_pct": ncu.get("issue_slots_busy_pct"),
+            "pairs_in_cutoff": pairs_in_cutoff, "flops": flops_nb, "fp32_tflops": flops_nb / t_kernel / 1e12,
+            "fp32_peak_tflops": fp32_peak, "fp32_frac": flops_nb / t_kernel / 1e12 / fp32_peak,
+            "fp32_peak_source": f"148 SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz (scalar FP32, no tensor cores on this path)",
+            "pair_slots_per_s": 1024.0 * T / t_kernel,
+            "note": "`bound`/`frac` are the HBM roofline north_star asks for; the kernel is not HBM-bound: its working set (tile "
+                    "list + 32 B/atom) is L2-resident and DRAM sees it about once per launch.  What limits it is in "
+                    "measured_bound / l1_pipe_pct / issue_slots_pct (ncu --set full, profiles/) and fp32_frac",
         }
 
     # ---------------- baselines on rank 0 ----------------------------------------------------------------------------------
@@ -610,7 +670,7 @@ def main():
     ref_gpu = None
     if rank == 0 and world == 1:
         if not args.no_cpu_baseline:
-            cns, cdt, threads, n = cpu_arm(args, s, x_eq, v_eq, float(lambdas[my_state]))
+            cns, cdt, threads, n = cpu_arm(args, s, x_eq, v_eq, float(lambdas[rank]))
             cpu_baseline = {
                 "value": cns, "unit": "ns/day", "cores": threads, "kind": "port",
                 "sample": f"{n} full MD steps of the same {N}-atom system with oracle/tm_oracle_c.c (C/OpenMP restatement of the "
@@ -624,7 +684,7 @@ def main():
                 if ref is not None:
                     with stdout_to_stderr():
                         rimpl = make_reference_potential(ref, s)
-                        rbp = ref.BoundPotential(rimpl, flats[my_state])
+                        rbp = ref.BoundPotential(rimpl, flats[rank])
                         rintg = ref.LangevinIntegrator(s["masses"], TEMPERATURE, DT, FRICTION, 1234)
                         rctx = ref.Context(x_eq, v_eq, s["box"], rintg, [rbp])
                         rctx.multiple_steps(args.md_steps, args.md_steps + 1)
@@ -643,17 +703,20 @@ def main():
     # ---------------- NPT variant of the same leg: + MonteCarloBarostat every 25 steps ----------------
     npt = None
     if rank == 0 and world == 1 and not args.no_npt:
-        npt = npt_arm(args, s, ops, impl, flats[my_state], x_eq, v_eq, dev, torch)
+        npt = npt_arm(args, s, ops, impl, flats[rank], x_eq, v_eq, dev, torch)
     water_sampling = None
     if rank == 0 and world == 1 and not args.no_water_sampling:
-        water_sampling = water_sampling_arm(args, s, ops, impl, flats[my_state], float(lambdas[my_state]), x_eq, v_eq, dev, torch)
+        water_sampling = water_sampling_arm(args, s, ops, impl, flats[rank], float(lambdas[rank]), x_eq, v_eq, dev, torch)
 
     if rank == 0:
         out = {
             "metric": "ns_per_day", "value": ns_day, "unit": "ns/day", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(workload, l2="256 MiB buffer rewritten between timed steps; MD state itself is carried step to step",
-                                                timing="CUDA events on the MD stream per bench step, summed; max over ranks"),
+            "data": "synthetic", "config": workload,
+            "method": {"l2": "256 MiB buffer rewritten between timed steps; MD state itself is carried step to step",
+                       "timing": "CUDA events on the MD stream around every bench step (frame), summed; max over ranks",
+                       "driver": "timemachine_b200.hrex.run_sims_hrex: DeviceResidentSampler for `value`, ContextSampler (host buffers, frames stored) for `e2e`"},
+            "hrex_swaps_accepted_proposed": swaps.tolist(),
             "clocks": clocks, "gpu_launches": int(gpu_launches), "nblist_rebuilds": int(nblist_rebuilds), "md_steps_timed": int(args.md_steps * args.steps), "wall_s": wall,
             "e2e": {"value": e2e_ns_day, "unit": "ns/day", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": ref_gpu, "npt": npt, "water_sampling": water_sampling,
@@ -666,4 +729,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')}] FAILED\n{traceback.format_exc()}\n")
+        sys.stderr.flush()
+        raise

@@ -310,6 +310,16 @@ int tmb_hilbert_sort_create(int size, tmb_hilbert_sort *out);
 int tmb_hilbert_sort_destroy(tmb_hilbert_sort hs);
 int tmb_hilbert_sort_sort(tmb_hilbert_sort hs, int N, const double *coords, const double *box, uint32_t *perm);
 
+/* ---- HREX host loop: a batch of neighbour-swap attempts, `_run_neighbor_swaps` of timemachine/md/hrex.py:50-129 --------
+ * (a jitted lax.scan there).  Attempt i takes the state pair neighbor_pairs[pair_idxs[i]] = (s_a, s_b) held by replicas
+ * (r_a, r_b) and is accepted iff uniform_samples[i] < exp(min(log_q[r_a,s_b] + log_q[r_b,s_a] - log_q[r_a,s_a] -
+ * log_q[r_b,s_b], 0)); NaN differences reject.  replica_idx_by_state[n_states] is updated in place; proposed / accepted
+ * [n_pairs] are overwritten.  Host only: runs without a GPU.  Every rank calls it on the all-gathered matrix. */
+int tmb_hrex_run_neighbor_swaps(
+    int n_states, int n_replicas, int n_pairs, const int32_t *neighbor_pairs, const double *log_q_kl, int n_attempts,
+    const int32_t *pair_idxs, const double *uniform_samples, int32_t *replica_idx_by_state, uint32_t *proposed,
+    uint32_t *accepted);
+
 /* ---- test utilities ---------------------------------------------------------------------------------------------- */
 /* N x 3 standard normals from the integrator's Philox stream for (seed, step) */
 int tmb_fill_normal(float *out, int n_atoms, uint64_t seed, uint64_t step);

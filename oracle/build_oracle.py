@@ -39,6 +39,8 @@ def lib() -> C.CDLL:
         _lib.tmo_baoab.restype = None
         _lib.tmo_baoab.argtypes = [C.c_int, d, d, d, C.c_double, d, d, C.c_double, d]
         _lib.tmo_num_threads.restype = C.c_int
+        _lib.tmo_set_num_threads.restype = None
+        _lib.tmo_set_num_threads.argtypes = [C.c_int]
     return _lib
 
 
@@ -54,6 +56,11 @@ def _i(a):
 
 def num_threads() -> int:
     return int(lib().tmo_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """omp_set_num_threads: overrides an inherited OMP_NUM_THREADS (torchrun sets it to 1 for its workers)."""
+    lib().tmo_set_num_threads(int(n))
 
 
 def nonbonded_block(x, params, box, rows, cols, beta, cutoff, triangular, want_dx=True, want_dp=False):

@@ -286,6 +286,17 @@ void tmo_baoab(int N, double *x, double *v, const double *du_dx, double ca, cons
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline asks for all host cores explicitly. */
+void tmo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) {
+        omp_set_num_threads(n);
+    }
+#else
+    (void)n;
+#endif
+}
+
 int tmo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

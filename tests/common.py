@@ -18,6 +18,12 @@ def load_reference_ops():
     d = ROOT / "oracle" / "_ref"
     cands = sorted(d.glob("custom_ops*.so"))
     if not cands:
+        import os
+
+        if os.environ.get("TMB_REQUIRE_REF") == "1":
+            # the GPU-box runs set this: oracle/_ref travels with the snapshot, and a missing reference must not silently
+            # turn the bitwise parity tests into skips
+            raise RuntimeError("TMB_REQUIRE_REF=1 but oracle/_ref/custom_ops*.so is not built (make -C oracle/ref_build)")
         return None
     name = "tm_reference_custom_ops"
     if name in sys.modules:
@@ -27,6 +33,21 @@ def load_reference_ops():
     spec.loader.exec_module(mod)
     sys.modules[name] = mod
     return mod
+
+
+def require_reference_ops():
+    """The compiled reference, or a skip - a hard failure when TMB_REQUIRE_REF=1 (set for the GPU-box runs, where
+    oracle/_ref travels with the snapshot: a missing reference must not silently drop the bitwise parity tests)."""
+    import os
+
+    import pytest
+
+    ref = load_reference_ops()
+    if ref is None:
+        if os.environ.get("TMB_REQUIRE_REF") == "1":
+            pytest.fail("TMB_REQUIRE_REF=1 but oracle/_ref/custom_ops*.so is not built (make -C oracle/ref_build)")
+        pytest.skip("oracle/_ref/custom_ops*.so not built")
+    return ref
 
 
 def assert_forces_close(ref, test, rtol, what="forces"):

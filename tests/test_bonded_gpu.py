@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import tm_oracle as O
-from tests.common import assert_forces_close, load_reference_ops, round_to_f32
+from tests.common import assert_forces_close, require_reference_ops, round_to_f32
 
 pytestmark = pytest.mark.gpu
 
@@ -134,9 +134,7 @@ def test_bonded_validation_messages():
 
 @pytest.mark.parametrize("precision,rtol", [(np.float32, 1e-5), (np.float64, 1e-10)])
 def test_bonded_against_reference_custom_ops(precision, rtol, rng):
-    ref = load_reference_ops()
-    if ref is None:
-        pytest.skip("oracle/_ref/custom_ops*.so not built")
+    ref = require_reference_ops()
     suffix = "f32" if precision == np.float32 else "f64"
     n = 200
     x, box = chain(rng, n)
@@ -156,3 +154,38 @@ def test_bonded_against_reference_custom_ops(precision, rtol, rng):
         assert_forces_close(rdx, dx, rtol, what=name)
         np.testing.assert_allclose(dp, rdp, rtol=rtol * 10, atol=rtol * 10 * max(1.0, np.abs(rdp).max()))
         np.testing.assert_allclose(u, ru, rtol=rtol * 10)
+
+
+@pytest.mark.parametrize("precision", [np.float32, np.float64])
+def test_bonded_far_from_the_origin(precision, rng):
+    """Coordinates are never wrapped into the box, atoms drift nanometres away from the origin.  The reference forms
+    x_i - x_j in double and rounds the DIFFERENCE to the kernel's type (k_harmonic_bond.cuh:26, k_harmonic_angle.cuh:43-44,
+    k_periodic_torsion.cuh:48-50): the f32 kernels keep ~1e-8 nm on a bond vector wherever the molecule sits.  Rounding the
+    coordinates first would lose ~1e-6 nm at 10 nm, a 1e-3 relative error on a stiff bond.  Checked against the f64 oracle
+    and, on f64-only-representable coordinates, bitwise against the compiled reference."""
+    n = 200
+    x, box = chain(rng, n)
+    x = x + np.array([11.3, -9.7, 10.1])  # NOT rounded to f32: the low bits of the doubles matter here
+    cases = [
+        ("HarmonicBond", O.harmonic_bond, np.array([(i, i + 1) for i in range(n - 1)], dtype=np.int32),
+         np.stack([np.full(n - 1, 462750.4), np.linalg.norm(x[1:] - x[:-1], axis=1) + rng.normal(0, 0.003, n - 1)], 1)),
+        ("HarmonicAngle", O.harmonic_angle, np.array([(i, i + 1, i + 2) for i in range(n - 2)], dtype=np.int32),
+         np.stack([rng.uniform(50, 800, n - 2), rng.uniform(0.8, 3.0, n - 2), np.full(n - 2, 0.01)], 1)),
+        ("PeriodicTorsion", O.periodic_torsion, np.array([(i, i + 1, i + 2, i + 3) for i in range(n - 3)], dtype=np.int32),
+         np.stack([rng.uniform(0.5, 30, n - 3), rng.uniform(-3, 3, n - 3), rng.integers(1, 7, n - 3).astype(float)], 1)),
+    ]
+    suffix = "f32" if precision == np.float32 else "f64"
+    from tests.common import load_reference_ops
+
+    ref = load_reference_ops()
+    for name, oracle_fn, idxs, params in cases:
+        params = round_to_f32(params)
+        dx, dp, u = getattr(ops(), f"{name}_{suffix}")(idxs).execute(x, params, box)
+        _, odx, _ = oracle_fn(x, params, idxs)
+        # stiff bonds: |r - b0| ~ 3e-3 nm, so a 1e-6 nm error in the bond vector would show up as 3e-4 here
+        # f32 arithmetic on an exact bond vector: ~3e-5 of the force on these stiff bonds (sqrt and the r - b0 difference)
+        assert_forces_close(odx, dx, 1e-4 if precision == np.float32 else 1e-9, what=name + " vs f64 oracle, offset 10 nm")
+        if ref is not None:
+            rdx, rdp, ru = getattr(ref, f"{name}_{suffix}")(idxs).execute(x, params, box)
+            assert_forces_close(rdx, dx, 1e-5 if precision == np.float32 else 1e-10, what=name + " vs compiled reference, offset 10 nm")
+            np.testing.assert_allclose(u, ru, rtol=1e-4 if precision == np.float32 else 1e-9)

@@ -220,6 +220,14 @@ def test_context_sampler_drives_the_water_sampler_like_the_reference():
     assert calls == [
         ("params", [4.0, 5.0]), ("step", (1 << 40) + 800), ("baro_step", 800), ("water_params", water[2].tolist()), ("water_step", 800),
     ]
+    # the movers count frames like the reference (current_frame * steps_per_frame), the noise stream counts every step
+    calls.clear()
+    s.sample(xvb, replica_idx=1, state_idx=2, steps_done=1000, n_steps=400, mover_step=800)
+    assert calls == [
+        ("params", [4.0, 5.0]), ("step", (1 << 40) + 1000), ("baro_step", 800), ("water_params", water[2].tolist()), ("water_step", 800),
+    ]
+    counts["p"] -= 1000
+    counts["a"] -= 7
     s.sample(xvb, replica_idx=0, state_idx=0, steps_done=800, n_steps=400)
     assert s.water_sampling_counts == {2: (7, 1000), 0: (7, 1000)}
     with pytest.raises(AssertionError, match="no exchange mover"):

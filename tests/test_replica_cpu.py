@@ -98,3 +98,33 @@ def test_run_neighbor_swaps_matches_reference_golden():
     np.testing.assert_array_equal(accepted, g["accepted"])
     assert sorted(final.tolist()) == list(range(len(final)))  # still a permutation
     assert proposed.sum() == len(g["pair_idxs"]) and 0 < accepted.sum() < proposed.sum()
+
+
+def test_native_neighbor_swap_loop_equals_the_python_statement():
+    """`tmb_hrex_run_neighbor_swaps` (C ABI, host code) against `replica.run_neighbor_swaps` (the restatement of the
+    reference's `_run_neighbor_swaps`, md/hrex.py:50-129, pinned by tests/golden/hrex_driver.npz): identical permutations
+    and counters, including +inf (not evaluated), -inf and NaN entries of log_q."""
+    from timemachine_b200 import replica as R
+
+    rng = np.random.default_rng(5)
+    for n_states, n_attempts in ((2, 8), (4, 64), (8, 512), (11, 1331)):
+        pairs = [(s, s + 1) for s in range(n_states - 1)]
+        if n_states == 2:
+            pairs = [(0, 0), *pairs]
+        for trial in range(6):
+            log_q = rng.normal(0, 3.0, (n_states, n_states))
+            if trial >= 2:
+                log_q[rng.random(log_q.shape) < 0.3] = -np.inf  # energies of +inf: states that were not evaluated
+            if trial >= 4:
+                log_q[rng.random(log_q.shape) < 0.1] = np.nan
+                log_q[rng.random(log_q.shape) < 0.1] = np.inf
+            perm0 = rng.permutation(n_states)
+            pidx = rng.integers(0, len(pairs), n_attempts)
+            us = rng.random(n_attempts)
+            with np.errstate(invalid="ignore"):
+                a = R.run_neighbor_swaps(perm0, pairs, log_q, pidx, us)
+            b = R.run_neighbor_swaps_native(perm0, pairs, log_q, pidx, us)
+            for x, y in zip(a, b):
+                np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+    with pytest.raises(RuntimeError, match="outside"):
+        R.run_neighbor_swaps_native([0, 1], [(0, 5)], np.zeros((2, 2)), [0], [0.5])

@@ -154,6 +154,7 @@ SIGNATURES = {
     "tmb_hilbert_sort_destroy": [_h],
     "tmb_hilbert_sort_sort": [_h, _int, _p_f64, _p_f64, _p_u32],
     "tmb_fill_normal": [_p_f32, _int, C.c_uint64, C.c_uint64],
+    "tmb_hrex_run_neighbor_swaps": [_int, _int, _int, _p_i32, _p_f64, _int, _p_i32, _p_f64, _p_i32, _p_u32, _p_u32],
     # non-status functions
     "tmb_last_error": [],
     "tmb_version": [],

@@ -307,6 +307,10 @@ MonteCarloBarostat<Real>::MonteCarloBarostat(
     d_counters_.realloc(2);
     d_u_init_.realloc(std::max<size_t>(1, bps_.size()));
     d_u_final_.realloc(std::max<size_t>(1, bps_.size()));
+    // a potential with nothing to evaluate (no terms, empty pair list, empty interaction group) returns without writing its
+    // energy slot, and k_barostat_decide sums every slot: they must read as zero, not as whatever cudaMalloc handed out
+    d_u_init_.zero();
+    d_u_final_.zero();
     d_volume_.realloc(2);
     d_volume_scale_.realloc(1);
     d_volume_scale_.copy_from(&initial_volume_scale_factor);

@@ -1127,4 +1127,46 @@ int tmb_fill_normal(float *out, int n_atoms, uint64_t seed, uint64_t step) {
     });
 }
 
+// ---- HREX host loop (reference timemachine/md/hrex.py:50-129, `_run_neighbor_swaps`) ---------------------------------
+int tmb_hrex_run_neighbor_swaps(
+    int n_states, int n_replicas, int n_pairs, const int32_t *neighbor_pairs, const double *log_q_kl, int n_attempts,
+    const int32_t *pair_idxs, const double *uniform_samples, int32_t *replica_idx_by_state, uint32_t *proposed,
+    uint32_t *accepted) {
+    return guarded([&] {
+        for (int p = 0; p < n_pairs; p++) {
+            proposed[p] = 0;
+            accepted[p] = 0;
+            for (int k = 0; k < 2; k++) {
+                const int s = neighbor_pairs[p * 2 + k];
+                if (s < 0 || s >= n_states) {
+                    throw std::runtime_error("neighbor_pairs holds a state outside [0, n_states)");
+                }
+            }
+        }
+        for (int s = 0; s < n_states; s++) {
+            if (replica_idx_by_state[s] < 0 || replica_idx_by_state[s] >= n_replicas) {
+                throw std::runtime_error("replica_idx_by_state holds a replica outside [0, n_replicas)");
+            }
+        }
+        for (int i = 0; i < n_attempts; i++) {
+            const int p = pair_idxs[i];
+            if (p < 0 || p >= n_pairs) {
+                throw std::runtime_error("pair_idxs holds an index outside [0, n_pairs)");
+            }
+            const int s_a = neighbor_pairs[p * 2 + 0], s_b = neighbor_pairs[p * 2 + 1];
+            proposed[p] += 1;
+            const int r_a = replica_idx_by_state[s_a], r_b = replica_idx_by_state[s_b];
+            const double *qa = log_q_kl + static_cast<size_t>(r_a) * n_states;
+            const double *qb = log_q_kl + static_cast<size_t>(r_b) * n_states;
+            const double diff = (qa[s_b] + qb[s_a]) - (qa[s_a] + qb[s_b]);
+            const double m = (0.0 < diff) ? 0.0 : diff; // min(diff, 0) that lets NaN through, like jnp.minimum
+            if (uniform_samples[i] < std::exp(m)) {
+                replica_idx_by_state[s_a] = r_b;
+                replica_idx_by_state[s_b] = r_a;
+                accepted[p] += 1;
+            }
+        }
+    });
+}
+
 } // extern "C"

@@ -51,6 +51,12 @@ inline void cuda_check(cudaError_t code, const char *what, const char *file, int
 // Count of kernels this library has launched (bench.py reports it as gpu_launches).
 extern std::atomic<long long> g_kernel_launches;
 
+// Bumped by every host-side mutation that changes what a step ENQUEUES (kernel arguments, grid sizes, buffer addresses):
+// set_atom_idxs, a BoundPotential changing its parameter count, the integrator's noise source, kernel-timing hooks.  A
+// Context remembers the value its CUDA graph was captured under and re-captures when it has moved (context.cu).
+extern std::atomic<long long> g_launch_generation;
+inline void bump_launch_generation() { g_launch_generation.fetch_add(1, std::memory_order_relaxed); }
+
 #define TMB_LAUNCH(kernel, grid, block, smem, stream, ...)                                                             \
     do {                                                                                                               \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                                    \

@@ -34,6 +34,7 @@ LangevinIntegrator::LangevinIntegrator(int N, const double *masses, double tempe
 }
 
 void LangevinIntegrator::set_external_noise(const float *h_noise) {
+    bump_launch_generation(); // the noise pointer (or its absence) is an argument of the captured k_baoab launches
     if (h_noise == nullptr) {
         external_noise_ = false;
         return;
@@ -136,26 +137,44 @@ void Context::run_steps(int n, cudaStream_t stream) {
         }
         if (use_graphs_ && cap >= GRAPH_STEPS && remaining >= GRAPH_STEPS) {
             intg_->publish_step_base(stream);
-            if (graph_exec_ == nullptr || graph_stream_ != stream) {
+            const long long generation = g_launch_generation.load();
+            if (graph_exec_ == nullptr || graph_stream_ != stream || graph_generation_ != generation) {
                 destroy_graph();
                 cudaGraph_t graph = nullptr;
                 const long long launches_before = g_kernel_launches.load();
+                const long long intg_step_before = intg_->step_count();
                 TMB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+                int captured = 0;
                 try {
                     for (int s = 0; s < GRAPH_STEPS; s++) {
                         intg_->step_fwd(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream, s);
+                        captured++;
                     }
+                    TMB_CUDA(cudaStreamEndCapture(stream, &graph));
+                    TMB_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
                 } catch (...) {
-                    cudaStreamEndCapture(stream, &graph);
-                    if (graph) {
+                    // nothing ran: end the capture (it is invalid if a forked stream was left un-joined), put the host-side
+                    // cadence counters back where they were so that the context stays in step with the device
+                    cudaGraph_t dead = nullptr;
+                    cudaStreamEndCapture(stream, &dead);
+                    if (dead) {
+                        cudaGraphDestroy(dead);
+                    }
+                    if (graph && graph != dead) {
                         cudaGraphDestroy(graph);
                     }
+                    cudaGetLastError();
+                    graph_exec_ = nullptr;
+                    for (auto &bp : bps_) {
+                        bp->potential->advance(-captured);
+                    }
+                    intg_->set_step(intg_step_before);
+                    g_kernel_launches.store(launches_before);
                     throw;
                 }
-                TMB_CUDA(cudaStreamEndCapture(stream, &graph));
-                TMB_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
                 TMB_CUDA(cudaGraphDestroy(graph));
                 graph_stream_ = stream;
+                graph_generation_ = generation;
                 // the capture pass already advanced the host-side counters of the potentials and the integrator, and
                 // counted its kernels once (they run on the first launch below)
                 graph_kernels_ = g_kernel_launches.load() - launches_before;

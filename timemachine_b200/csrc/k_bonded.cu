@@ -21,15 +21,16 @@ template <typename Real> struct V3 {
     Real x, y, z;
 };
 
-template <typename Real> __device__ __forceinline__ V3<Real> load3(const double *__restrict__ x, int idx) {
+// x[a] - x[b]: the difference is formed in double and THEN rounded to Real, as the reference's bonded kernels do
+// (`RealType delta = coords[src * 3 + d] - coords[dst * 3 + d]`, k_harmonic_bond.cuh:26, k_harmonic_angle.cuh:43-44,
+// k_periodic_torsion.cuh:48-50).  Rounding each coordinate first would cost ~ulp(|x|) ~ 1e-6 nm at 8 nm from the origin
+// (coordinates are not wrapped into the box) - 100x the reference's error on a stiff bond - and translation invariance.
+template <typename Real> __device__ __forceinline__ V3<Real> delta3(const double *__restrict__ x, int a, int b) {
     V3<Real> r;
-    r.x = static_cast<Real>(x[idx * 3 + 0]);
-    r.y = static_cast<Real>(x[idx * 3 + 1]);
-    r.z = static_cast<Real>(x[idx * 3 + 2]);
+    r.x = static_cast<Real>(x[a * 3 + 0] - x[b * 3 + 0]);
+    r.y = static_cast<Real>(x[a * 3 + 1] - x[b * 3 + 1]);
+    r.z = static_cast<Real>(x[a * 3 + 2] - x[b * 3 + 2]);
     return r;
-}
-template <typename Real> __device__ __forceinline__ V3<Real> sub3(const V3<Real> &a, const V3<Real> &b) {
-    return {a.x - b.x, a.y - b.y, a.z - b.z};
 }
 template <typename Real> __device__ __forceinline__ Real dot3(const V3<Real> &a, const V3<Real> &b) {
     return a.x * b.x + a.y * b.y + a.z * b.z;
@@ -50,7 +51,7 @@ template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_harmoni
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.n_terms; b += gridDim.x * blockDim.x) {
         const int src = a.idxs[b * 2 + 0];
         const int dst = a.idxs[b * 2 + 1];
-        const V3<Real> d = sub3(load3<Real>(a.x, src), load3<Real>(a.x, dst));
+        const V3<Real> d = delta3<Real>(a.x, src, dst);
         const Real kb = static_cast<Real>(a.p[b * 2 + 0]);
         const Real b0 = static_cast<Real>(a.p[b * 2 + 1]);
         const Real r = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
@@ -91,9 +92,8 @@ template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_harmoni
         const Real a0 = static_cast<Real>(a.p[t * 3 + 1]);
         const Real eps = static_cast<Real>(a.p[t * 3 + 2]);
 
-        const V3<Real> xj = load3<Real>(a.x, j);
-        const V3<Real> vji = sub3(load3<Real>(a.x, i), xj);
-        const V3<Real> vjk = sub3(load3<Real>(a.x, k), xj);
+        const V3<Real> vji = delta3<Real>(a.x, i, j);
+        const V3<Real> vjk = delta3<Real>(a.x, k, j);
         const Real rji[4] = {vji.x, vji.y, vji.z, eps};
         const Real rjk[4] = {vjk.x, vjk.y, vjk.z, eps};
         Real sji = 0, sjk = 0;
@@ -178,10 +178,9 @@ template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_periodi
         const int j = a.idxs[t * 4 + 1];
         const int k = a.idxs[t * 4 + 2];
         const int l = a.idxs[t * 4 + 3];
-        const V3<Real> xi = load3<Real>(a.x, i), xj = load3<Real>(a.x, j), xk = load3<Real>(a.x, k), xl = load3<Real>(a.x, l);
-        const V3<Real> rij = sub3(xj, xi);
-        V3<Real> rkj = sub3(xj, xk);
-        const V3<Real> rkl = sub3(xl, xk);
+        const V3<Real> rij = delta3<Real>(a.x, j, i);
+        V3<Real> rkj = delta3<Real>(a.x, j, k);
+        const V3<Real> rkl = delta3<Real>(a.x, l, k);
 
         const Real rkj2 = dot3(rkj, rkj);
         const Real rkj_n = sqrt(rkj2);

@@ -91,6 +91,7 @@ template <typename Real> void NonbondedTiled<Real>::set_kernel_timing(bool on) {
     }
     timing_ = on;
     timing_used_ = 0;
+    bump_launch_generation();
 }
 
 template <typename Real> std::vector<float> NonbondedTiled<Real>::drain_kernel_times() {
@@ -246,6 +247,7 @@ template <typename Real> void NonbondedAllPairs<Real>::set_atom_idxs(const std::
     this->nblist_.set_all_pairs(this->K_);
     this->steps_since_last_sort_ = 0; // forces a sort, hence a rebuild, on the next evaluation
     this->force_rebuild_ = true;
+    bump_launch_generation(); // K_, NR_ and the grid sizes are baked into captured launches
 }
 
 template <typename Real> std::vector<int> NonbondedAllPairs<Real>::get_atom_idxs() {
@@ -341,6 +343,7 @@ void NonbondedInteractionGroup<Real>::set_atom_idxs(const std::vector<int> &row_
     this->K_ = NR + NC;
     this->steps_since_last_sort_ = 0;
     this->force_rebuild_ = true;
+    bump_launch_generation();
 }
 
 template <typename Real>

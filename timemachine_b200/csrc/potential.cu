@@ -9,6 +9,7 @@
 namespace tmb {
 
 std::atomic<long long> g_kernel_launches{0};
+std::atomic<long long> g_launch_generation{0};
 
 static cudaStream_t g_main_stream = nullptr;
 cudaStream_t main_stream() { return g_main_stream; }
@@ -227,6 +228,9 @@ void BoundPotential::set_params_device(int new_size, const double *d_params, cud
             std::to_string(d_p.length));
     }
     TMB_CUDA(cudaMemcpyAsync(d_p.data, d_params, new_size * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    if (size != new_size) {
+        bump_launch_generation(); // P is a kernel argument of every captured launch
+    }
     size = new_size;
 }
 

@@ -480,6 +480,7 @@ private:
     cudaStream_t graph_stream_ = nullptr;
     cudaGraphExec_t graph_exec_ = nullptr;
     long long graph_kernels_ = 0;
+    long long graph_generation_ = -1; // g_launch_generation at capture time
     void run_steps(int n, cudaStream_t stream);
     void eager_step(cudaStream_t stream); // integrator step, then every mover (reference context.cu:261-277)
     void verify_frame(const double *h_x, const double *h_box) const;

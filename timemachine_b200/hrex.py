@@ -152,7 +152,7 @@ class HREX:
         rng = np.random.Generator(np.random.Philox(int(seed)))
         pair_idxs = rng.integers(0, len(neighbor_pairs), n_swap_attempts)
         uniform_samples = rng.random(n_swap_attempts)
-        final, proposed, accepted = _replica.run_neighbor_swaps(
+        final, proposed, accepted = _replica.run_neighbor_swaps_native(
             np.asarray(self.replica_idx_by_state), np.asarray(neighbor_pairs), np.asarray(log_q_kl), pair_idxs, uniform_samples
         )
         return HREX(self.replicas, [int(r) for r in final]), list(zip(accepted.tolist(), proposed.tolist()))
@@ -327,7 +327,13 @@ class ContextSampler:
             assert len(self.water_params_by_state) == len(self.params_by_state)
         self.water_sampling_counts = {}  # state -> (accepted, proposed) during the most recent sample() under that state
 
-    def sample(self, xvb: CoordsVelBox, replica_idx: int, state_idx: int, steps_done: int, n_steps: int):
+    def sample(self, xvb: CoordsVelBox, replica_idx: int, state_idx: int, steps_done: int, n_steps: int, mover_step: Optional[int] = None):
+        """steps_done positions the integrator's counter-based noise stream (it includes the equilibration steps of frame
+        0); mover_step is what the barostat and the water sampler are told, `current_frame * steps_per_frame` in the
+        reference (fe/free_energy.py:1497-1510: equilibration steps are NOT counted, so the phase of the movers relative
+        to the frames matches the reference for any n_eq_steps).  Defaults to steps_done."""
+        if mover_step is None:
+            mover_step = steps_done
         ctx = self.context
         ctx.set_x_t(xvb.coords)
         ctx.set_v_t(xvb.velocities)
@@ -335,11 +341,11 @@ class ContextSampler:
         self.bound.set_params(self.params_by_state[state_idx])
         self.integrator.set_step((replica_idx << self.SUBSTREAM_BITS) + steps_done)
         if self.barostat is not None:
-            self.barostat.set_step(steps_done)
+            self.barostat.set_step(mover_step)
         if self.water_sampler is not None:
             if self.water_params_by_state is not None:
                 self.water_sampler.set_params(self.water_params_by_state[state_idx])
-            self.water_sampler.set_step(steps_done)
+            self.water_sampler.set_step(mover_step)
             proposed0, accepted0 = self.water_sampler.n_proposed(), self.water_sampler.n_accepted()
         xs, boxes = ctx.multiple_steps(n_steps)
         if self.water_sampler is not None:
@@ -356,6 +362,117 @@ class ContextSampler:
             coords, self.params_by_state, boxes, np.asarray(coords_batch_idxs, np.uint32), np.asarray(params_batch_idxs, np.uint32), False, False, True
         )
         return np.asarray(U)
+
+
+class ResidentCoordsVelBox:
+    """Stands for a replica whose coordinates, velocities and box live in a Context's device buffers.  `coords`,
+    `velocities` and `box` read them back on demand; once the sampler loads another replica into the context the values are
+    captured to the host first (`_materialize`), so the object stays valid."""
+
+    def __init__(self, sampler, replica_idx):
+        self._sampler = sampler
+        self.replica_idx = replica_idx
+        self._host = None
+
+    def _materialize(self):
+        if self._host is None:
+            ctx = self._sampler.context
+            self._host = CoordsVelBox(np.asarray(ctx.get_x_t()), np.asarray(ctx.get_v_t()), np.asarray(ctx.get_box()))
+        return self._host
+
+    @property
+    def coords(self):
+        return self._host.coords if self._host is not None else np.asarray(self._sampler.context.get_x_t())
+
+    @property
+    def velocities(self):
+        return self._host.velocities if self._host is not None else np.asarray(self._sampler.context.get_v_t())
+
+    @property
+    def box(self):
+        return self._host.box if self._host is not None else np.asarray(self._sampler.context.get_box())
+
+
+class DeviceResidentSampler(ContextSampler):
+    """ContextSampler for the one-replica-per-GPU layout: the replica a rank owns never leaves the device.
+
+    The reference reloads every replica into its single Context each frame (set_x_t / set_v_t / set_box / set_params,
+    fe/free_energy.py:1485-1496) because all replicas share one GPU.  With a GPU per replica none of those copies is
+    needed: the state stays in the Context's buffers, all K parameter sets are resident in HBM ([K, P] doubles) and a swap
+    is a device-to-device re-bind (`BoundPotential.set_params_device`, reference bound_potential.cu:139-147); the energies
+    of U_kl are energy-only evaluations on the resident coordinates (`Potential.execute_device` with du_dx = du_dp = null)
+    read back as one small D2H copy.  Everything is enqueued on one stream.  Falls back to loading from the host when a rank
+    owns several replicas (the previously resident one is captured to the host first)."""
+
+    def __init__(self, context, params_by_state, device, stream=None, water_params_by_state=None):
+        super().__init__(context, params_by_state, water_params_by_state)
+        import torch
+
+        self._torch = torch
+        self.device = torch.device(device)
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device)
+        context.set_stream(self.stream.cuda_stream)
+        self.d_x, self.d_v, self.d_box = context.device_state()
+        self.d_params = torch.from_numpy(self.params_by_state).to(self.device)  # [K, P]
+        self.n_atoms = None
+        self.n_params = int(self.params_by_state.shape[1])
+        self.d_u = torch.zeros(2 * max(4, 2 * len(self.params_by_state)), dtype=torch.int64, device=self.device)  # int128 slots
+        self._resident = None  # the ResidentCoordsVelBox whose replica is in the context
+
+    def sample(self, xvb, replica_idx: int, state_idx: int, steps_done: int, n_steps: int, mover_step: Optional[int] = None):
+        if mover_step is None:
+            mover_step = steps_done
+        ctx = self.context
+        if not (xvb is self._resident and self._resident._host is None):
+            # not what the context holds right now: keep the resident replica's state on the host, load this one
+            if self._resident is not None:
+                self._resident._materialize()
+            x, v, b = xvb.coords, xvb.velocities, xvb.box
+            ctx.set_x_t(x)
+            ctx.set_v_t(v)
+            ctx.set_box(b)
+            self.n_atoms = int(np.asarray(x).shape[0])
+        self.bound.set_params_device(self.d_params[state_idx].data_ptr(), self.n_params, self.stream.cuda_stream)
+        self.integrator.set_step((replica_idx << self.SUBSTREAM_BITS) + steps_done)
+        if self.barostat is not None:
+            self.barostat.set_step(mover_step)
+        if self.water_sampler is not None:
+            if self.water_params_by_state is not None:
+                self.water_sampler.set_params(self.water_params_by_state[state_idx])
+            self.water_sampler.set_step(mover_step)
+            proposed0, accepted0 = self.water_sampler.n_proposed(), self.water_sampler.n_accepted()
+        ctx.multiple_steps(n_steps, n_steps + 1)  # nothing is copied out
+        if self.water_sampler is not None:
+            self.water_sampling_counts[state_idx] = (
+                self.water_sampler.n_accepted() - accepted0, self.water_sampler.n_proposed() - proposed0,
+            )
+        scale = self.barostat.get_volume_scale_factor() if self.barostat is not None else None
+        self._resident = ResidentCoordsVelBox(self, replica_idx)
+        return self._resident, scale
+
+    def energies(self, xvbs, coords_batch_idxs, params_batch_idxs) -> np.ndarray:
+        torch = self._torch
+        out = np.empty(len(coords_batch_idxs))
+        resident_pairs = []
+        for slot, (c, p) in enumerate(zip(coords_batch_idxs, params_batch_idxs)):
+            if xvbs[int(c)] is self._resident and self._resident._host is None:
+                resident_pairs.append((slot, int(p)))
+        if len(self.d_u) < 2 * len(resident_pairs):
+            self.d_u = torch.zeros(2 * len(resident_pairs), dtype=torch.int64, device=self.device)
+        for n, (slot, p) in enumerate(resident_pairs):
+            self.potential.execute_device(
+                self.n_atoms, self.n_params, self.d_x, self.d_params[p].data_ptr(), self.d_box, 0, 0, self.d_u.data_ptr() + 16 * n,
+                self.stream.cuda_stream,
+            )
+        if resident_pairs:
+            with torch.cuda.stream(self.stream):
+                host = self.d_u[: 2 * len(resident_pairs)].cpu().numpy()  # the frame's only device -> host copy
+            for n, (slot, _) in enumerate(resident_pairs):
+                out[slot] = _replica.i128_to_energy(int(host[2 * n]), int(host[2 * n + 1]))
+        rest = [i for i in range(len(out)) if i not in {s for s, _ in resident_pairs}]
+        if rest:  # replicas that are not in the context right now: the host path
+            out[rest] = super().energies(xvbs, np.asarray(coords_batch_idxs)[rest], np.asarray(params_batch_idxs)[rest])
+        return out
 
 
 def _all_gather_rows(local_rows: np.ndarray, owners: list, n_replicas: int, dist, device) -> np.ndarray:
@@ -392,6 +509,8 @@ def run_sims_hrex(
     device=None,
     print_diagnostics_interval: Optional[int] = None,
     on_iteration: Optional[Callable] = None,
+    store_frames: bool = True,
+    replica_idx_by_state: Optional[Sequence[int]] = None,
 ):
     """Nearest-neighbour HREX over len(replicas) states (reference run_sims_hrex, fe/free_energy.py:1383-1618, up to and
     including the diagnostics; the BAR analysis that follows it there is host science outside this path).
@@ -401,7 +520,9 @@ def run_sims_hrex(
     on_iteration(frame, U_kl, hrex) is called on every rank after the energies of an iteration are known, before its swaps.
     Returns ([Trajectory by state], HREXDiagnostics, final HREX).  Trajectories are backed by `<out_dir>/state_<s>`; on
     ranks > 0 only the frames those ranks sampled exist until every rank has finished (shared filesystem), which the
-    final barrier guarantees.
+    final barrier guarantees.  store_frames=False keeps nothing on disk and returns None for the trajectories (throughput
+    runs with a DeviceResidentSampler: no frame ever leaves the GPU); the diagnostics and the final HREX are as usual.
+    replica_idx_by_state continues an earlier run's permutation (default: replica k starts in state k).
     """
     n_states = len(replicas)
     world = 1 if dist is None or not dist.is_initialized() else dist.get_world_size()
@@ -414,34 +535,43 @@ def run_sims_hrex(
         neighbor_pairs = [(0, 0), *neighbor_pairs]  # identity move for aperiodicity (fe/free_energy.py:1455-1457)
 
     tmp = None
-    if out_dir is None:
+    if out_dir is None and store_frames:
         assert world == 1, "ranks must share an out_dir"
         tmp = tempfile.TemporaryDirectory()
         out_dir = Path(tmp.name)
-    out_dir = Path(out_dir)
+    out_dir = Path(out_dir) if store_frames else Path("/nonexistent")
     state_dirs = [out_dir / f"state_{s}" for s in range(n_states)]
-    for d in state_dirs:
+    for d in state_dirs if store_frames else []:
         d.mkdir(parents=True, exist_ok=True)
 
     hrex = HREX.from_replicas([replicas[k] if k in mine else None for k in range(n_states)])
+    if replica_idx_by_state is not None:
+        assert sorted(replica_idx_by_state) == list(range(n_states)), "replica_idx_by_state must be a permutation"
+        hrex = HREX(hrex.replicas, [int(r) for r in replica_idx_by_state])
     steps_done = {k: 0 for k in mine}
     box_dirs = [out_dir / f"state_{s}_boxes" for s in range(n_states)]
-    for d in box_dirs:
+    for d in box_dirs if store_frames else []:
         d.mkdir(parents=True, exist_ok=True)
     water_dirs = [out_dir / f"state_{s}_water_sampling" for s in range(n_states)]  # created on first use
     replica_idx_by_state_by_iter, fraction_accepted_by_pair_by_iter = [], []
     kT = BOLTZ * temperature
     t_begin = t_last = time.perf_counter()
 
+    import inspect
+
+    takes_mover_step = "mover_step" in inspect.signature(sampler.sample).parameters
     for frame in range(md_params.n_frames):
         state_of_replica = np.argsort(hrex.replica_idx_by_state)
         local = list(hrex.replicas)
         for k in mine:
             s = int(state_of_replica[k])
             n_steps = md_params.steps_per_frame + (md_params.n_eq_steps if frame == 0 else 0)
-            xvb, scale = sampler.sample(local[k], k, s, steps_done[k], n_steps)
+            extra = {"mover_step": frame * md_params.steps_per_frame} if takes_mover_step else {}
+            xvb, scale = sampler.sample(local[k], k, s, steps_done[k], n_steps, **extra)
             steps_done[k] += n_steps
             local[k] = xvb
+            if not store_frames:
+                continue
             # one chunk per (state, iteration), written by whoever sampled it: the reference's StoredArrays layout
             np.save(StoredArrays.get_chunk_path(state_dirs[s], frame), xvb.coords[None])
             np.save(StoredArrays.get_chunk_path(box_dirs[s], frame), xvb.box[None])
@@ -467,7 +597,10 @@ def run_sims_hrex(
             on_iteration(frame, U_kl, hrex)
 
         replica_idx_by_state_by_iter.append(list(hrex.replica_idx_by_state))
-        hrex, fraction = hrex.attempt_neighbor_swaps_fast(neighbor_pairs, log_q_kl, n_swaps, md_params.seed + frame + 1)
+        if n_states == 1:
+            fraction = []  # a single window: nothing to swap with
+        else:
+            hrex, fraction = hrex.attempt_neighbor_swaps_fast(neighbor_pairs, log_q_kl, n_swaps, md_params.seed + frame + 1)
         if n_states == 2:
             fraction = fraction[1:]
         fraction_accepted_by_pair_by_iter.append(fraction)
@@ -483,6 +616,9 @@ def run_sims_hrex(
 
     if world > 1:
         dist.barrier()  # every chunk is on disk
+    diagnostics = HREXDiagnostics(replica_idx_by_state_by_iter, fraction_accepted_by_pair_by_iter)
+    if not store_frames:
+        return None, diagnostics, hrex
     trajectories = []
     for s in range(n_states):
         frames = StoredArrays.load(state_dirs[s])
@@ -490,7 +626,6 @@ def run_sims_hrex(
         final = np.load(out_dir / f"final_state_{s}.npz")
         scale = float(final["scale"])
         trajectories.append(Trajectory(frames, boxes, final["velocities"], None if np.isnan(scale) else scale))
-    diagnostics = HREXDiagnostics(replica_idx_by_state_by_iter, fraction_accepted_by_pair_by_iter)
     if all(d.is_dir() for d in water_dirs):
         per_state = [np.array(list(StoredArrays.load(d)), dtype=np.int32) for d in water_dirs]  # [n_iters, 2] each
         diagnostics.water_sampling_diagnostics = WaterSamplingDiagnostics(np.stack(per_state, axis=1))

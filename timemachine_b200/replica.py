@@ -93,6 +93,36 @@ def run_neighbor_swaps(replica_idx_by_state, neighbor_pairs, log_q_kl, pair_idxs
     return replica_idx_by_state, proposed, accepted
 
 
+def run_neighbor_swaps_native(replica_idx_by_state, neighbor_pairs, log_q_kl, pair_idxs, uniform_samples):
+    """`run_neighbor_swaps` through the C ABI (`tmb_hrex_run_neighbor_swaps`, host code of libtmb200.so): the reference
+    jit-compiles this loop (md/hrex.py:50); n_states^3 attempts per frame in Python would cost milliseconds of idle GPU on
+    every rank.  Same results as the Python statement above, bit for bit (tests/test_replica_cpu.py)."""
+    import ctypes as C
+
+    from ._lib import load
+
+    L = load()
+    perm = np.ascontiguousarray(replica_idx_by_state, dtype=np.int32).copy()
+    pairs = np.ascontiguousarray(neighbor_pairs, dtype=np.int32).reshape(-1, 2)
+    q = np.ascontiguousarray(log_q_kl, dtype=np.float64)
+    pidx = np.ascontiguousarray(pair_idxs, dtype=np.int32)
+    us = np.ascontiguousarray(uniform_samples, dtype=np.float64)
+    assert q.ndim == 2 and q.shape[1] == len(perm) and len(pidx) == len(us)
+    proposed = np.zeros(len(pairs), dtype=np.uint32)
+    accepted = np.zeros(len(pairs), dtype=np.uint32)
+
+    def ptr(a, t):
+        return a.ctypes.data_as(C.POINTER(t))
+
+    rc = L.tmb_hrex_run_neighbor_swaps(
+        len(perm), q.shape[0], len(pairs), ptr(pairs, C.c_int32), ptr(q, C.c_double), len(pidx), ptr(pidx, C.c_int32),
+        ptr(us, C.c_double), ptr(perm, C.c_int32), ptr(proposed, C.c_uint32), ptr(accepted, C.c_uint32),
+    )
+    if rc != 0:
+        raise RuntimeError(L.tmb_last_error().decode())
+    return perm, proposed, accepted
+
+
 def i128_to_energy(lo: int, hi: int) -> float:
     """Fixed-point int128 energy -> kJ/mol, NaN when it left the int64 range (reference wrap_kernels.cpp:83-89)."""
     v = (int(hi) << 64) | (int(lo) & ((1 << 64) - 1))
