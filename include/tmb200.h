@@ -129,6 +129,9 @@ int tmb_nonbonded_num_tiles(tmb_potential pot, unsigned int *out);
 /* neighbour-list (re)builds since construction; the rebuild decision itself never leaves the device
  * (reference: host-side flag read every step, nonbonded_all_pairs.cu:217-235) */
 int tmb_nonbonded_num_rebuilds(tmb_potential pot, unsigned int *out);
+/* capacity (tiles) of the list buffer and the worst case the reference allocates up front (neighborlist.cu:22-28); the
+ * buffer here starts at 4 tiles per atom and grows when a build needs more */
+int tmb_nonbonded_tile_capacity(tmb_potential pot, unsigned long long *capacity, unsigned long long *worst_case);
 /* measurement hooks (bench.py roofline): bracket each tile-kernel launch with CUDA events on its launch stream;
  * drain returns the per-launch durations in ms recorded since the previous drain (at most `capacity`). */
 int tmb_nonbonded_set_kernel_timing(tmb_potential pot, int on);

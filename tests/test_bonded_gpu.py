@@ -187,5 +187,10 @@ def test_bonded_far_from_the_origin(precision, rng):
         assert_forces_close(odx, dx, 1e-4 if precision == np.float32 else 1e-9, what=name + " vs f64 oracle, offset 10 nm")
         if ref is not None:
             rdx, rdp, ru = getattr(ref, f"{name}_{suffix}")(idxs).execute(x, params, box)
-            assert_forces_close(rdx, dx, 1e-5 if precision == np.float32 else 1e-10, what=name + " vs compiled reference, offset 10 nm")
+            if name == "HarmonicBond" and precision == np.float32:
+                # the bond kernel reproduces the reference's operation sequence (the same FMA chain for |d|^2)
+                np.testing.assert_array_equal(dx, rdx, err_msg="HarmonicBond forces are not bitwise the compiled reference's")
+            # angle / torsion: same formulas, the compilers contract them differently; on these stiff terms an ulp of a
+            # length is 2e-5 of the force
+            assert_forces_close(rdx, dx, 1e-4 if precision == np.float32 else 1e-10, what=name + " vs compiled reference, offset 10 nm")
             np.testing.assert_allclose(u, ru, rtol=1e-4 if precision == np.float32 else 1e-9)

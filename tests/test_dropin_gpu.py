@@ -80,15 +80,19 @@ def test_replayed_reference_calls_construct_and_evaluate():
         assert np.isfinite(u) and np.isfinite(du_dx).all() and du_dp.shape == p.shape, c["cls"]
         again = impl.execute(x, p, box)
         np.testing.assert_array_equal(du_dx, again[0])
-        results.setdefault((base, json.dumps(c["args"], sort_keys=True)), {})[suffix] = (du_dx, u)
+        # the wrappers construct the f32 and the f64 class of a potential one after the other: pair them by order
+        slot = results.setdefault(base, {"f32": [], "f64": []})
+        slot[suffix].append((du_dx, u))
         n_exec += 1
     assert n_exec >= 30
     # the two precisions of one recorded constructor call agree
-    pairs = [v for v in results.values() if len(v) == 2]
-    assert len(pairs) >= 14
-    for v in pairs:
-        assert_forces_close(v["f64"][0], v["f32"][0], 1e-3)
-        np.testing.assert_allclose(v["f32"][1], v["f64"][1], rtol=2e-4, atol=1e-2)
+    n_pairs = 0
+    for base, v in results.items():
+        for (dx32, u32), (dx64, u64) in zip(v["f32"], v["f64"]):
+            assert_forces_close(dx64, dx32, 1e-3, what=base)
+            np.testing.assert_allclose(u32, u64, rtol=2e-4, atol=1e-2, err_msg=base)
+            n_pairs += 1
+    assert n_pairs >= 14
 
 
 def test_replayed_composite_matches_the_oracle_and_runs_md():
@@ -119,14 +123,14 @@ def test_replayed_composite_matches_the_oracle_and_runs_md():
     assert baro.get_interval() == 15
 
 
-@pytest.mark.parametrize("precision,tol", [(np.float64, 2e-6), (np.float32, 2e-3)])
+@pytest.mark.parametrize("precision,tol", [(np.float64, 5e-3), (np.float32, 5e-3)])
 def test_jvp_rule_against_finite_differences(precision, tol):
     """reference potentials/jax_interface.py:27-46 restated in NumPy (timemachine_b200/jax_interface.py): the directional
     derivative u'(0) of u(x + t dx, p + t dp) equals sum(du_dx dx) + sum(du_dp dp)."""
     from timemachine_b200 import jax_interface as J
     from timemachine_b200 import potentials
 
-    s = water_box(200, seed=9)
+    s = water_box(700, seed=9)  # box 2.76 nm > 2 cutoff: the energy is a smooth function of the coordinates
     N = s["N"]
     box = s["box"]
     x, params = round_to_f32(s["x"]), round_to_f32(s["params"])
@@ -134,12 +138,18 @@ def test_jvp_rule_against_finite_differences(precision, tol):
     rng = np.random.default_rng(0)
     dx = rng.normal(size=x.shape)
     dp = rng.normal(size=params.shape) * np.array([1.0, 0.01, 0.05, 0.0])
+    dp[params[:, 2] == 0, 2] = 0.0  # eps == 0 switches the LJ term off (k_nonbonded.cuh:232): not differentiable there
     u, t_full = J.unbound_impl_jvp(impl, (x, params, box), (dx, dp, None))
     _, t_x = J.unbound_impl_jvp(impl, (x, params, box), (dx, None, None))
     _, t_p = J.unbound_impl_jvp(impl, (x, params, box), (None, dp, None))
     np.testing.assert_allclose(t_full, t_x + t_p, rtol=1e-12)
     assert u == J.call_unbound_impl(impl, x, params, box)
-    # central differences through the f64 implementation of the same potential
+    # the rule itself, exactly: sum(du_dx * dx) + sum(du_dp * dp) of what execute returns
+    du_dx, du_dp, u2 = impl.execute(x, params, box, True, True, True)
+    assert u2 == u and t_x == np.sum(du_dx * dx) and t_p == np.sum(du_dp * dp)
+    # and it is the directional derivative: central differences through the f64 implementation of the same potential.
+    # (Loose: the reference's LJ term is not switched, every O-O pair that crosses the cutoff between x - h dx and x + h dx
+    # moves the energy by 8e-4 kJ/mol whatever h is - about 1e-3 of this derivative.)
     ref = potentials.Nonbonded(N, s["exclusion_idxs"], s["scale_factors"], 2.0, 1.2).to_gpu(np.float64).unbound_impl
     h = 1e-5
     fd_x = (J.call_unbound_impl(ref, x + h * dx, params, box) - J.call_unbound_impl(ref, x - h * dx, params, box)) / (2 * h)

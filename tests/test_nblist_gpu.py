@@ -155,3 +155,58 @@ def test_neighborlist_matches_reference_custom_ops(precision):
     c, e = nblist_cls(precision)(len(x)).compute_block_bounds(x, box, 32)
     np.testing.assert_allclose(c, rc, rtol=0, atol=1e-6)
     np.testing.assert_allclose(e, re_, rtol=0, atol=1e-6)
+
+
+def test_tile_buffer_is_sized_from_measured_counts_and_grows(tmp_path):
+    """The list buffer starts at 4 tiles per atom instead of the O((N/32)^2) worst case the reference allocates
+    (neighborlist.cu:22-28), and a build that needs more grows it and redoes the evaluation: results with a deliberately
+    tiny initial buffer (TMB_NBLIST_TILES_PER_ATOM_X100=5: 0.05 tiles per atom) are bitwise those of the default."""
+    import subprocess
+    import sys
+
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from tests.common import water_box, round_to_f32
+from timemachine_b200 import custom_ops as ops, potentials as P
+s = water_box(4000, seed=3)
+N = s["N"]; x, p, box = round_to_f32(s["x"]), round_to_f32(s["params"]), s["box"]
+ap = ops.NonbondedAllPairs_f32(N, 2.0, 1.2, None, False, 0.1)
+cap0, worst = ap.get_tile_capacity()
+dx, dp, u = ap.execute(x, p, box)
+cap1, _ = ap.get_tile_capacity()
+T = ap.get_tile_count()
+nl = ops.Neighborlist_f32(N)
+ixn = nl.get_nblist(x, box, 1.3)
+# MD through a Context with a list that is too small at first: the call fails loudly once, then runs
+pot = P.SummedPotential(
+    [P.HarmonicBond(s["bond_idxs"]), P.HarmonicAngle(s["angle_idxs"]), P.Nonbonded(N, s["exclusion_idxs"], s["scale_factors"], 2.0, 1.2)],
+    [s["bond_params"], s["angle_params"], p])
+flat = np.concatenate([s["bond_params"].reshape(-1), s["angle_params"].reshape(-1), p.reshape(-1)])
+bp = ops.BoundPotential(pot.to_gpu(np.float32).unbound_impl, flat)
+ctx = ops.Context(x, np.zeros_like(x), box, ops.LangevinIntegrator(s["masses"], 300.0, 1e-3, 1.0, 1), [bp])
+msg = ""
+try:
+    ctx.multiple_steps(20)
+except RuntimeError as e:
+    msg = str(e)
+    ctx.set_x_t(x); ctx.set_v_t(np.zeros_like(x))
+xs, _ = ctx.multiple_steps(20)
+np.savez(sys.argv[1], dx=dx, dp=dp, u=u, cap0=cap0, cap1=cap1, worst=worst, T=T, n_ixn=sum(len(r) for r in ixn), msg=msg, xs=xs)
+""" % str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    import os
+
+    outs = {}
+    for name, env in (("default", {}), ("tiny", {"TMB_NBLIST_TILES_PER_ATOM_X100": "5"})):
+        out = tmp_path / f"{name}.npz"
+        subprocess.run([sys.executable, "-c", code, str(out)], check=True, env={**os.environ, **env})
+        outs[name] = dict(np.load(out))
+    d, t = outs["default"], outs["tiny"]
+    N = 12000
+    assert int(d["cap0"]) == 4 * N + 1024 and int(d["cap1"]) == int(d["cap0"])  # liquid density needs ~1 tile per atom
+    assert int(d["worst"]) > int(d["cap0"])  # 1.4x at 12k atoms, 3.6x at 30k, 11x at 90k: the worst case grows as N^2
+    assert 0.5 * N < int(d["T"]) < 2 * N and int(d["T"]) * 2 < int(d["cap0"])
+    assert int(t["cap0"]) == N * 5 // 100 and int(t["cap1"]) >= int(t["T"]) > int(t["cap0"])  # grown past what was needed
+    for k in ("dx", "dp", "u", "T", "n_ixn", "xs"):
+        np.testing.assert_array_equal(d[k], t[k], err_msg=k)
+    assert str(d["msg"]) == "" and "neighborlist tile buffer overflow during MD steps" in str(t["msg"])

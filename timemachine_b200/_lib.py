@@ -68,6 +68,7 @@ SIGNATURES = {
     "tmb_potential_execute_device": [_h, _int, _int, _h, _h, _h, _h, _h, _h, _h],
     "tmb_nonbonded_num_tiles": [_h, C.POINTER(C.c_uint)],
     "tmb_nonbonded_num_rebuilds": [_h, C.POINTER(C.c_uint)],
+    "tmb_nonbonded_tile_capacity": [_h, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)],
     "tmb_nonbonded_set_kernel_timing": [_h, _int],
     "tmb_nonbonded_drain_kernel_times": [_h, _p_f32, _int, C.POINTER(_int)],
     "tmb_bound_potential_create": [_h, _p_f64, _int, _ph],

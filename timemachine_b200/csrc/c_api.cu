@@ -387,6 +387,20 @@ int tmb_nonbonded_num_tiles(tmb_potential pot, unsigned int *out) {
     });
 }
 
+int tmb_nonbonded_tile_capacity(tmb_potential pot, unsigned long long *capacity, unsigned long long *worst_case) {
+    return guarded([&] {
+        if (auto a = std::dynamic_pointer_cast<NonbondedTiled<float>>(as_pot(pot))) {
+            *capacity = a->tile_capacity();
+            *worst_case = a->tile_worst_case();
+        } else if (auto b = std::dynamic_pointer_cast<NonbondedTiled<double>>(as_pot(pot))) {
+            *capacity = b->tile_capacity();
+            *worst_case = b->tile_worst_case();
+        } else {
+            throw std::runtime_error("not a tile-list nonbonded potential");
+        }
+    });
+}
+
 int tmb_nonbonded_num_rebuilds(tmb_potential pot, unsigned int *out) {
     return guarded([&] {
         if (auto a = std::dynamic_pointer_cast<NonbondedTiled<float>>(as_pot(pot))) {

@@ -208,6 +208,23 @@ void Context::step() {
     cudaStream_t stream = active_stream();
     eager_step(stream);
     TMB_CUDA(cudaStreamSynchronize(stream));
+    check_list_overflow();
+}
+
+// The tile-list buffers are sized from measured counts (4x the liquid-density count, neighborlist.cu).  Steps cannot be
+// redone the way a single evaluation can, so a build that ran out of room during them is an error: the buffers have been
+// grown by the time this throws, the caller restores its state (set_x_t / set_v_t / set_box) and runs again.
+void Context::check_list_overflow() {
+    bool any = false;
+    for (auto &bp : bps_) {
+        any = bp->potential->recover_overflow() || any;
+    }
+    if (any) {
+        destroy_graph();
+        throw std::runtime_error(
+            "neighborlist tile buffer overflow during MD steps: the buffer has been enlarged, but the steps of this call "
+            "used an incomplete interaction list - restore the state and run them again");
+    }
 }
 
 std::shared_ptr<MonteCarloBarostat<float>> Context::get_barostat() const {
@@ -263,6 +280,7 @@ void Context::multiple_steps(int n_steps, int n_samples, double *h_x, double *h_
         }
     }
     TMB_CUDA(cudaStreamSynchronize(stream));
+    check_list_overflow();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -302,7 +320,15 @@ void Context::run_local_steps(int n_steps, int n_samples, double *h_x, double *h
         throw;
     }
     TMB_CUDA(cudaStreamSynchronize(stream));
+    bool local_overflow = false;
+    for (auto &bp : pots) {
+        local_overflow = bp->potential->recover_overflow() || local_overflow;
+    }
     local_md_->reset();
+    if (local_overflow) {
+        throw std::runtime_error("neighborlist tile buffer overflow during local MD steps: buffer enlarged, run them again");
+    }
+    check_list_overflow();
 }
 
 void Context::multiple_steps_local(

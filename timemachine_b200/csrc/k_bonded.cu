@@ -54,7 +54,9 @@ template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_harmoni
         const V3<Real> d = delta3<Real>(a.x, src, dst);
         const Real kb = static_cast<Real>(a.p[b * 2 + 0]);
         const Real b0 = static_cast<Real>(a.p[b * 2 + 1]);
-        const Real r = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+        // the reference's `d2ij += delta * delta` loop is contracted by nvcc into this chain (default -fmad=true there, off
+        // here): with it the bond term is the same sequence of rounded operations as the reference's
+        const Real r = sqrt(fma(d.z, d.z, fma(d.y, d.y, d.x * d.x)));
         const Real db = r - b0;
         if (a.du_dx != nullptr) {
             const Real inv_r = 1 / r;

@@ -259,6 +259,14 @@ template <typename Real> static int nb_tiles_grid_impl() {
     return cached;
 }
 
+static bool use_async_staging() {
+    static const bool on = [] {
+        const char *e = std::getenv("TMB_NB_ASYNC");
+        return e != nullptr && e[0] == '1';
+    }();
+    return on;
+}
+
 static bool use_ring_for_f32() {
     static const bool ring = [] {
         const char *e = std::getenv("TMB_NB_RING");
@@ -283,7 +291,11 @@ template <typename Real>
 void launch_nb_tiles(const NbTileArgs<Real> &args, bool with_u, bool with_dx, bool with_dp, cudaStream_t stream) {
     if (std::is_same<Real, float>::value && !use_ring_for_f32()) {
         // f32 (the MD path): compaction-queue kernel; the ring kernel below stays as the f64 path and as an A/B reference
-        launch_nb_tiles_cq(reinterpret_cast<const NbTileArgs<float> &>(args), with_u, with_dx, with_dp, stream);
+        if (use_async_staging()) {
+            launch_nb_tiles_cq_async(reinterpret_cast<const NbTileArgs<float> &>(args), with_u, with_dx, with_dp, stream);
+        } else {
+            launch_nb_tiles_cq(reinterpret_cast<const NbTileArgs<float> &>(args), with_u, with_dx, with_dp, stream);
+        }
         return;
     }
     int grid = nb_tiles_grid_impl<Real>();

@@ -128,6 +128,7 @@ struct WarpTileWriter {
                 tiles.cols[static_cast<size_t>(t) * TILE + lane] = stage[s * TILE + lane];
             } else if (lane == 0) {
                 *tiles.overflow = 1;
+                atomicMax(tiles.overflow + 1, base + static_cast<unsigned int>(nstage)); // how much room was needed
             }
         }
         __syncwarp();

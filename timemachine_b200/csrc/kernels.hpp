@@ -43,6 +43,10 @@ int nb_tiles_reserved_ctas();
 // f32 "compaction queue" formulation (k_nb_tiles_cq.cu); launch_nb_tiles<float> uses it unless TMB_NB_RING=1
 int nb_tiles_cq_max_grid();
 void launch_nb_tiles_cq(const NbTileArgs<float> &args, bool with_u, bool with_dx, bool with_dp, cudaStream_t stream);
+// the same tile evaluation behind an asynchronous staging pipeline (TMA bulk copy of the index vector + cp.async gather of
+// the column atoms, k_nb_tiles_cq_async.cu); selected with TMB_NB_ASYNC=1 for A/B measurements
+int nb_tiles_cq_async_max_grid();
+void launch_nb_tiles_cq_async(const NbTileArgs<float> &args, bool with_u, bool with_dx, bool with_dp, cudaStream_t stream);
 template <typename Real> int nb_tiles_max_grid();
 template <typename Real>
 void launch_nb_tiles(const NbTileArgs<Real> &args, bool with_u, bool with_dx, bool with_dp, cudaStream_t stream);

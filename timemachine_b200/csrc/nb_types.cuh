@@ -27,7 +27,8 @@ struct TileList {
     int *rows;               // [capacity]
     unsigned int *cols;      // [capacity * 32]
     unsigned int capacity;   // tiles
-    unsigned int *overflow;  // [1] set when a build ran out of capacity
+    unsigned int *overflow;  // [2]: [0] set when a build ran out of capacity (cleared by the next build);
+                             //      [1] sticky: the largest tile count that did not fit since the host last looked
 };
 
 } // namespace tmb

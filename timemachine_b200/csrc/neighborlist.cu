@@ -3,6 +3,7 @@
 #include "potential.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <numeric>
 
@@ -75,20 +76,50 @@ Neighborlist<Real>::Neighborlist(int N)
     d_col_ctr_.realloc(nb * 3);
     d_col_ext_.realloc(nb * 3);
     d_count_.realloc(1);
-    d_overflow_.realloc(1);
+    d_overflow_.realloc(2);
     d_count_.zero();
     d_overflow_.zero();
-    // Worst case for an all-pairs list is nb(nb+1)/2 tiles; a row/column split can reach nb_r * nb_c <= (nb+1)^2/4+nb.
-    // Like the reference (neighborlist.cu:22-28) this is address space, not touched memory.
-    const size_t cap = std::max(worst_case_tiles(N), (nb + 1) * (nb + 1) / 4 + nb + 1);
-    d_rows_.realloc(cap);
-    d_cols_.realloc(cap * TILE);
+    // Worst case for an all-pairs list is nb(nb+1)/2 tiles; a row/column split can reach nb_r * nb_c <= (nb+1)^2/4+nb:
+    // O((N/32)^2), what the reference allocates (neighborlist.cu:22-28: 58 MB at 30k atoms, 522 MB at 90k).  A list at
+    // liquid density with cutoff + padding = 1.3 nm holds about ONE tile per atom (measured: 1.03 N at 23k-90k atoms), so
+    // the buffer starts at 4 tiles per atom (4x the measured count: 16 MB at 30k, 48 MB at 90k) and never above the worst
+    // case; a build that needs more records how much (sticky word of `overflow`) and the host grows the buffer and redoes
+    // the evaluation at its next synchronisation point (recover_overflow).
+    worst_case_ = std::max(worst_case_tiles(N), (nb + 1) * (nb + 1) / 4 + nb + 1);
+    size_t per_atom = 4;
+    if (const char *env = std::getenv("TMB_NBLIST_TILES_PER_ATOM_X100")) { // tests: start small to exercise the growth path
+        per_atom = 0;
+        set_capacity(std::max<size_t>(1, static_cast<size_t>(std::atoll(env)) * N / 100));
+    }
+    if (per_atom > 0) {
+        set_capacity(std::min(worst_case_, per_atom * static_cast<size_t>(N) + 1024));
+    }
     tiles_.count = d_count_.data;
     tiles_.overflow = d_overflow_.data;
+    TMB_CUDA(cudaDeviceSynchronize());
+}
+
+template <typename Real> void Neighborlist<Real>::set_capacity(size_t cap) {
+    cap = std::min(cap, worst_case_);
+    d_rows_.realloc(cap);
+    d_cols_.realloc(cap * TILE);
     tiles_.rows = d_rows_.data;
     tiles_.cols = d_cols_.data;
     tiles_.capacity = static_cast<unsigned int>(cap);
+}
+
+template <typename Real> bool Neighborlist<Real>::recover_overflow() {
+    unsigned int needed = 0;
+    TMB_CUDA(cudaMemcpy(&needed, d_overflow_.data + 1, sizeof(needed), cudaMemcpyDeviceToHost));
+    if (needed == 0) {
+        return false;
+    }
     TMB_CUDA(cudaDeviceSynchronize());
+    set_capacity(std::max<size_t>(2 * static_cast<size_t>(needed), 2 * static_cast<size_t>(tiles_.capacity)));
+    d_overflow_.zero();
+    d_count_.zero();
+    TMB_CUDA(cudaDeviceSynchronize());
+    return true;
 }
 
 template <typename Real> void Neighborlist<Real>::set_all_pairs(int K) {
@@ -243,12 +274,15 @@ Neighborlist<Real>::get_nblist_host(int N, const double *h_coords, const double 
     d_coords.copy_from(h_coords);
     d_box.copy_from(h_box);
     cudaStream_t stream = main_stream();
-    build_device(d_coords.data, nullptr, d_box.data, cutoff, nullptr, stream);
-    TMB_CUDA(cudaStreamSynchronize(stream));
-    unsigned int overflow = 0;
-    TMB_CUDA(cudaMemcpy(&overflow, d_overflow_.data, sizeof(overflow), cudaMemcpyDeviceToHost));
-    if (overflow) {
-        throw std::runtime_error("neighborlist tile buffer overflow");
+    for (int attempt = 0;; attempt++) {
+        build_device(d_coords.data, nullptr, d_box.data, cutoff, nullptr, stream);
+        TMB_CUDA(cudaStreamSynchronize(stream));
+        if (!recover_overflow()) {
+            break;
+        }
+        if (attempt >= 8) {
+            throw std::runtime_error("neighborlist tile buffer overflow");
+        }
     }
     const unsigned int T = num_tile_ixns();
     std::vector<int> rows(T);

@@ -73,6 +73,15 @@ template <typename Real> void NonbondedTiled<Real>::du_dp_fixed_to_float(int N, 
 }
 
 template <typename Real> unsigned int NonbondedTiled<Real>::num_tiles() { return nblist_.num_tile_ixns(); }
+
+template <typename Real> bool NonbondedTiled<Real>::recover_overflow() {
+    if (!nblist_.recover_overflow()) {
+        return false;
+    }
+    force_rebuild_ = true;
+    bump_launch_generation(); // the list moved: captured launches hold the old addresses
+    return true;
+}
 template <typename Real> unsigned int NonbondedTiled<Real>::num_rebuilds() {
     TMB_CUDA(cudaDeviceSynchronize());
     unsigned int n = 0;

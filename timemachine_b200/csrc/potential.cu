@@ -71,6 +71,18 @@ void Potential::du_dp_fixed_to_float(int, int P, const u64 *du_dp, double *out) 
     }
 }
 
+// After a synchronised host-level evaluation: did a neighbour-list build run out of room (Potential::recover_overflow)?
+// Then the buffers have been grown and the evaluation is repeated from zeroed outputs.
+static bool redo_after_overflow(Potential &pot, int attempt) {
+    if (!pot.recover_overflow()) {
+        return false;
+    }
+    if (attempt >= 8) {
+        throw std::runtime_error("neighborlist tile buffer overflow");
+    }
+    return true;
+}
+
 void Potential::execute_host(
     int N, int P, const double *h_x, const double *h_p, const double *h_box, u64 *h_du_dx, u64 *h_du_dp, i128 *h_u) {
     DeviceBuffer<double> d_x(static_cast<size_t>(N) * D), d_box(D * D), d_p(P);
@@ -85,20 +97,25 @@ void Potential::execute_host(
     // the kernels accumulate: outputs must start at zero
     if (h_du_dx) {
         d_du_dx.realloc(static_cast<size_t>(N) * D);
-        d_du_dx.zero(stream);
     }
     if (h_du_dp) {
         d_du_dp.realloc(P);
-        d_du_dp.zero(stream);
     }
     if (h_u) {
         d_u.realloc(1);
-        d_u.zero(stream);
     }
-    this->execute_device(
-        N, P, d_x.data, P > 0 ? d_p.data : nullptr, d_box.data, h_du_dx ? d_du_dx.data : nullptr,
-        (h_du_dp && P > 0) ? d_du_dp.data : nullptr, h_u ? d_u.data : nullptr, stream);
-    TMB_CUDA(cudaStreamSynchronize(stream));
+    for (int attempt = 0;; attempt++) {
+        d_du_dx.zero(stream);
+        d_du_dp.zero(stream);
+        d_u.zero(stream);
+        this->execute_device(
+            N, P, d_x.data, P > 0 ? d_p.data : nullptr, d_box.data, h_du_dx ? d_du_dx.data : nullptr,
+            (h_du_dp && P > 0) ? d_du_dp.data : nullptr, h_u ? d_u.data : nullptr, stream);
+        TMB_CUDA(cudaStreamSynchronize(stream));
+        if (!redo_after_overflow(*this, attempt)) {
+            break;
+        }
+    }
     if (h_du_dx) {
         d_du_dx.copy_to(h_du_dx);
     }
@@ -126,28 +143,33 @@ void Potential::execute_batch_host(
     DeviceBuffer<i128> d_u;
     if (h_du_dx) {
         d_du_dx.realloc(total * N * D);
-        d_du_dx.zero(stream);
     }
     if (h_du_dp) {
         d_du_dp.realloc(total * P);
-        d_du_dp.zero(stream);
     }
     if (h_u) {
         d_u.realloc(total);
-        d_u.zero(stream);
     }
-    // serial loop over (coords_i x params_j): the potentials are stateful, coordinates vary slowest so a cached
-    // neighbour list is reused across parameter sets (reference potential.cu:10-38)
-    for (int i = 0; i < coord_batch; i++) {
-        for (int j = 0; j < param_batch; j++) {
-            const size_t k = static_cast<size_t>(i) * param_batch + j;
-            this->execute_device(
-                N, P, d_x.data + static_cast<size_t>(i) * N * D, P > 0 ? d_p.data + static_cast<size_t>(j) * P : nullptr,
-                d_box.data + static_cast<size_t>(i) * D * D, h_du_dx ? d_du_dx.data + k * N * D : nullptr,
-                (h_du_dp && P > 0) ? d_du_dp.data + k * P : nullptr, h_u ? d_u.data + k : nullptr, stream);
+    for (int attempt = 0;; attempt++) {
+        d_du_dx.zero(stream);
+        d_du_dp.zero(stream);
+        d_u.zero(stream);
+        // serial loop over (coords_i x params_j): the potentials are stateful, coordinates vary slowest so a cached
+        // neighbour list is reused across parameter sets (reference potential.cu:10-38)
+        for (int i = 0; i < coord_batch; i++) {
+            for (int j = 0; j < param_batch; j++) {
+                const size_t k = static_cast<size_t>(i) * param_batch + j;
+                this->execute_device(
+                    N, P, d_x.data + static_cast<size_t>(i) * N * D, P > 0 ? d_p.data + static_cast<size_t>(j) * P : nullptr,
+                    d_box.data + static_cast<size_t>(i) * D * D, h_du_dx ? d_du_dx.data + k * N * D : nullptr,
+                    (h_du_dp && P > 0) ? d_du_dp.data + k * P : nullptr, h_u ? d_u.data + k : nullptr, stream);
+            }
+        }
+        TMB_CUDA(cudaStreamSynchronize(stream));
+        if (!redo_after_overflow(*this, attempt)) {
+            break;
         }
     }
-    TMB_CUDA(cudaStreamSynchronize(stream));
     if (h_du_dx) {
         d_du_dx.copy_to(h_du_dx);
     }
@@ -175,25 +197,30 @@ void Potential::execute_batch_sparse_host(
     DeviceBuffer<i128> d_u;
     if (h_du_dx) {
         d_du_dx.realloc(static_cast<size_t>(batch_size) * N * D);
-        d_du_dx.zero(stream);
     }
     if (h_du_dp) {
         d_du_dp.realloc(static_cast<size_t>(batch_size) * P);
-        d_du_dp.zero(stream);
     }
     if (h_u) {
         d_u.realloc(batch_size);
+    }
+    for (int attempt = 0;; attempt++) {
+        d_du_dx.zero(stream);
+        d_du_dp.zero(stream);
         d_u.zero(stream);
+        for (int k = 0; k < batch_size; k++) {
+            const size_t ic = coords_idxs[k];
+            const size_t ip = params_idxs[k];
+            this->execute_device(
+                N, P, d_x.data + ic * N * D, P > 0 ? d_p.data + ip * P : nullptr, d_box.data + ic * D * D,
+                h_du_dx ? d_du_dx.data + static_cast<size_t>(k) * N * D : nullptr,
+                (h_du_dp && P > 0) ? d_du_dp.data + static_cast<size_t>(k) * P : nullptr, h_u ? d_u.data + k : nullptr, stream);
+        }
+        TMB_CUDA(cudaStreamSynchronize(stream));
+        if (!redo_after_overflow(*this, attempt)) {
+            break;
+        }
     }
-    for (int k = 0; k < batch_size; k++) {
-        const size_t ic = coords_idxs[k];
-        const size_t ip = params_idxs[k];
-        this->execute_device(
-            N, P, d_x.data + ic * N * D, P > 0 ? d_p.data + ip * P : nullptr, d_box.data + ic * D * D,
-            h_du_dx ? d_du_dx.data + static_cast<size_t>(k) * N * D : nullptr,
-            (h_du_dp && P > 0) ? d_du_dp.data + static_cast<size_t>(k) * P : nullptr, h_u ? d_u.data + k : nullptr, stream);
-    }
-    TMB_CUDA(cudaStreamSynchronize(stream));
     if (h_du_dx) {
         d_du_dx.copy_to(h_du_dx);
     }
@@ -248,14 +275,19 @@ void BoundPotential::execute_host(int N, const double *h_x, const double *h_box,
     DeviceBuffer<i128> d_u;
     if (h_du_dx) {
         d_du_dx.realloc(static_cast<size_t>(N) * 3);
-        d_du_dx.zero(stream);
     }
     if (h_u) {
         d_u.realloc(1);
-        d_u.zero(stream);
     }
-    execute_device(N, d_x.data, d_box.data, h_du_dx ? d_du_dx.data : nullptr, nullptr, h_u ? d_u.data : nullptr, stream);
-    TMB_CUDA(cudaStreamSynchronize(stream));
+    for (int attempt = 0;; attempt++) {
+        d_du_dx.zero(stream);
+        d_u.zero(stream);
+        execute_device(N, d_x.data, d_box.data, h_du_dx ? d_du_dx.data : nullptr, nullptr, h_u ? d_u.data : nullptr, stream);
+        TMB_CUDA(cudaStreamSynchronize(stream));
+        if (!redo_after_overflow(*potential, attempt)) {
+            break;
+        }
+    }
     if (h_du_dx) {
         d_du_dx.copy_to(h_du_dx);
     }
@@ -273,18 +305,23 @@ void BoundPotential::execute_batch_host(int coord_batch, int N, const double *h_
     DeviceBuffer<i128> d_u;
     if (h_du_dx) {
         d_du_dx.realloc(static_cast<size_t>(coord_batch) * N * 3);
-        d_du_dx.zero(stream);
     }
     if (h_u) {
         d_u.realloc(coord_batch);
+    }
+    for (int attempt = 0;; attempt++) {
+        d_du_dx.zero(stream);
         d_u.zero(stream);
+        for (int i = 0; i < coord_batch; i++) {
+            execute_device(
+                N, d_x.data + static_cast<size_t>(i) * N * 3, d_box.data + static_cast<size_t>(i) * 9,
+                h_du_dx ? d_du_dx.data + static_cast<size_t>(i) * N * 3 : nullptr, nullptr, h_u ? d_u.data + i : nullptr, stream);
+        }
+        TMB_CUDA(cudaStreamSynchronize(stream));
+        if (!redo_after_overflow(*potential, attempt)) {
+            break;
+        }
     }
-    for (int i = 0; i < coord_batch; i++) {
-        execute_device(
-            N, d_x.data + static_cast<size_t>(i) * N * 3, d_box.data + static_cast<size_t>(i) * 9,
-            h_du_dx ? d_du_dx.data + static_cast<size_t>(i) * N * 3 : nullptr, nullptr, h_u ? d_u.data + i : nullptr, stream);
-    }
-    TMB_CUDA(cudaStreamSynchronize(stream));
     if (h_du_dx) {
         d_du_dx.copy_to(h_du_dx);
     }
@@ -353,6 +390,13 @@ void SummedPotential::advance(int n) {
         p->advance(n);
     }
 }
+bool SummedPotential::recover_overflow() {
+    bool any = false;
+    for (auto &p : potentials_) {
+        any = p->recover_overflow() || any; // every child gets to grow
+    }
+    return any;
+}
 
 FanoutSummedPotential::FanoutSummedPotential(std::vector<std::shared_ptr<Potential>> potentials, bool parallel)
     : potentials_(std::move(potentials)), parallel_(parallel), d_u_children_(potentials_.size()) {}
@@ -395,6 +439,13 @@ void FanoutSummedPotential::advance(int n) {
     for (auto &p : potentials_) {
         p->advance(n);
     }
+}
+bool FanoutSummedPotential::recover_overflow() {
+    bool any = false;
+    for (auto &p : potentials_) {
+        any = p->recover_overflow() || any;
+    }
+    return any;
 }
 
 void collect_nonbonded_cutoffs(const std::shared_ptr<Potential> &pot, std::vector<double> &out) {

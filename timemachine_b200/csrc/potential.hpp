@@ -98,6 +98,10 @@ public:
     virtual int capturable_steps() const { return 1 << 30; }
     // Advance host-side cadence counters as if execute_device had been called `n` times (graph replays).
     virtual void advance(int n) { (void)n; }
+    // Tile-list potentials size their list buffer from measured counts (neighborlist.cu); a build that ran out of room
+    // leaves a record on the device.  Called by the host after a synchronisation: true = the buffer was too small during
+    // the work just synchronised, it has been grown, and that work must be redone (its results miss interactions).
+    virtual bool recover_overflow() { return false; }
 
     void execute_host(
         int N, int P, const double *h_x, const double *h_p, const double *h_box, u64 *h_du_dx, u64 *h_du_dp, i128 *h_u);
@@ -133,6 +137,7 @@ public:
     void du_dp_fixed_to_float(int N, int P, const u64 *du_dp, double *out) const override;
     int capturable_steps() const override;
     void advance(int n) override;
+    bool recover_overflow() override;
 private:
     std::vector<std::shared_ptr<Potential>> potentials_;
     std::vector<int> params_sizes_;
@@ -150,6 +155,7 @@ public:
     void du_dp_fixed_to_float(int N, int P, const u64 *du_dp, double *out) const override;
     int capturable_steps() const override;
     void advance(int n) override;
+    bool recover_overflow() override;
 private:
     std::vector<std::shared_ptr<Potential>> potentials_;
     bool parallel_;
@@ -248,11 +254,18 @@ public:
                       const unsigned int *flag, cudaStream_t stream, const Snapshot *snap = nullptr);
 
     const TileList &tiles() const { return tiles_; }
+    // Host side of the measured sizing of the tile buffer: true when a build since the last call did not fit; the buffer
+    // has then been grown (to twice what was needed) and the caller must rebuild and redo whatever it evaluated.
+    bool recover_overflow();
+    size_t capacity() const { return tiles_.capacity; }
+    size_t worst_case_capacity() const { return worst_case_; }
     bool upper_triangular() const { return NR_ == N_ && NC_ == N_; }
     int num_row_blocks() const { return ceil_div(NR_, TILE); }
     int num_col_blocks() const { return ceil_div(NC_, TILE); }
 
 private:
+    void set_capacity(size_t tiles);
+    size_t worst_case_ = 0;
     const int max_size_;
     int N_, NC_, NR_;
     bool contiguous_ = true;
@@ -281,6 +294,9 @@ public:
     void set_kernel_timing(bool on);
     std::vector<float> drain_kernel_times(); // milliseconds per launch since the last drain (synchronises)
     void advance(int n) override { steps_since_last_sort_ += n; }
+    bool recover_overflow() override;
+    size_t tile_capacity() const { return nblist_.capacity(); }
+    size_t tile_worst_case() const { return nblist_.worst_case_capacity(); }
     double get_cutoff() const { return cutoff_; }
     double get_beta() const { return beta_; }
     double get_nblist_padding() const { return nblist_padding_; }
@@ -484,6 +500,7 @@ private:
     void run_steps(int n, cudaStream_t stream);
     void eager_step(cudaStream_t stream); // integrator step, then every mover (reference context.cu:261-277)
     void verify_frame(const double *h_x, const double *h_box) const;
+    void check_list_overflow();
     void destroy_graph();
     std::unique_ptr<LocalMD> local_md_;
     void run_local_steps(int n_steps, int n_samples, double *h_x, double *h_box, cudaStream_t stream);

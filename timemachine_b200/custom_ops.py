@@ -364,6 +364,12 @@ class _TiledExtras:
         _check(_L.tmb_nonbonded_num_rebuilds(self._handle, C.byref(n)))
         return n.value
 
+    def get_tile_capacity(self):
+        """(tiles the list buffer holds now, worst-case tiles the reference would allocate)"""
+        cap, worst = C.c_ulonglong(), C.c_ulonglong()
+        _check(_L.tmb_nonbonded_tile_capacity(self._handle, C.byref(cap), C.byref(worst)))
+        return cap.value, worst.value
+
     def set_kernel_timing(self, on: bool) -> None:
         _check(_L.tmb_nonbonded_set_kernel_timing(self._handle, int(bool(on))))
 
