@@ -46,14 +46,29 @@ def build_system(n_waters: int, n_lig: int, seed: int):
     rng = np.random.default_rng(seed)
     w = water_box(n_waters, seed=seed, jitter=0.01)
     L = w["box"][0, 0]
-    # ligand: self-avoiding chain around the box centre
+    # ligand: self-avoiding chain around the box centre with bond angles of 100-130 degrees.  (Round 1 accepted any angle
+    # the 0.2 nm contact rule allowed - up to 173 degrees - and used the as-built angles as equilibrium values: a harmonic
+    # angle within a few sigma of 180 degrees has a singular gradient, and the decoupled half of the ligand, which feels no
+    # solvent near lambda = 1, got there within ~10^4 steps: "simulation unstable" in the high-lambda windows of the
+    # 4- and 8-GPU runs.)
     lig = [np.full(3, L / 2)]
+    attempts = 0
     while len(lig) < n_lig:
+        attempts += 1
+        if attempts > 400:  # dead end: back up a few atoms and grow another way
+            del lig[max(1, len(lig) - 4):]
+            attempts = 0
         step = rng.normal(size=3)
         cand = lig[-1] + 0.14 * step / np.linalg.norm(step)
+        if len(lig) >= 2:
+            b1, b2 = lig[-2] - lig[-1], cand - lig[-1]
+            angle = np.degrees(np.arccos(np.clip(np.dot(b1, b2) / (np.linalg.norm(b1) * np.linalg.norm(b2)), -1.0, 1.0)))
+            if not 100.0 <= angle <= 130.0:
+                continue
         d = np.linalg.norm(np.array(lig[:-1] or [cand + 1.0]) - cand, axis=1)
         if np.all(d > 0.2) and np.linalg.norm(cand - L / 2) < 0.8:
             lig.append(cand)
+            attempts = 0
     lig = np.array(lig)
     # carve the cavity: drop waters whose oxygen is within 0.32 nm of a ligand atom
     xo = w["x"][0::3]
@@ -603,8 +618,9 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_ns_day = md_steps_total / float(t_e2e.item()) * 86400.0 * DT * 1e-3
     n_cand = 3 if world > 2 else world
-    # per frame and replica: x, v, box, parameters in for the MD call; x, box, all K parameter sets in for the U_kl row
-    h2d = (2 * N * 3 * 8 + 72 + P_total * 8) + (N * 3 * 8 + 72 + world * P_total * 8)
+    # per frame and replica: x, v, box, parameters in for the MD call; x, box and the parameter sets of the candidate states
+    # in for the U_kl row (execute_batch_sparse copies only the sets some pair refers to)
+    h2d = (2 * N * 3 * 8 + 72 + P_total * 8) + (N * 3 * 8 + 72 + n_cand * P_total * 8)
     d2h = (2 * N * 3 * 8 + 72) + 16 * n_cand
 
     # ---------------- roofline of the dominant kernel (k_nb_tiles of NonbondedAllPairs), rank 0 ----------------------------

@@ -184,14 +184,15 @@ pot = P.SummedPotential(
     [s["bond_params"], s["angle_params"], p])
 flat = np.concatenate([s["bond_params"].reshape(-1), s["angle_params"].reshape(-1), p.reshape(-1)])
 bp = ops.BoundPotential(pot.to_gpu(np.float32).unbound_impl, flat)
-ctx = ops.Context(x, np.zeros_like(x), box, ops.LangevinIntegrator(s["masses"], 300.0, 1e-3, 1.0, 1), [bp])
+intg = ops.LangevinIntegrator(s["masses"], 300.0, 1e-3, 1.0, 1)
+ctx = ops.Context(x, np.zeros_like(x), box, intg, [bp])
 msg = ""
 try:
-    ctx.multiple_steps(20)
+    xs, _ = ctx.multiple_steps(20)
 except RuntimeError as e:
     msg = str(e)
-    ctx.set_x_t(x); ctx.set_v_t(np.zeros_like(x))
-xs, _ = ctx.multiple_steps(20)
+    ctx.set_x_t(x); ctx.set_v_t(np.zeros_like(x)); intg.set_step(0)  # restore the state, noise stream included
+    xs, _ = ctx.multiple_steps(20)
 np.savez(sys.argv[1], dx=dx, dp=dp, u=u, cap0=cap0, cap1=cap1, worst=worst, T=T, n_ixn=sum(len(r) for r in ixn), msg=msg, xs=xs)
 """ % str(__import__("pathlib").Path(__file__).resolve().parents[1])
     import os

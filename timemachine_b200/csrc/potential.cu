@@ -1,6 +1,8 @@
 // Potential base-class host paths, BoundPotential, Summed/Fanout composition, stream fan-out.
 // Reference: potential.cu:10-328, bound_potential.cu:6-147, summed_potential.cu:33-99, fanout_summed_potential.cu:23-70.
 #include "potential.hpp"
+
+#include <mutex>
 #include "fixed_point.cuh"
 
 #include <algorithm>
@@ -71,6 +73,64 @@ void Potential::du_dp_fixed_to_float(int, int P, const u64 *du_dp, double *out) 
     }
 }
 
+// ---- cache of freed device blocks behind ScratchBuffer (potential.hpp) ------------------------------------------------
+namespace {
+struct ScratchCache {
+    std::mutex mu;
+    std::vector<std::pair<size_t, void *>> free_blocks; // (capacity, ptr)
+    size_t cached_bytes = 0;
+    ~ScratchCache() {
+        for (auto &b : free_blocks) {
+            cudaFree(b.second);
+        }
+    }
+};
+ScratchCache &scratch_cache() {
+    static ScratchCache c;
+    return c;
+}
+size_t scratch_capacity_for(size_t bytes) {
+    // size classes: powers of two from 256 B, so that a block serves every request of its class
+    size_t cap = 256;
+    while (cap < bytes) {
+        cap <<= 1;
+    }
+    return cap;
+}
+} // namespace
+
+void *scratch_alloc(size_t bytes) {
+    const size_t cap = scratch_capacity_for(bytes);
+    ScratchCache &c = scratch_cache();
+    {
+        std::lock_guard<std::mutex> lock(c.mu);
+        for (size_t i = 0; i < c.free_blocks.size(); i++) {
+            if (c.free_blocks[i].first == cap) {
+                void *p = c.free_blocks[i].second;
+                c.free_blocks[i] = c.free_blocks.back();
+                c.free_blocks.pop_back();
+                c.cached_bytes -= cap;
+                return p;
+            }
+        }
+    }
+    void *p = nullptr;
+    TMB_CUDA(cudaMalloc(&p, cap));
+    return p;
+}
+
+void scratch_free(void *ptr, size_t bytes) {
+    const size_t cap = scratch_capacity_for(bytes);
+    ScratchCache &c = scratch_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.cached_bytes + cap > (size_t(4) << 30)) { // keep at most 4 GiB parked
+        cudaFree(ptr);
+        return;
+    }
+    c.free_blocks.emplace_back(cap, ptr);
+    c.cached_bytes += cap;
+}
+
 // After a synchronised host-level evaluation: did a neighbour-list build run out of room (Potential::recover_overflow)?
 // Then the buffers have been grown and the evaluation is repeated from zeroed outputs.
 static bool redo_after_overflow(Potential &pot, int attempt) {
@@ -85,15 +145,15 @@ static bool redo_after_overflow(Potential &pot, int attempt) {
 
 void Potential::execute_host(
     int N, int P, const double *h_x, const double *h_p, const double *h_box, u64 *h_du_dx, u64 *h_du_dp, i128 *h_u) {
-    DeviceBuffer<double> d_x(static_cast<size_t>(N) * D), d_box(D * D), d_p(P);
+    ScratchBuffer<double> d_x(static_cast<size_t>(N) * D), d_box(D * D), d_p(P);
     d_x.copy_from(h_x);
     d_box.copy_from(h_box);
     if (P > 0) {
         d_p.copy_from(h_p);
     }
     cudaStream_t stream = main_stream();
-    DeviceBuffer<u64> d_du_dx, d_du_dp;
-    DeviceBuffer<i128> d_u;
+    ScratchBuffer<u64> d_du_dx, d_du_dp;
+    ScratchBuffer<i128> d_u;
     // the kernels accumulate: outputs must start at zero
     if (h_du_dx) {
         d_du_dx.realloc(static_cast<size_t>(N) * D);
@@ -130,7 +190,7 @@ void Potential::execute_host(
 void Potential::execute_batch_host(
     int coord_batch, int N, int param_batch, int P, const double *h_x, const double *h_p, const double *h_box,
     u64 *h_du_dx, u64 *h_du_dp, i128 *h_u) {
-    DeviceBuffer<double> d_p(static_cast<size_t>(param_batch) * P), d_box(static_cast<size_t>(coord_batch) * D * D),
+    ScratchBuffer<double> d_p(static_cast<size_t>(param_batch) * P), d_box(static_cast<size_t>(coord_batch) * D * D),
         d_x(static_cast<size_t>(coord_batch) * N * D);
     if (P > 0) {
         d_p.copy_from(h_p);
@@ -139,8 +199,8 @@ void Potential::execute_batch_host(
     d_x.copy_from(h_x);
     const size_t total = static_cast<size_t>(coord_batch) * param_batch;
     cudaStream_t stream = main_stream();
-    DeviceBuffer<u64> d_du_dx, d_du_dp;
-    DeviceBuffer<i128> d_u;
+    ScratchBuffer<u64> d_du_dx, d_du_dp;
+    ScratchBuffer<i128> d_u;
     if (h_du_dx) {
         d_du_dx.realloc(total * N * D);
     }
@@ -185,16 +245,32 @@ void Potential::execute_batch_sparse_host(
     int coords_size, int N, int params_size, int P, int batch_size, const unsigned int *coords_idxs,
     const unsigned int *params_idxs, const double *h_x, const double *h_p, const double *h_box, u64 *h_du_dx,
     u64 *h_du_dp, i128 *h_u) {
-    DeviceBuffer<double> d_p(static_cast<size_t>(params_size) * P), d_box(static_cast<size_t>(coords_size) * D * D),
+    ScratchBuffer<double> d_p(static_cast<size_t>(params_size) * P), d_box(static_cast<size_t>(coords_size) * D * D),
         d_x(static_cast<size_t>(coords_size) * N * D);
-    if (P > 0) {
-        d_p.copy_from(h_p);
+    // sparse batch: only the parameter sets and coordinate sets some pair refers to cross PCIe (an HREX rank evaluates its
+    // replica under 2-3 of K states: 3.4 MB per state at 30k atoms)
+    std::vector<char> p_used(params_size, 0), c_used(coords_size, 0);
+    for (int k = 0; k < batch_size; k++) {
+        if (coords_idxs[k] >= static_cast<unsigned int>(coords_size) || params_idxs[k] >= static_cast<unsigned int>(params_size)) {
+            throw std::runtime_error("batch index out of range");
+        }
+        c_used[coords_idxs[k]] = 1;
+        p_used[params_idxs[k]] = 1;
+    }
+    for (int j = 0; j < params_size && P > 0; j++) {
+        if (p_used[j]) {
+            TMB_CUDA(cudaMemcpy(d_p.data + static_cast<size_t>(j) * P, h_p + static_cast<size_t>(j) * P, sizeof(double) * P, cudaMemcpyHostToDevice));
+        }
+    }
+    for (int i = 0; i < coords_size; i++) {
+        if (c_used[i]) {
+            TMB_CUDA(cudaMemcpy(d_x.data + static_cast<size_t>(i) * N * D, h_x + static_cast<size_t>(i) * N * D, sizeof(double) * N * D, cudaMemcpyHostToDevice));
+        }
     }
     d_box.copy_from(h_box);
-    d_x.copy_from(h_x);
     cudaStream_t stream = main_stream();
-    DeviceBuffer<u64> d_du_dx, d_du_dp;
-    DeviceBuffer<i128> d_u;
+    ScratchBuffer<u64> d_du_dx, d_du_dp;
+    ScratchBuffer<i128> d_u;
     if (h_du_dx) {
         d_du_dx.realloc(static_cast<size_t>(batch_size) * N * D);
     }
@@ -267,12 +343,12 @@ void BoundPotential::execute_device(
 }
 
 void BoundPotential::execute_host(int N, const double *h_x, const double *h_box, u64 *h_du_dx, i128 *h_u) {
-    DeviceBuffer<double> d_x(static_cast<size_t>(N) * 3), d_box(9);
+    ScratchBuffer<double> d_x(static_cast<size_t>(N) * 3), d_box(9);
     d_x.copy_from(h_x);
     d_box.copy_from(h_box);
     cudaStream_t stream = main_stream();
-    DeviceBuffer<u64> d_du_dx;
-    DeviceBuffer<i128> d_u;
+    ScratchBuffer<u64> d_du_dx;
+    ScratchBuffer<i128> d_u;
     if (h_du_dx) {
         d_du_dx.realloc(static_cast<size_t>(N) * 3);
     }
@@ -297,12 +373,12 @@ void BoundPotential::execute_host(int N, const double *h_x, const double *h_box,
 }
 
 void BoundPotential::execute_batch_host(int coord_batch, int N, const double *h_x, const double *h_box, u64 *h_du_dx, i128 *h_u) {
-    DeviceBuffer<double> d_x(static_cast<size_t>(coord_batch) * N * 3), d_box(static_cast<size_t>(coord_batch) * 9);
+    ScratchBuffer<double> d_x(static_cast<size_t>(coord_batch) * N * 3), d_box(static_cast<size_t>(coord_batch) * 9);
     d_x.copy_from(h_x);
     d_box.copy_from(h_box);
     cudaStream_t stream = main_stream();
-    DeviceBuffer<u64> d_du_dx;
-    DeviceBuffer<i128> d_u;
+    ScratchBuffer<u64> d_du_dx;
+    ScratchBuffer<i128> d_u;
     if (h_du_dx) {
         d_du_dx.realloc(static_cast<size_t>(coord_batch) * N * 3);
     }

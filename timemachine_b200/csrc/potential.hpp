@@ -65,6 +65,57 @@ public:
     }
 };
 
+// Temporaries of the host-buffer entry points (execute / execute_batch / execute_batch_sparse copy their arguments to
+// the device on every call, reference potential.cu:70-320).  The reference cudaMallocs and cudaFrees them per call; both
+// are device-wide synchronisation points whose cost varies by an order of magnitude from process to process (measured:
+// 2 ms vs 56 ms per execute_batch_sparse of the 30k-atom system next to instantiated CUDA graphs).  These buffers come
+// from a process-wide cache of freed blocks instead: after the first call of a given size no driver allocation happens.
+void *scratch_alloc(size_t bytes);
+void scratch_free(void *ptr, size_t bytes);
+
+template <typename T> class ScratchBuffer {
+public:
+    T *data = nullptr;
+    size_t length = 0;
+
+    ScratchBuffer() = default;
+    explicit ScratchBuffer(size_t n) { realloc(n); }
+    ScratchBuffer(const ScratchBuffer &) = delete;
+    ScratchBuffer &operator=(const ScratchBuffer &) = delete;
+    ~ScratchBuffer() { release(); }
+
+    void release() {
+        if (data != nullptr) {
+            scratch_free(data, length * sizeof(T));
+            data = nullptr;
+            length = 0;
+        }
+    }
+    void realloc(size_t n) {
+        release();
+        if (n > 0) {
+            data = static_cast<T *>(scratch_alloc(n * sizeof(T)));
+        }
+        length = n;
+    }
+    size_t bytes() const { return length * sizeof(T); }
+    void zero(cudaStream_t s = nullptr) {
+        if (length) {
+            TMB_CUDA(cudaMemsetAsync(data, 0, bytes(), s));
+        }
+    }
+    void copy_from(const T *host) {
+        if (length) {
+            TMB_CUDA(cudaMemcpy(data, host, bytes(), cudaMemcpyHostToDevice));
+        }
+    }
+    void copy_to(T *host) const {
+        if (length) {
+            TMB_CUDA(cudaMemcpy(host, data, bytes(), cudaMemcpyDeviceToHost));
+        }
+    }
+};
+
 // Fork/join of per-child streams (reference stream_manager.cu:18-56)
 class StreamFan {
 public:
