@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace tmb {
 
@@ -46,7 +47,7 @@ void LangevinIntegrator::set_external_noise(const float *h_noise) {
 
 void LangevinIntegrator::step_fwd(
     std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box, unsigned int *d_idxs,
-    cudaStream_t stream, int graph_offset) {
+    cudaStream_t stream, int graph_offset, Potential *fusable) {
     const int n = static_cast<int>(bps.size());
     // one stream per bound potential, forked from and joined back into `stream`
     // (reference streamed_potential_runner.cu:10-29)
@@ -78,7 +79,20 @@ void LangevinIntegrator::step_fwd(
     a.v = d_v;
     a.du_dx = d_du_dx_.data;
     a.dt = dt_;
-    launch_baoab(a, stream);
+    FusedPrepareHook hook;
+    if (fusable != nullptr && d_idxs == nullptr && fusable->fused_prepare_hook(hook)) {
+        // integrate in the potential's sorted order and leave its next prepare pass done (k_baoab_prepare)
+        if (hook.is_double) {
+            hook.f64.box = d_box;
+            launch_baoab_prepare<double>(a, hook.f64, stream);
+        } else {
+            hook.f32.box = d_box;
+            launch_baoab_prepare<float>(a, hook.f32, stream);
+        }
+        fusable->skip_next_prepare();
+    } else {
+        launch_baoab(a, stream);
+    }
     step_++;
 }
 
@@ -88,6 +102,41 @@ void LangevinIntegrator::publish_step_base(cudaStream_t stream) {
 
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GRAPH_STEPS = 10;
+
+// The first potential (depth first) that can hand its prepare pass to the integrator: the all-pairs term of the system.
+static Potential *find_fusable(const std::shared_ptr<Potential> &pot) {
+    if (auto s = std::dynamic_pointer_cast<SummedPotential>(pot)) {
+        for (auto &c : s->get_potentials()) {
+            if (Potential *p = find_fusable(c)) {
+                return p;
+            }
+        }
+        return nullptr;
+    }
+    if (auto f = std::dynamic_pointer_cast<FanoutSummedPotential>(pot)) {
+        for (auto &c : f->get_potentials()) {
+            if (Potential *p = find_fusable(c)) {
+                return p;
+            }
+        }
+        return nullptr;
+    }
+    if (std::dynamic_pointer_cast<NonbondedAllPairs<float>>(pot) || std::dynamic_pointer_cast<NonbondedAllPairs<double>>(pot)) {
+        return pot.get();
+    }
+    return nullptr;
+}
+
+static bool fuse_prepare_enabled() {
+    static const bool on = [] {
+        // Measured and NOT adopted (profiles/r2_summary.md section 7): integrating in the potential's sorted order makes the
+        // 72 B per atom of x / v / du_dx traffic a gather (32-byte sectors, 24-byte rows), and the fused launch costs more than
+        // the two coalesced ones it replaces: 145.2 against 139.2 us per MD step.  TMB_FUSE_PREPARE=1 selects it for A/B runs.
+        const char *e = std::getenv("TMB_FUSE_PREPARE");
+        return e != nullptr && e[0] == '1';
+    }();
+    return on;
+}
 
 Context::Context(
     int N, const double *x0, const double *v0, const double *box0, std::shared_ptr<LangevinIntegrator> intg,
@@ -145,9 +194,20 @@ void Context::run_steps(int n, cudaStream_t stream) {
                 const long long intg_step_before = intg_->step_count();
                 TMB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
                 int captured = 0;
+                // inside the block the integrator of step s also runs the all-pairs potential's prepare pass of step
+                // s + 1 (the block's last step does not: what follows the block is not known here)
+                Potential *fusable = nullptr;
+                if (fuse_prepare_enabled()) {
+                    for (auto &bp : bps_) {
+                        if ((fusable = find_fusable(bp->potential)) != nullptr) {
+                            break;
+                        }
+                    }
+                }
                 try {
                     for (int s = 0; s < GRAPH_STEPS; s++) {
-                        intg_->step_fwd(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream, s);
+                        intg_->step_fwd(
+                            bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream, s, s + 1 < GRAPH_STEPS ? fusable : nullptr);
                         captured++;
                     }
                     TMB_CUDA(cudaStreamEndCapture(stream, &graph));
@@ -165,6 +225,9 @@ void Context::run_steps(int n, cudaStream_t stream) {
                     }
                     cudaGetLastError();
                     graph_exec_ = nullptr;
+                    if (fusable != nullptr) {
+                        fusable->cancel_skip_prepare();
+                    }
                     for (auto &bp : bps_) {
                         bp->potential->advance(-captured);
                     }

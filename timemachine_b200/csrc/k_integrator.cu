@@ -13,6 +13,7 @@
 // in registers: no noise buffer in HBM, no extra launches, and a trajectory is reproducible from (seed, step) alone.
 // The two generators cannot produce the same stream, so integrator parity is tested at friction = 0 (cc = 0), as the
 // reference's own tests/test_md.py:174-178 does, or with an externally supplied noise buffer.
+#include "block_bounds.cuh"
 #include "fixed_point.cuh"
 #include "kernels.hpp"
 
@@ -58,37 +59,111 @@ __device__ __forceinline__ void normal3(unsigned long long seed, unsigned long l
     (void)sb;
 }
 
+// One atom: the mixed-precision update of the file header; returns the new coordinates.
+__device__ __forceinline__ void baoab_atom(const BaoabArgs &a, const int atom, const unsigned long long step, double out[3]) {
+    const float cb = a.cbs[atom];
+    const float cc = a.ccs[atom];
+    float xi[3];
+    if (a.noise != nullptr) {
+        xi[0] = a.noise[atom * 3 + 0];
+        xi[1] = a.noise[atom * 3 + 1];
+        xi[2] = a.noise[atom * 3 + 2];
+    } else {
+        normal3(a.seed, step, static_cast<unsigned int>(atom), xi[0], xi[1], xi[2]);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const int q = atom * 3 + d;
+        const float force = -fixed_to_real<float>(a.du_dx[q]);
+        const float v_mid = static_cast<float>(a.v[q] + static_cast<double>(cb * force));
+        const float v_new = a.ca * v_mid + cc * xi[d];
+        const double v_new_d = static_cast<double>(v_new);
+        a.v[q] = v_new_d;
+        const double x_new = a.x[q] + static_cast<double>(0.5f * a.dt) * (static_cast<double>(v_mid) + v_new_d);
+        a.x[q] = x_new;
+        out[d] = x_new;
+        a.du_dx[q] = 0;
+    }
+}
+
 __global__ void __launch_bounds__(INT_THREADS) k_baoab(const BaoabArgs a) {
     const unsigned long long step = a.step + (a.step_base != nullptr ? *a.step_base : 0ull);
     for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < a.N; tid += gridDim.x * blockDim.x) {
         const int atom = a.idxs == nullptr ? tid : static_cast<int>(a.idxs[tid]);
         if (atom < a.N) {
-            const float cb = a.cbs[atom];
-            const float cc = a.ccs[atom];
-            float xi[3];
-            if (a.noise != nullptr) {
-                xi[0] = a.noise[atom * 3 + 0];
-                xi[1] = a.noise[atom * 3 + 1];
-                xi[2] = a.noise[atom * 3 + 2];
-            } else {
-                normal3(a.seed, step, static_cast<unsigned int>(atom), xi[0], xi[1], xi[2]);
-            }
-#pragma unroll
-            for (int d = 0; d < 3; d++) {
-                const int q = atom * 3 + d;
-                const float force = -fixed_to_real<float>(a.du_dx[q]);
-                const float v_mid = static_cast<float>(a.v[q] + static_cast<double>(cb * force));
-                const float v_new = a.ca * v_mid + cc * xi[d];
-                const double v_new_d = static_cast<double>(v_new);
-                a.v[q] = v_new_d;
-                a.x[q] += static_cast<double>(0.5f * a.dt) * (static_cast<double>(v_mid) + v_new_d);
-                a.du_dx[q] = 0;
-            }
+            double xn[3];
+            baoab_atom(a, atom, step, xn);
         } else if (a.idxs != nullptr) {
             // local-MD convention: idxs[tid] == N marks a frozen atom; its force slot still has to be cleared
             a.du_dx[tid * 3 + 0] = 0;
             a.du_dx[tid * 3 + 1] = 0;
             a.du_dx[tid * 3 + 2] = 0;
+        }
+    }
+}
+
+// BAOAB over the sorted slots of an all-pairs potential + that potential's next k_nb_prepare (kernels.hpp).  Thread k of
+// the first Kpad threads owns slot k (warp = 32-atom block, as in k_nb_prepare); the threads behind them integrate the
+// atoms that are not in the potential's set.  The prepare half is k_nb_prepare's code path for force_rebuild == 0 with the
+// parameter-derived fields (w, qse) left as the block's first prepare wrote them.
+template <typename Real> __global__ void __launch_bounds__(INT_THREADS) k_baoab_prepare(const BaoabArgs a, const FusedPrepareArgs<Real> f) {
+    const unsigned long long step = a.step + (a.step_base != nullptr ? *a.step_base : 0ull);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kpad = (f.K + WARP - 1) / WARP * WARP;
+    if (k >= kpad) {
+        const int o = k - kpad;
+        if (o < f.n_others) {
+            double xn[3];
+            baoab_atom(a, static_cast<int>(f.others[o]), step, xn);
+        }
+        return;
+    }
+    bool rebuild = false;
+    if (k == 0) {
+        *f.tile_cursor = 0;
+    }
+    double dbox = 0;
+    for (int c = 0; c < 3; c++) {
+        const double dc = f.box[c * 4] - f.box_build[c * 4];
+        dbox += dc * dc;
+    }
+    dbox = sqrt(dbox);
+    rebuild = rebuild || !(dbox < f.padding);
+    if (k < 9 && (k % 4) != 0) {
+        rebuild = rebuild || (f.box[k] != f.box_build[k]);
+    }
+    const double half_room = 0.5 * (f.padding - dbox);
+    Vec4<Real> c = {0, 0, 0, 0};
+    if (k < f.K) {
+        double xn[3];
+        baoab_atom(a, static_cast<int>(f.perm[k]), step, xn);
+        c.x = static_cast<Real>(xn[0]);
+        c.y = static_cast<Real>(xn[1]);
+        c.z = static_cast<Real>(xn[2]);
+        c.w = f.xw[k].w;
+        f.xw[k] = c;
+        const Vec4<Real> o = f.xw_build[k];
+        const Real dx = o.x - c.x;
+        const Real dy = o.y - c.y;
+        const Real dz = o.z - c.z;
+        const Real d2 = dx * dx + dy * dy + dz * dz;
+        rebuild = rebuild || (static_cast<double>(d2) > half_room * half_room);
+    }
+    if (rebuild) {
+        *f.flag = 1;
+        *f.reset_count = 0;
+        *f.reset_overflow = 0;
+    }
+    const int block = k / WARP;
+    const Real bx = static_cast<Real>(f.box[0]);
+    const Real by = static_cast<Real>(f.box[4]);
+    const Real bz = static_cast<Real>(f.box[8]);
+    Real ctr[3], ext[3];
+    warp_block_bounds_anchor<Real>(c.x, c.y, c.z, f.K - block * WARP, bx, by, bz, 1 / bx, 1 / by, 1 / bz, ctr, ext);
+    if ((threadIdx.x & 31) == 0) {
+        for (int d = 0; d < 3; d++) {
+            f.ctr[block * 3 + d] = ctr[d];
+            f.ext[block * 3 + d] = ext[d];
         }
     }
 }
@@ -99,6 +174,14 @@ void launch_baoab(const BaoabArgs &args, cudaStream_t stream) {
     }
     TMB_LAUNCH(k_baoab, ceil_div(args.N, INT_THREADS), INT_THREADS, 0, stream, args);
 }
+
+template <typename Real> void launch_baoab_prepare(const BaoabArgs &args, const FusedPrepareArgs<Real> &f, cudaStream_t stream) {
+    const int kpad = (f.K + WARP - 1) / WARP * WARP;
+    const int threads = kpad + f.n_others;
+    TMB_LAUNCH(k_baoab_prepare<Real>, ceil_div(threads, INT_THREADS), INT_THREADS, 0, stream, args, f);
+}
+template void launch_baoab_prepare<float>(const BaoabArgs &, const FusedPrepareArgs<float> &, cudaStream_t);
+template void launch_baoab_prepare<double>(const BaoabArgs &, const FusedPrepareArgs<double> &, cudaStream_t);
 
 // N x 3 standard normals with the same generator (used by tests to inspect the noise distribution)
 __global__ void k_fill_normal(float *__restrict__ out, const int n_atoms, const unsigned long long seed, const unsigned long long step) {

@@ -203,6 +203,30 @@ struct BaoabArgs {
     float dt;
 };
 void launch_baoab(const BaoabArgs &args, cudaStream_t stream);
+
+// BAOAB fused with the NEXT evaluation's k_nb_prepare of an all-pairs potential (Context: steps 0..8 of a 10-step graph
+// block).  The integrator walks the potential's sorted slots (a warp = a 32-atom block), integrates atom perm[k] and, with
+// the new coordinates still in registers, writes the packed sorted copy xw[k], makes the displacement / rebuild decision
+// and the block bounds exactly as k_nb_prepare would on the next step; atoms outside the potential's set come from
+// `others`.  The potential then skips its own prepare launch: one streaming pass and one launch less on the critical path.
+template <typename Real> struct FusedPrepareArgs {
+    int K;                      // slots of the all-pairs potential
+    const unsigned int *perm;   // [K] slot -> atom
+    const unsigned int *others; // [n_others] atoms that are not in perm
+    int n_others;
+    Vec4<Real> *xw;             // [Kpad] in/out: w is kept (parameters do not change inside a block)
+    const Vec4<Real> *xw_build;
+    const double *box;
+    const double *box_build;
+    double padding;
+    unsigned int *flag;
+    unsigned int *tile_cursor;
+    Real *ctr;
+    Real *ext;
+    unsigned int *reset_count;
+    unsigned int *reset_overflow;
+};
+template <typename Real> void launch_baoab_prepare(const BaoabArgs &args, const FusedPrepareArgs<Real> &f, cudaStream_t stream);
 void launch_fill_normal(float *out, int n, unsigned long long seed, unsigned long long step, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <numeric>
+#include <type_traits>
 
 namespace tmb {
 
@@ -131,6 +132,9 @@ void NonbondedTiled<Real>::run(
         force = 1;
     }
     force_rebuild_ = false;
+    // the integrator of the previous step already ran this evaluation's prepare pass (only honoured for a plain evaluation)
+    const bool prepared = skip_prepare_once_ && force == 0;
+    skip_prepare_once_ = false;
 
     NbPrepareArgs<Real> pa;
     pa.K = K_;
@@ -155,7 +159,9 @@ void NonbondedTiled<Real>::run(
         pa.reset_count = nblist_.tiles().count;
         pa.reset_overflow = nblist_.tiles().overflow;
     }
-    launch_nb_prepare<Real>(pa, stream);
+    if (!prepared) {
+        launch_nb_prepare<Real>(pa, stream);
+    }
 
     const unsigned int *flag = d_flags_.data;
     typename Neighborlist<Real>::Snapshot snap{d_xw_build_.data, d_box_build_.data, fuse_bounds, K_};
@@ -251,12 +257,57 @@ template <typename Real> void NonbondedAllPairs<Real>::set_atom_idxs(const std::
     verify_atom_idxs(this->N_, atom_idxs);
     std::vector<unsigned int> u(atom_idxs.begin(), atom_idxs.end());
     TMB_CUDA(cudaMemcpy(d_atom_idxs_.data, u.data(), u.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    {
+        std::vector<char> in_set(this->N_, 0);
+        for (unsigned int a : u) {
+            in_set[a] = 1;
+        }
+        std::vector<unsigned int> others;
+        for (int a = 0; a < this->N_; a++) {
+            if (!in_set[a]) {
+                others.push_back(static_cast<unsigned int>(a));
+            }
+        }
+        n_others_ = static_cast<int>(others.size());
+        d_other_idxs_.realloc(others.size());
+        d_other_idxs_.copy_from(others.data());
+    }
     this->K_ = static_cast<int>(u.size());
     this->NR_ = this->K_;
     this->nblist_.set_all_pairs(this->K_);
     this->steps_since_last_sort_ = 0; // forces a sort, hence a rebuild, on the next evaluation
     this->force_rebuild_ = true;
     bump_launch_generation(); // K_, NR_ and the grid sizes are baked into captured launches
+}
+
+template <typename Real> bool NonbondedAllPairs<Real>::fused_prepare_hook(FusedPrepareHook &hook) {
+    if (this->timing_ || this->force_rebuild_ || this->needs_sort()) {
+        return false; // the next evaluation is not a plain one
+    }
+    FusedPrepareArgs<Real> f;
+    f.K = this->K_;
+    f.perm = this->d_perm_.data;
+    f.others = d_other_idxs_.data;
+    f.n_others = n_others_;
+    f.xw = this->d_xw_.data;
+    f.xw_build = this->d_xw_build_.data;
+    f.box = nullptr; // filled by the caller (the Context's box)
+    f.box_build = this->d_box_build_.data;
+    f.padding = this->nblist_padding_;
+    f.flag = this->d_flags_.data;
+    f.tile_cursor = this->d_flags_.data + 1;
+    f.ctr = this->nblist_.col_ctr();
+    f.ext = this->nblist_.col_ext();
+    f.reset_count = this->nblist_.tiles().count;
+    f.reset_overflow = this->nblist_.tiles().overflow;
+    if constexpr (std::is_same<Real, double>::value) {
+        hook.is_double = true;
+        hook.f64 = f;
+    } else {
+        hook.is_double = false;
+        hook.f32 = f;
+    }
+    return true;
 }
 
 template <typename Real> std::vector<int> NonbondedAllPairs<Real>::get_atom_idxs() {

@@ -131,6 +131,14 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// What the integrator needs to run an all-pairs potential's next k_nb_prepare inside its own kernel (kernels.hpp,
+// launch_baoab_prepare); filled by NonbondedAllPairs::fused_prepare_hook.
+struct FusedPrepareHook {
+    bool is_double = false;
+    FusedPrepareArgs<float> f32{};
+    FusedPrepareArgs<double> f64{};
+};
+
 class Potential {
 public:
     virtual ~Potential() = default;
@@ -153,6 +161,15 @@ public:
     // leaves a record on the device.  Called by the host after a synchronisation: true = the buffer was too small during
     // the work just synchronised, it has been grown, and that work must be redone (its results miss interactions).
     virtual bool recover_overflow() { return false; }
+    // Fusion of the integrator with the next evaluation's gather / rebuild decision (Context, inside CUDA-graph blocks):
+    // a potential that can hand its prepare pass to the integrator fills `hook` and returns true; skip_next_prepare()
+    // tells it that its NEXT execute_device finds that pass already done.
+    virtual bool fused_prepare_hook(FusedPrepareHook &hook) {
+        (void)hook;
+        return false;
+    }
+    virtual void skip_next_prepare() {}
+    virtual void cancel_skip_prepare() {}
 
     void execute_host(
         int N, int P, const double *h_x, const double *h_p, const double *h_box, u64 *h_du_dx, u64 *h_du_dp, i128 *h_u);
@@ -363,6 +380,7 @@ protected:
     const int steps_per_sort_;
     long long steps_since_last_sort_ = 0;
     bool force_rebuild_ = true;
+    bool skip_prepare_once_ = false; // the integrator ran this evaluation's prepare pass (fused_prepare_hook)
     bool timing_ = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events_;
     size_t timing_used_ = 0;
@@ -392,10 +410,15 @@ public:
     void set_atom_idxs(const std::vector<int> &atom_idxs);
     std::vector<int> get_atom_idxs();
     int get_num_atom_idxs() const { return this->K_; }
+    bool fused_prepare_hook(FusedPrepareHook &hook) override;
+    void skip_next_prepare() override { this->skip_prepare_once_ = true; }
+    void cancel_skip_prepare() override { this->skip_prepare_once_ = false; }
 protected:
     void sort(const double *d_x, const double *d_box, cudaStream_t stream) override;
 private:
     DeviceBuffer<unsigned int> d_atom_idxs_;
+    DeviceBuffer<unsigned int> d_other_idxs_; // atoms NOT in the set (the integrator's fused pass covers them too)
+    int n_others_ = 0;
 };
 
 template <typename Real> class NonbondedInteractionGroup : public NonbondedTiled<Real> {
@@ -438,8 +461,10 @@ public:
     // One force evaluation + BAOAB update on `stream` (reference langevin_integrator.cu:55-88)
     // graph_offset >= 0: the call is being captured into a CUDA graph; the noise counter is then
     // *d_step_base + graph_offset so that replays draw fresh noise.
+    // fusable: a potential whose next prepare pass this step's update kernel takes over (Potential::fused_prepare_hook), or
+    // null
     void step_fwd(std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box,
-                  unsigned int *d_idxs, cudaStream_t stream, int graph_offset = -1);
+                  unsigned int *d_idxs, cudaStream_t stream, int graph_offset = -1, Potential *fusable = nullptr);
     void publish_step_base(cudaStream_t stream);   // *d_step_base = step_
     void set_external_noise(const float *h_noise); // tests: N x 3 normals reused every step; nullptr restores Philox
     long long step_count() const { return step_; }
