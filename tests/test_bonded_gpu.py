@@ -154,6 +154,11 @@ def test_bonded_against_reference_custom_ops(precision, rtol, rng):
         assert_forces_close(rdx, dx, rtol, what=name)
         np.testing.assert_allclose(dp, rdp, rtol=rtol * 10, atol=rtol * 10 * max(1.0, np.abs(rdp).max()))
         np.testing.assert_allclose(u, ru, rtol=rtol * 10)
+        if precision == np.float32:
+            # the f32 kernels reproduce the reference's operation sequence (its FMA contraction is written out in k_bonded.cu)
+            np.testing.assert_array_equal(dx, rdx, err_msg=name)
+            np.testing.assert_array_equal(dp, rdp, err_msg=name)
+            assert u == ru, name
 
 
 @pytest.mark.parametrize("precision", [np.float32, np.float64])
@@ -187,10 +192,8 @@ def test_bonded_far_from_the_origin(precision, rng):
         assert_forces_close(odx, dx, 1e-4 if precision == np.float32 else 1e-9, what=name + " vs f64 oracle, offset 10 nm")
         if ref is not None:
             rdx, rdp, ru = getattr(ref, f"{name}_{suffix}")(idxs).execute(x, params, box)
-            if name == "HarmonicBond" and precision == np.float32:
-                # the bond kernel reproduces the reference's operation sequence (the same FMA chain for |d|^2)
-                np.testing.assert_array_equal(dx, rdx, err_msg="HarmonicBond forces are not bitwise the compiled reference's")
-            # angle / torsion: same formulas, the compilers contract them differently; on these stiff terms an ulp of a
-            # length is 2e-5 of the force
-            assert_forces_close(rdx, dx, 1e-4 if precision == np.float32 else 1e-10, what=name + " vs compiled reference, offset 10 nm")
+            if precision == np.float32:
+                # the f32 kernels reproduce the reference's operation sequence
+                np.testing.assert_array_equal(dx, rdx, err_msg=name + ": forces are not bitwise the compiled reference's")
+            assert_forces_close(rdx, dx, 1e-10, what=name + " vs compiled reference, offset 10 nm")
             np.testing.assert_allclose(u, ru, rtol=1e-4 if precision == np.float32 else 1e-9)

@@ -32,8 +32,9 @@ template <typename Real> __device__ __forceinline__ V3<Real> delta3(const double
     r.z = static_cast<Real>(x[a * 3 + 2] - x[b * 3 + 2]);
     return r;
 }
+// a.b as nvcc contracts the reference's `a[0]*b[0] + a[1]*b[1] + a[2]*b[2]` (the left product of each sum is fused)
 template <typename Real> __device__ __forceinline__ Real dot3(const V3<Real> &a, const V3<Real> &b) {
-    return a.x * b.x + a.y * b.y + a.z * b.z;
+    return fma(a.z, b.z, fma(a.x, b.x, a.y * b.y));
 }
 template <typename Real> __device__ __forceinline__ V3<Real> cross3(const V3<Real> &a, const V3<Real> &b) {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
@@ -98,14 +99,16 @@ template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_harmoni
         const V3<Real> vjk = delta3<Real>(a.x, k, j);
         const Real rji[4] = {vji.x, vji.y, vji.z, eps};
         const Real rjk[4] = {vjk.x, vjk.y, vjk.z, eps};
-        Real sji = 0, sjk = 0;
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            sji += rji[d] * rji[d];
-            sjk += rjk[d] * rjk[d];
-        }
-        const Real nji = sqrt(sji + eps * eps);
-        const Real njk = sqrt(sjk + eps * eps);
+        // From here to the gradient every operation is written out with its rounding, in the order nvcc emits for the
+        // reference's k_harmonic_angle (default -fmad there; read off the SASS of oracle/_ref/obj/harmonic_angle.o): squares
+        // are separate products (they are reused by the dot products), sums of squares are plain adds, every other
+        // sum of products is an FMA chain that fuses the LEFT product of each `x*y + z*w`.  With it the f32 angle term is
+        // the same sequence of rounded operations as the reference's.
+        const Real eps2 = eps * eps;
+        const Real sji = ((rji[0] * rji[0] + rji[1] * rji[1]) + rji[2] * rji[2]) + eps2; // = a.a below, bit for bit
+        const Real sjk = ((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]) + eps2; // = b.b
+        const Real nji = sqrt(sji);
+        const Real njk = sqrt(sjk);
 
         Real hi = 0, lo = 0;
 #pragma unroll
@@ -114,29 +117,27 @@ template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_harmoni
             const Real q = nji * rjk[d];
             const Real m = p - q;
             const Real s = p + q;
-            hi += m * m;
-            lo += s * s;
+            hi = fma(m, m, hi);
+            lo = fma(s, s, lo);
         }
         const Real theta = 2 * atan2(sqrt(hi), sqrt(lo));
         const Real delta = theta - a0;
 
         // gradient direction via a x (b x c) = b (a.c) - c (a.b), in 4-D
-        Real a_dot_b = 0, a_dot_a = 0, b_dot_b = 0;
-#pragma unroll
-        for (int d = 0; d < 4; d++) {
-            a_dot_b += rji[d] * rjk[d];
-            a_dot_a += rji[d] * rji[d];
-            b_dot_b += rjk[d] * rjk[d];
-        }
+        const Real a_dot_b = eps2 + fma(rji[2], rjk[2], fma(rji[0], rjk[0], rji[1] * rjk[1]));
+        const Real a_dot_a = sji;
+        const Real b_dot_b = sjk;
         Real aab[4], bba[4];
-        Real aab2 = 0, bba2 = 0;
 #pragma unroll
-        for (int d = 0; d < 4; d++) {
-            aab[d] = rji[d] * a_dot_b - rjk[d] * a_dot_a;
-            bba[d] = rjk[d] * a_dot_b - rji[d] * b_dot_b;
-            aab2 += aab[d] * aab[d];
-            bba2 += bba[d] * bba[d];
+        for (int d = 0; d < 3; d++) {
+            aab[d] = fma(rji[d], a_dot_b, -(rjk[d] * a_dot_a));
+            bba[d] = fma(rjk[d], a_dot_b, -(rji[d] * b_dot_b));
         }
+        const Real eps_adb = eps * a_dot_b;
+        aab[3] = fma(eps, -a_dot_a, eps_adb);
+        bba[3] = fma(eps, -b_dot_b, eps_adb);
+        const Real aab2 = fma(aab[3], aab[3], fma(aab[2], aab[2], fma(aab[0], aab[0], aab[1] * aab[1])));
+        const Real bba2 = fma(bba[3], bba[3], fma(bba[2], bba[2], fma(bba[0], bba[0], bba[1] * bba[1])));
         const Real aab_n = sqrt(aab2);
         const Real bba_n = sqrt(bba2);
         const Real pref = ka * delta;
@@ -184,7 +185,12 @@ template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_periodi
         V3<Real> rkj = delta3<Real>(a.x, j, k);
         const V3<Real> rkl = delta3<Real>(a.x, l, k);
 
-        const Real rkj2 = dot3(rkj, rkj);
+        // As in the angle kernel: the operation sequence nvcc emits for the reference's k_periodic_torsion (read off the SASS of
+        // oracle/_ref/obj/periodic_torsion.o).  Cross products are products then a subtraction (the reference forces that
+        // with rmul_rn for bitwise anticommutativity); every dot product is fma(z, z', fma(x, x', y * y')); |r_kj|^2 is formed
+        // twice by the reference's source, in two different associations, and both are kept.
+        const Real rkj_yy = rkj.y * rkj.y;
+        const Real rkj2 = fma(rkj.z, rkj.z, rkj.x * rkj.x + rkj_yy);
         const Real rkj_n = sqrt(rkj2);
         const V3<Real> n1 = cross3(rij, rkj);
         const V3<Real> n2 = cross3(rkj, rkl);
@@ -196,6 +202,8 @@ template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_periodi
 
         const Real c0 = rkj_n / n1_2;
         const Real c3 = -rkj_n / n2_2;
+        const Real q1m1 = rij_rkj / rkj2 - 1;
+        const Real q2m1 = rkl_rkj / rkj2 - 1;
         const Real n1v[3] = {n1.x, n1.y, n1.z};
         const Real n2v[3] = {n2.x, n2.y, n2.z};
         Real dR0[3], dR1[3], dR2[3], dR3[3];
@@ -203,18 +211,19 @@ template <typename Real> __global__ void __launch_bounds__(BD_THREADS) k_periodi
         for (int d = 0; d < 3; d++) {
             dR0[d] = c0 * n1v[d];
             dR3[d] = c3 * n2v[d];
-            dR1[d] = (rij_rkj / rkj2 - 1) * dR0[d] - dR3[d] * rkl_rkj / rkj2;
-            dR2[d] = (rkl_rkj / rkj2 - 1) * dR3[d] - dR0[d] * rij_rkj / rkj2;
+            dR1[d] = fma(q1m1, dR0[d], -((dR3[d] * rkl_rkj) / rkj2));
+            dR2[d] = fma(q2m1, dR3[d], -((dR0[d] * rij_rkj) / rkj2));
         }
-        rkj.x /= rkj_n;
-        rkj.y /= rkj_n;
-        rkj.z /= rkj_n;
+        const Real rkj_n2 = sqrt(fma(rkj.z, rkj.z, fma(rkj.x, rkj.x, rkj_yy)));
+        rkj.x /= rkj_n2;
+        rkj.y /= rkj_n2;
+        rkj.z /= rkj_n2;
         const Real phi = atan2(dot3(n3, rkj), dot3(n1, n2));
 
         const Real kt = static_cast<Real>(a.p[t * 3 + 0]);
         const Real phase = static_cast<Real>(a.p[t * 3 + 1]);
         const Real period = static_cast<Real>(a.p[t * 3 + 2]);
-        const Real arg = period * phi - phase;
+        const Real arg = fma(period, phi, -phase);
         const Real pref = kt * sin(arg) * period;
 
         if (a.du_dx != nullptr) {
