@@ -744,12 +744,36 @@ def main():
         dist.destroy_process_group()
 
 
+def _error_line(msg: str) -> None:
+    """Rank 0 answers with a JSON line even when the run dies (the driver parses stdout)."""
+    try:
+        os.write(_REAL_STDOUT, (json.dumps({"metric": "ns_per_day", "value": None, "unit": "ns/day", "error": msg[:2000]}) + "\n").encode())
+    except OSError:
+        pass
+
+
+_REAL_STDOUT = os.dup(1)
+
 if __name__ == "__main__":
+    _rank = os.environ.get("RANK", "0")
+    if _rank == "0" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import signal
+
+        def _terminated(signum, frame):  # torchrun stops the surviving ranks when one of them has failed
+            _error_line("terminated by the launcher: another rank failed, its traceback is on stderr ([bench rank N] FAILED)")
+            os._exit(1)
+
+        signal.signal(signal.SIGTERM, _terminated)
     try:
         main()
+    except SystemExit:
+        raise
     except BaseException:
         import traceback
 
-        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')}] FAILED\n{traceback.format_exc()}\n")
+        tb = traceback.format_exc()
+        sys.stderr.write(f"[bench rank {_rank}] FAILED\n{tb}\n")
         sys.stderr.flush()
+        if _rank == "0":
+            _error_line(f"rank 0 failed: {tb.strip().splitlines()[-1]}")
         raise

@@ -363,9 +363,33 @@ def fixed_to_float(v):
     return np.asarray(v, dtype=np.uint64).view(np.int64).astype(np.float64) / FIXED_EXPONENT
 
 
+def fma32_exact(a, b, c):
+    """Correctly rounded float32 fma(a, b, c), vectorised.  The product of two floats is exact in double and so is the
+    error of the double sum (two-sum); rounding that sum to float can only go wrong when it sits exactly on a float
+    midpoint while the discarded error is non-zero - then the error's sign decides instead of ties-to-even."""
+    a64, b64, c64 = (np.asarray(t, dtype=np.float32).astype(np.float64) for t in (a, b, c))
+    p = a64 * b64
+    s = p + c64
+    bb = s - p
+    err = (p - (s - bb)) + (c64 - bb)
+    r = s.astype(np.float32)
+    r64 = r.astype(np.float64)
+    up = np.nextafter(r, np.float32(np.inf)).astype(np.float64)
+    dn = np.nextafter(r, np.float32(-np.inf)).astype(np.float64)
+    d = s - r64
+    with np.errstate(invalid="ignore"):
+        tie_above = (d > 0) & (d == 0.5 * (up - r64))  # s is the midpoint of [r, up]: ties-to-even chose r
+        tie_below = (d < 0) & (d == -0.5 * (r64 - dn))  # s is the midpoint of [dn, r]
+    out = r.copy()
+    out = np.where(tie_above & (err > 0), up.astype(np.float32), out)
+    out = np.where(tie_below & (err < 0), dn.astype(np.float32), out)
+    return out.astype(np.float32)
+
+
 def baoab_step_mixed(x, v, du_dx_fixed, masses, temperature, dt, friction, noise_f32):
-    """Bit-level restatement of k_integrator.cuh:32-46 + langevin_integrator.cu:17-30: f32 coefficients/force, f64 state.
-    du_dx_fixed: uint64[N,3]."""
+    """Bit-level restatement of k_integrator.cuh:32-46 + langevin_integrator.cu:17-30 AS COMPILED (nvcc contracts
+    `ca * v_mid + ccs * noise` into fma(v_mid, ca, ccs * noise): FFMA in the SASS of the reference's
+    k_update_forward_baoab<float>): f32 coefficients/force, f64 state.  du_dx_fixed: uint64[N,3]."""
     dt32 = np.float32(dt)
     ca = np.float32(np.exp(-friction * dt))
     kT = BOLTZ * temperature
@@ -376,8 +400,7 @@ def baoab_step_mixed(x, v, du_dx_fixed, masses, temperature, dt, friction, noise
     f = -(np.asarray(du_dx_fixed, dtype=np.uint64).view(np.int64).astype(np.float32) / np.float32(FIXED_EXPONENT))
     cbf = (cbs[:, None] * f).astype(np.float32)
     v_mid = (v + cbf.astype(np.float64)).astype(np.float32)
-    v_new = (ca * v_mid).astype(np.float32) + (ccs[:, None] * np.asarray(noise_f32, dtype=np.float32)).astype(np.float32)
-    v_new = v_new.astype(np.float32)
+    v_new = fma32_exact(np.full_like(v_mid, ca), v_mid, (ccs[:, None] * np.asarray(noise_f32, dtype=np.float32)).astype(np.float32))
     half_dt = np.float32(np.float32(0.5) * dt32)
     x_new = x + np.float64(half_dt) * (v_mid.astype(np.float64) + v_new.astype(np.float64))
     return x_new, v_new.astype(np.float64)

@@ -46,10 +46,29 @@ def _sources() -> list[Path]:
     return sorted(SRC_DIR.glob("*.cu"))
 
 
-def _headers_mtime() -> float:
-    hs = list(SRC_DIR.glob("*.cuh")) + list(SRC_DIR.glob("*.hpp")) + list(SRC_DIR.glob("*.h"))
+def _headers_digest() -> str:
+    import hashlib
+
+    hs = sorted(list(SRC_DIR.glob("*.cuh")) + list(SRC_DIR.glob("*.hpp")) + list(SRC_DIR.glob("*.h")))
     hs.append(PKG_DIR.parent / "include" / "tmb200.h")
-    return max(h.stat().st_mtime for h in hs if h.exists())
+    h = hashlib.sha256()
+    for f in hs:
+        if f.exists():
+            h.update(f.name.encode())
+            h.update(f.read_bytes())
+    return h.hexdigest()
+
+
+def _stamp(src: Path, headers: str, flags: list[str]) -> str:
+    """What an object file was built from: source text, every header, the flags.  Content, not mtimes: the snapshot that
+    travels to the GPU box does not keep the relative order of file times, and a needless rebuild there costs a minute."""
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(src.read_bytes())
+    h.update(headers.encode())
+    h.update(" ".join(flags).encode())
+    return h.hexdigest()
 
 
 # barostat.cu and exchange.cu inline cbrtf / logf / expf from libdevice and must contract them like the reference build
@@ -71,14 +90,26 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
     LIB_DIR.mkdir(parents=True, exist_ok=True)
     srcs = _sources()
-    hdr_time = _headers_mtime()
-    todo = []
-    for s in srcs:
-        obj = OBJ_DIR / (s.stem + ".o")
-        if force or not obj.exists() or obj.stat().st_mtime < max(s.stat().st_mtime, hdr_time):
-            todo.append(s)
+    headers = _headers_digest()
     extra = ["-Xptxas", "-v"] if ptxas_info else []
     extra += os.environ.get("TMB_NVCC_EXTRA", "").split()  # experiments, e.g. -DCQ_MIN_CTAS=3
+    todo = []
+    stamps = {}
+    for s in srcs:
+        obj = OBJ_DIR / (s.stem + ".o")
+        stamp_file = OBJ_DIR / (s.stem + ".stamp")
+        flags = [f for f in NVCC_FLAGS if not (s.name in DEFAULT_FMAD_SOURCES and f == "--fmad=false")] + extra
+        stamps[s] = _stamp(s, headers, flags)
+        if force or ptxas_info or not obj.exists() or not stamp_file.exists() or stamp_file.read_text() != stamps[s]:
+            todo.append(s)
+    # the library carries a stamp of everything it was built from: where only the .so travelled (the GPU box gets no object
+    # files) an up-to-date library is recognised without recompiling
+    import hashlib
+
+    lib_stamp = hashlib.sha256("".join(stamps[s] for s in srcs).encode()).hexdigest()
+    lib_stamp_file = LIB_DIR / "libtmb200.stamp"
+    if not force and not ptxas_info and LIB_PATH.exists() and lib_stamp_file.exists() and lib_stamp_file.read_text() == lib_stamp:
+        return LIB_PATH
     if todo:
         if verbose:
             print(f"[tmb200] compiling {len(todo)} translation units with {NVCC}", file=sys.stderr)
@@ -92,7 +123,9 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
                 return None
 
         with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
-            for res in pool.map(job, todo):
+            for s, res in zip(todo, pool.map(job, todo)):
+                if res:
+                    (OBJ_DIR / (s.stem + ".stamp")).write_text(stamps[s])
                 if res and (verbose or ptxas_info) and res[1].strip():
                     print(res[1], file=sys.stderr)
         if errors:
@@ -104,6 +137,7 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError(f"link failed:\n{proc.stdout}\n{proc.stderr}")
+    lib_stamp_file.write_text(lib_stamp)
     return LIB_PATH
 
 

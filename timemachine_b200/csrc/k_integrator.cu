@@ -4,7 +4,7 @@
 // cheat-sheet item 9): f32 coefficients and force, f64 state.
 //     F      = -(float)( (float)(int64)du_dx / 2^36 )
 //     v_mid  = (float)( v_f64 + (double)(cb * F) )
-//     v_new  = ca * v_mid + cc * xi                         (f32), stored to the f64 array
+//     v_new  = fma(ca, v_mid, cc * xi)                      (f32; the reference's source line is contracted by nvcc)
 //     x_f64 += (double)(0.5f * dt) * ( (double)v_mid + v_new_f64 )
 // and du_dx is zeroed for the next step.
 //
@@ -76,7 +76,8 @@ __device__ __forceinline__ void baoab_atom(const BaoabArgs &a, const int atom, c
         const int q = atom * 3 + d;
         const float force = -fixed_to_real<float>(a.du_dx[q]);
         const float v_mid = static_cast<float>(a.v[q] + static_cast<double>(cb * force));
-        const float v_new = a.ca * v_mid + cc * xi[d];
+        // one FMA, as nvcc compiles the reference's `ca * v_mid + ccs * noise` (FFMA in its k_update_forward_baoab<float>)
+        const float v_new = __fmaf_rn(a.ca, v_mid, cc * xi[d]);
         const double v_new_d = static_cast<double>(v_new);
         a.v[q] = v_new_d;
         const double x_new = a.x[q] + static_cast<double>(0.5f * a.dt) * (static_cast<double>(v_mid) + v_new_d);
