@@ -220,3 +220,41 @@ def test_philox_noise_statistics():
     assert abs(np.corrcoef(a[:, 0], b[:, 0])[0, 1]) < 1e-2 and abs(np.corrcoef(a[:, 0], c[:, 0])[0, 1]) < 1e-2
     np.testing.assert_array_equal(o.fill_normal(1000, 123, 0), a[:1000].astype(np.float32))
     assert np.abs(a).max() < 7.0
+
+
+def test_captured_graph_is_dropped_when_launch_state_changes():
+    """Round-1 advisor finding: the step graph bakes in kernel arguments (atom counts and grid sizes of the all-pairs
+    potential, the integrator's noise pointer).  Mutating them between two multiple_steps calls must not replay the stale
+    graph: after set_atom_idxs / set_noise the graph context equals, bit for bit, an eager context that went through the
+    same calls."""
+    a, s, impl_a, _ = water_context(700, seed=4)
+    b, _, impl_b, _ = water_context(700, seed=4)
+    a.set_use_graphs(True)
+    b.set_use_graphs(False)
+    N = s["N"]
+    for ctx in (a, b):
+        ctx.multiple_steps(60, 61)  # captures (a) the 10-step graph
+    np.testing.assert_array_equal(a.get_x_t(), b.get_x_t())
+    # restrict the all-pairs term to two thirds of the atoms: K, NR and every grid derived from them change
+    subset = np.arange(0, 2 * N // 3, dtype=np.int32)
+    for impl in (impl_a, impl_b):
+        impl.get_potentials()[2].get_potentials()[0].set_atom_idxs(subset)
+    for ctx in (a, b):
+        ctx.multiple_steps(40, 41)
+    np.testing.assert_array_equal(a.get_x_t(), b.get_x_t())
+    np.testing.assert_array_equal(a.get_v_t(), b.get_v_t())
+    # the forces really changed (the comparison above is not vacuous): a third context that keeps all atoms differs
+    c, _, _, _ = water_context(700, seed=4)
+    c.multiple_steps(100, 101)
+    assert np.abs(c.get_x_t() - a.get_x_t()).max() > 1e-6
+    # external noise switched on after a capture
+    noise = np.random.default_rng(1).normal(size=(N, 3)).astype(np.float32)
+    for ctx in (a, b):
+        ctx.get_integrator().set_noise(noise)
+        ctx.multiple_steps(30, 31)
+    np.testing.assert_array_equal(a.get_x_t(), b.get_x_t())
+    for ctx in (a, b):
+        ctx.get_integrator().set_noise(None)
+        ctx.multiple_steps(30, 31)
+    np.testing.assert_array_equal(a.get_x_t(), b.get_x_t())
+    np.testing.assert_array_equal(a.get_v_t(), b.get_v_t())
