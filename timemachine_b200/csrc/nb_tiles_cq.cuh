@@ -266,9 +266,11 @@ __device__ __forceinline__ void cq_tile_prefilter(
         }
         const int head = end; // entries consumed
         count -= end;
+        // every lane has read its entries of [0, head) before any lane overwrites the queue again (the move below, or the next
+        // half's appends when nothing is left over: found by compute-sanitizer racecheck, profiles/r2_sanitizer.txt)
+        __syncwarp();
         if (!last && head > 0 && count > 0) {
-            // what is left (< 32) moves to the front; every lane has finished reading [0, head) once this converges
-            __syncwarp();
+            // what is left (< 32) moves to the front
             const unsigned short v = Q[head + (lane < count ? lane : 0)];
             __syncwarp();
             if (lane < count) {
