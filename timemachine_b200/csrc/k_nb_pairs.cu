@@ -47,15 +47,15 @@ template <typename Real, bool NEG> __global__ void __launch_bounds__(PL_THREADS)
         if (d2 < cutoff2) {
             PairTerms<Real> t = pair_terms<Real, true>(q_scale, lj_scale, qi, qj, si, sj, ei, ej, d2, beta);
             if (a.du_dx != nullptr) {
-                const u64 fx = to_fixed_force(t.prefactor * dx);
-                const u64 fy = to_fixed_force(t.prefactor * dy);
-                const u64 fz = to_fixed_force(t.prefactor * dz);
-                accum<NEG>(a.du_dx + i * 3 + 0, fx);
-                accum<NEG>(a.du_dx + i * 3 + 1, fy);
-                accum<NEG>(a.du_dx + i * 3 + 2, fz);
-                accum<NEG>(a.du_dx + j * 3 + 0, 0ull - fx);
-                accum<NEG>(a.du_dx + j * 3 + 1, 0ull - fy);
-                accum<NEG>(a.du_dx + j * 3 + 2, 0ull - fz);
+                // j gets fixed(-v), not -fixed(v), like the reference (k_nonbonded_pair_list.cuh:146-152): the same inside the
+                // int64 range, the reference's bits beyond it (then exclusions still cancel the all-pairs term exactly)
+                const Real rx = t.prefactor * dx, ry = t.prefactor * dy, rz = t.prefactor * dz;
+                accum<NEG>(a.du_dx + i * 3 + 0, to_fixed_force(rx));
+                accum<NEG>(a.du_dx + i * 3 + 1, to_fixed_force(ry));
+                accum<NEG>(a.du_dx + i * 3 + 2, to_fixed_force(rz));
+                accum<NEG>(a.du_dx + j * 3 + 0, to_fixed_force(-rx));
+                accum<NEG>(a.du_dx + j * 3 + 1, to_fixed_force(-ry));
+                accum<NEG>(a.du_dx + j * 3 + 2, to_fixed_force(-rz));
             }
             if (a.du_dp != nullptr) {
                 u64 *gi = a.du_dp + static_cast<size_t>(i) * P_PER_ATOM;
@@ -69,9 +69,9 @@ template <typename Real, bool NEG> __global__ void __launch_bounds__(PL_THREADS)
                     accum<NEG>(gi + P_EPS, to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ej));
                     accum<NEG>(gj + P_EPS, to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ei));
                 }
-                const u64 fw = to_fixed<FIXED_EXPONENT_DU_DW>(t.prefactor * dw);
-                accum<NEG>(gi + P_W, fw);
-                accum<NEG>(gj + P_W, 0ull - fw);
+                const Real vw = t.prefactor * dw;
+                accum<NEG>(gi + P_W, to_fixed<FIXED_EXPONENT_DU_DW>(vw));
+                accum<NEG>(gj + P_W, to_fixed<FIXED_EXPONENT_DU_DW>(-vw));
             }
             // negate AFTER the conversion: -fixed(u), never fixed(-u) (an overflowed term is LLONG_MAX either sign)
             const i128 e = energy_to_fixed<Real>(t.u);

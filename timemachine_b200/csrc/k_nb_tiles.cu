@@ -106,16 +106,15 @@ __device__ __forceinline__ void tile_rounds(
             PairTerms<Real> t = pair_terms<Real, U>(
                 static_cast<Real>(1), static_cast<Real>(1), ai.q, aj.q, ai.sig, aj.sig, ai.eps, aj.eps, d2, beta);
             if (X) {
-                u64 fx = to_fixed_force(t.prefactor * dx);
-                u64 fy = to_fixed_force(t.prefactor * dy);
-                u64 fz = to_fixed_force(t.prefactor * dz);
-                ai.gx += fx;
-                ai.gy += fy;
-                ai.gz += fz;
-                // fixed(-v) == -fixed(v): round-half-even is symmetric, so the column side is the exact negation
-                aj.gx -= fx;
-                aj.gy -= fy;
-                aj.gz -= fz;
+                const Real rx = t.prefactor * dx, ry = t.prefactor * dy, rz = t.prefactor * dz;
+                ai.gx += to_fixed_force(rx);
+                ai.gy += to_fixed_force(ry);
+                ai.gz += to_fixed_force(rz);
+                // the column side converts -v like the reference (k_nonbonded.cuh:252-254): fixed(-v) == -fixed(v) inside the
+                // int64 range (round-half-even is symmetric), and beyond it these are the reference's bits
+                aj.gx += to_fixed_force(-rx);
+                aj.gy += to_fixed_force(-ry);
+                aj.gz += to_fixed_force(-rz);
             }
             if (P) {
                 ai.gq += to_fixed<FIXED_EXPONENT_DU_DCHARGE>(aj.q * t.inv_d * t.damping);
@@ -128,9 +127,9 @@ __device__ __forceinline__ void tile_rounds(
                     aj.geps += to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ai.eps);
                 }
                 if (ALCH) {
-                    u64 fw = to_fixed<FIXED_EXPONENT_DU_DW>(t.prefactor * dw);
-                    ai.gw += fw;
-                    aj.gw -= fw;
+                    const Real vw = t.prefactor * dw;
+                    ai.gw += to_fixed<FIXED_EXPONENT_DU_DW>(vw);
+                    aj.gw += to_fixed<FIXED_EXPONENT_DU_DW>(-vw);
                 }
             }
             if (U) {

@@ -87,12 +87,12 @@ __device__ __forceinline__ void cq_pair(
     const int sj = SI[S_JSLOT + j - 32];
     if (X) {
         const float rx = t.prefactor * dx, ry = t.prefactor * dy, rz = t.prefactor * dz;
-        const u64 fx = to_fixed_force(rx);
-        const u64 fy = to_fixed_force(ry);
-        const u64 fz = to_fixed_force(rz);
         int *acc = SI + S_ACCX;
         // all three fixed-point values below 2^52 in magnitude (two limbs hold 2^53); NaN / inf compare false
         if (fabsf(rx) + fabsf(ry) + fabsf(rz) < 65536.0f) {
+            const u64 fx = to_fixed_in_range<FIXED_EXPONENT>(rx);
+            const u64 fy = to_fixed_in_range<FIXED_EXPONENT>(ry);
+            const u64 fz = to_fixed_in_range<FIXED_EXPONENT>(rz);
             limb_add(acc + 0 * 128, i, fx);
             limb_add(acc + 1 * 128, i, fy);
             limb_add(acc + 2 * 128, i, fz);
@@ -101,29 +101,33 @@ __device__ __forceinline__ void cq_pair(
             limb_add(acc + 1 * 128, j, fy);
             limb_add(acc + 2 * 128, j, fz);
         } else {
-            // clashing atoms: too large for two limbs, add to the global accumulators directly
+            // clashing atoms: too large for two limbs, add to the global accumulators directly.  Terms beyond the int64 range
+            // are converted exactly as the reference converts them, the column atom's from -v like the reference's
+            // (k_nonbonded.cuh:248-254): fixed(-v) == -fixed(v) only holds in range
             u64 *gi = sink.du_dx + static_cast<size_t>(sink.perm[si]) * 3;
             u64 *gj = sink.du_dx + static_cast<size_t>(sink.perm[sj]) * 3;
-            atomicAdd(gi + 0, fx);
-            atomicAdd(gi + 1, fy);
-            atomicAdd(gi + 2, fz);
-            atomicAdd(gj + 0, 0ull - fx);
-            atomicAdd(gj + 1, 0ull - fy);
-            atomicAdd(gj + 2, 0ull - fz);
+            atomicAdd(gi + 0, to_fixed_force(rx));
+            atomicAdd(gi + 1, to_fixed_force(ry));
+            atomicAdd(gi + 2, to_fixed_force(rz));
+            atomicAdd(gj + 0, to_fixed_force(-rx));
+            atomicAdd(gj + 1, to_fixed_force(-ry));
+            atomicAdd(gj + 2, to_fixed_force(-rz));
         }
     }
     if (P) {
         int *acc = SI + S_ACCP;
-        const u64 pqi = to_fixed<FIXED_EXPONENT_DU_DCHARGE>(qj * t.inv_d * t.damping);
-        const u64 pqj = to_fixed<FIXED_EXPONENT_DU_DCHARGE>(qi * t.inv_d * t.damping);
+        const float vqi = qj * t.inv_d * t.damping, vqj = qi * t.inv_d * t.damping;
+        const float vei = t.eps_grad * ej, vej = t.eps_grad * ei, vw = t.prefactor * dw;
+        const u64 pqi = to_fixed_in_range<FIXED_EXPONENT_DU_DCHARGE>(vqi);
+        const u64 pqj = to_fixed_in_range<FIXED_EXPONENT_DU_DCHARGE>(vqj);
         u64 psig = 0, pei = 0, pej = 0, pw = 0;
         if (t.lj) {
-            psig = to_fixed<FIXED_EXPONENT_DU_DSIG>(t.sig_grad);
-            pei = to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ej);
-            pej = to_fixed<FIXED_EXPONENT_DU_DEPS>(t.eps_grad * ei);
+            psig = to_fixed_in_range<FIXED_EXPONENT_DU_DSIG>(t.sig_grad);
+            pei = to_fixed_in_range<FIXED_EXPONENT_DU_DEPS>(vei);
+            pej = to_fixed_in_range<FIXED_EXPONENT_DU_DEPS>(vej);
         }
         if (ALCH) {
-            pw = to_fixed<FIXED_EXPONENT_DU_DW>(t.prefactor * dw); // antisymmetric: the column atom gets -pw
+            pw = to_fixed_in_range<FIXED_EXPONENT_DU_DW>(vw); // antisymmetric: the column atom gets -pw
         }
         if (limb_small(pqi) && limb_small(pqj) && limb_small(psig) && limb_small(pei) && limb_small(pej) &&
             limb_small(pw)) {
@@ -142,14 +146,19 @@ __device__ __forceinline__ void cq_pair(
         } else {
             u64 *gi = sink.du_dp + static_cast<size_t>(sink.perm[si]) * P_PER_ATOM;
             u64 *gj = sink.du_dp + static_cast<size_t>(sink.perm[sj]) * P_PER_ATOM;
-            atomicAdd(gi + P_CHARGE, pqi);
-            atomicAdd(gj + P_CHARGE, pqj);
-            atomicAdd(gi + P_SIG, psig);
-            atomicAdd(gj + P_SIG, psig);
-            atomicAdd(gi + P_EPS, pei);
-            atomicAdd(gj + P_EPS, pej);
-            atomicAdd(gi + P_W, pw);
-            atomicAdd(gj + P_W, 0ull - pw);
+            // some term is too large for two limbs, possibly for int64: the reference's conversion, term by term
+            atomicAdd(gi + P_CHARGE, to_fixed<FIXED_EXPONENT_DU_DCHARGE>(vqi));
+            atomicAdd(gj + P_CHARGE, to_fixed<FIXED_EXPONENT_DU_DCHARGE>(vqj));
+            if (t.lj) {
+                atomicAdd(gi + P_SIG, to_fixed<FIXED_EXPONENT_DU_DSIG>(t.sig_grad));
+                atomicAdd(gj + P_SIG, to_fixed<FIXED_EXPONENT_DU_DSIG>(t.sig_grad));
+                atomicAdd(gi + P_EPS, to_fixed<FIXED_EXPONENT_DU_DEPS>(vei));
+                atomicAdd(gj + P_EPS, to_fixed<FIXED_EXPONENT_DU_DEPS>(vej));
+            }
+            if (ALCH) {
+                atomicAdd(gi + P_W, to_fixed<FIXED_EXPONENT_DU_DW>(vw));
+                atomicAdd(gj + P_W, to_fixed<FIXED_EXPONENT_DU_DW>(-vw));
+            }
         }
     }
     if (U) {
