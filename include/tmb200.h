@@ -30,7 +30,7 @@ typedef struct tmb_i128 {
 
 typedef void *tmb_potential;       /* std::shared_ptr<Potential>            (wrap_kernels.cpp:729  declare_potential) */
 typedef void *tmb_bound_potential; /* std::shared_ptr<BoundPotential>       (wrap_kernels.cpp:1133 declare_bound_potential) */
-typedef void *tmb_integrator;      /* std::shared_ptr<LangevinIntegrator>   (wrap_kernels.cpp:698) */
+typedef void *tmb_integrator;      /* std::shared_ptr<Integrator>           (wrap_kernels.cpp:692-729) */
 typedef void *tmb_context;         /* Context                               (wrap_kernels.cpp:296) */
 typedef void *tmb_neighborlist;    /* Neighborlist<float|double>            (wrap_kernels.cpp:113) */
 typedef void *tmb_hilbert_sort;    /* HilbertSort                           (wrap_kernels.cpp:174) */
@@ -67,6 +67,11 @@ int tmb_periodic_torsion_create(int precision, const int32_t *torsion_idxs, int 
  * NonbondedPairListPrecomputed_{f32,f64}(pair_idxs[M,2], beta, cutoff); params [M,4] = (q_ij, sig_ij, eps_ij, w_ij)
  *                                                                   wrap_kernels.cpp:1351-1364, nonbonded_precomputed.cu */
 int tmb_flat_bottom_bond_create(int precision, const int32_t *bond_idxs, int n_values, tmb_potential *out);
+/* CentroidRestraint_{f32,f64}(group_a_idxs[A], group_b_idxs[B], kb, b0)   wrap_kernels.cpp:1410-1430, centroid_restraint.cu
+ * kb (|centroid_a - centroid_b| - b0)^2 with geometric centroids; takes no parameters (P = 0) */
+int tmb_centroid_restraint_create(
+    int precision, const int32_t *group_a_idxs, int n_a, const int32_t *group_b_idxs, int n_b, double kb, double b0,
+    tmb_potential *out);
 /* LogFlatBottomBond_{f32,f64}(bond_idxs[B,2], beta)   wrap_kernels.cpp:1337-1349, log_flat_bottom_bond.cu; params [B,3] */
 int tmb_log_flat_bottom_bond_create(int precision, const int32_t *bond_idxs, int n_values, double beta, tmb_potential *out);
 int tmb_chiral_atom_restraint_create(int precision, const int32_t *idxs, int n_values, tmb_potential *out);
@@ -164,6 +169,18 @@ int tmb_langevin_integrator_set_noise(tmb_integrator intg, const float *noise);
  * makes HREX trajectories independent of how replicas are laid out over GPUs (timemachine_b200/hrex.py). */
 int tmb_langevin_integrator_set_step(tmb_integrator intg, unsigned long long step);
 int tmb_langevin_integrator_get_step(tmb_integrator intg, unsigned long long *step);
+
+/* rmsd_align(x1[N,3], x2[N,3]) -> x2 rotated (no reflection) and shifted onto x1   wrap_kernels.cpp:1975-2001,
+ * rmsd_align.cpp:11-61.  A host function in the reference too (Eigen JacobiSVD); f64. */
+int tmb_rmsd_align(const double *x1, const double *x2, int N, double *x2_aligned);
+
+/* ---- VelocityVerletIntegrator(dt, cbs)                          wrap_kernels.cpp:717-729, verlet_integrator.cu ------ */
+/* cbs[N] = -dt / mass (the caller's sign convention, lib/__init__.py:25-37); all arithmetic in f64.  A context driven by it
+ * brackets every multiple_steps call with the half kicks (tmb_context_initialize / _finalize for single steps).  The
+ * tmb_langevin_integrator_* accessors fail on it with "integrator must be LangevinIntegrator." */
+int tmb_velocity_verlet_integrator_create(double dt, const double *cbs, int N, tmb_integrator *out);
+/* releases a handle of either integrator class (tmb_langevin_integrator_destroy is the same call) */
+int tmb_integrator_destroy(tmb_integrator intg);
 
 /* ---- Mover / MonteCarloBarostat           wrap_kernels.cpp:1591-1659, barostat.cu ------------- */
 /* MonteCarloBarostat<float>(N, pressure[bar], temperature[K], group_idxs, interval, bps, seed, adaptive_scaling_enabled,
@@ -268,6 +285,9 @@ int tmb_context_create_with_movers(
     int n_bps, const tmb_mover *movers, int n_movers, tmb_context *out);
 int tmb_context_destroy(tmb_context ctx);
 int tmb_context_step(tmb_context ctx);
+/* Context::initialize / finalize (context.cu:250-260): the integrator's opening / closing half step on the context's state */
+int tmb_context_initialize(tmb_context ctx);
+int tmb_context_finalize(tmb_context ctx);
 /* Context::multiple_steps(n_steps, n_samples, h_x[n_samples,N,3], h_box[n_samples,3,3])   context.cu:216-242 */
 int tmb_context_multiple_steps(tmb_context ctx, int n_steps, int n_samples, double *h_x, double *h_box);
 /* Local MD: Context.setup_local_md / multiple_steps_local / multiple_steps_local_selection (wrap_kernels.cpp:368-612,

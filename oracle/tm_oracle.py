@@ -354,6 +354,45 @@ def baoab_step(x, v, force, ca, cb, cc, dt, noise):
     return new_x, new_v
 
 
+def velocity_verlet_multiple_steps(force_fn, x, v, masses, dt, n_steps):
+    """integrator.py:169-201 (VelocityVerletIntegrator.multiple_steps): x and v are carried in 64-bit fixed point, every
+    increment is rounded to fixed point before it is added.  force_fn(x) = -du/dx.  Returns (xs, vs), n_steps + 1 entries:
+    the start, the state after each of the n_steps - 1 inner steps (velocities half a step behind), the end."""
+    cb = dt / np.asarray(masses, dtype=np.float64)[:, None]
+    # jnp.int64(v * 2^36) truncates toward zero (lib/fixed_point.py:14-16)
+    to_fixed = lambda a: np.trunc(np.asarray(a, dtype=np.float64) * FIXED_EXPONENT).astype(np.int64)  # noqa: E731
+    to_float = lambda a: a.astype(np.float64) / FIXED_EXPONENT  # noqa: E731
+    x_fixed, v_fixed = to_fixed(x), to_fixed(v)
+    zs = [(x_fixed, v_fixed)]
+    v_fixed = v_fixed + to_fixed((0.5 * cb) * force_fn(to_float(x_fixed)))
+    x_fixed = x_fixed + to_fixed(dt * to_float(v_fixed))
+    for _ in range(n_steps - 1):
+        v_fixed = v_fixed + to_fixed(cb * force_fn(to_float(x_fixed)))
+        x_fixed = x_fixed + to_fixed(dt * to_float(v_fixed))
+        zs.append((x_fixed, v_fixed))
+    v_fixed = v_fixed + to_fixed((0.5 * cb) * force_fn(to_float(x_fixed)))
+    zs.append((x_fixed, v_fixed))
+    return to_float(np.array([a for a, _ in zs])), to_float(np.array([b for _, b in zs]))
+
+
+def velocity_verlet_f64(du_dx_fn, x, v, cbs, dt, n_steps):
+    """The compiled path (verlet_integrator.cu:26-110, k_integrator.cuh:64-130): plain f64 state, cbs = -dt / m,
+    initialize = half kick + drift, n_steps x (kick + drift), finalize = half kick.  du_dx_fn(x) = +du/dx as the fixed
+    point buffer holds it.  Returns (frames after every step_fwd, final x, final v)."""
+    x = np.array(x, dtype=np.float64)
+    v = np.array(v, dtype=np.float64)
+    cbs = np.asarray(cbs, dtype=np.float64)[:, None]
+    v = v + (0.5 * cbs) * du_dx_fn(x)
+    x = x + dt * v
+    frames = []
+    for _ in range(n_steps):
+        v = v + cbs * du_dx_fn(x)
+        x = x + dt * v
+        frames.append(x.copy())
+    v = v + (0.5 * cbs) * du_dx_fn(x)
+    return np.array(frames), x, v
+
+
 def float_to_fixed(v):
     """k_fixed_point.cuh:10-24 is round-half-even of v * 2^36 (SURVEY.md §8c sub-oracle 3)"""
     return np.rint(np.asarray(v, dtype=np.float64) * FIXED_EXPONENT).astype(np.int64).view(np.uint64)
@@ -667,6 +706,26 @@ def flat_bottom_bond(x, params, box, bond_idxs):
     np.add.at(du_dx, j, -g)
     du_dp = np.stack([(lo * dlo**4 + hi * dhi**4) / 4, lo * (-k * dlo**3), hi * (-k * dhi**3)], axis=1)
     return u, du_dx, du_dp
+
+
+def centroid_restraint(x, group_a_idxs, group_b_idxs, kb, b0):
+    """potentials/bonded.py:8-31: kb (|<x_a> - <x_b>| - b0)^2, geometric centroids, no periodic imaging, no parameters.
+    Gradient as k_centroid_restraint.cuh:62-80 (the b0 == 0 form needs no division by the distance).  Returns (u, du_dx)."""
+    x = np.asarray(x, dtype=np.float64)
+    ga = np.asarray(group_a_idxs).reshape(-1)
+    gb = np.asarray(group_b_idxs).reshape(-1)
+    delta = x[ga].mean(axis=0) - x[gb].mean(axis=0)
+    dij = np.sqrt(np.sum(delta * delta))
+    du_dx = np.zeros_like(x)
+    if b0 == 0:
+        u = kb * dij * dij
+        g = 2 * kb * delta
+    else:
+        u = kb * (dij - b0) ** 2
+        g = 2 * kb * (dij - b0) * delta / dij
+    np.add.at(du_dx, ga, g / ga.size)
+    np.add.at(du_dx, gb, -g / gb.size)
+    return u, du_dx
 
 
 def log_flat_bottom_bond(x, params, box, bond_idxs, beta):

@@ -181,6 +181,7 @@ def scenario(pots, lib):
         pots.LogFlatBottomBond(pairs, 1.0 / (0.008314462618 * 300.0)),
         pots.ChiralAtomRestraint(chain),
         pots.ChiralBondRestraint(chain, np.where(rng.random(len(chain)) < 0.5, -1, 1).astype(np.int32)),
+        pots.CentroidRestraint(lig, env[:30], 250.0, 0.4),
     ]
     for p in plist:
         for precision in (np.float32, np.float64):
@@ -193,6 +194,7 @@ def scenario(pots, lib):
     plist[0].bind(s["bond_params"]).to_gpu(np.float64)
     pots.FanoutSummedPotential([plist[5], plist[9]], parallel=False).to_gpu(np.float32)
     intg = lib.LangevinIntegrator(300.0, 1.5e-3, 1.0, s["masses"], 2024).impl()
+    lib.VelocityVerletIntegrator(1.5e-3, s["masses"]).impl()
     groups = [np.arange(i, i + 3) for i in range(0, N, 3)]
     lib.MonteCarloBarostat(N, 1.013, 300.0, groups, 15, 7).impl([bound.bound_impl])
     lib.MonteCarloBarostat(N, 1.013, 300.0, groups, 5, 9, adaptive_scaling_enabled=False, initial_volume_scale_factor=0.02).impl([bound.bound_impl])

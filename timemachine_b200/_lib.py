@@ -45,6 +45,7 @@ SIGNATURES = {
     "tmb_harmonic_angle_create": [_int, _p_i32, _int, _ph],
     "tmb_periodic_torsion_create": [_int, _p_i32, _int, _ph],
     "tmb_flat_bottom_bond_create": [_int, _p_i32, _int, _ph],
+    "tmb_centroid_restraint_create": [_int, _p_i32, _int, _p_i32, _int, _dbl, _dbl, _ph],
     "tmb_log_flat_bottom_bond_create": [_int, _p_i32, _int, _dbl, _ph],
     "tmb_chiral_atom_restraint_create": [_int, _p_i32, _int, _ph],
     "tmb_chiral_bond_restraint_create": [_int, _p_i32, _int, _p_i32, _int, _ph],
@@ -84,6 +85,11 @@ SIGNATURES = {
     "tmb_langevin_integrator_set_noise": [_h, _p_f32],
     "tmb_langevin_integrator_set_step": [_h, C.c_uint64],
     "tmb_langevin_integrator_get_step": [_h, _p_u64],
+    "tmb_rmsd_align": [_p_f64, _p_f64, _int, _p_f64],
+    "tmb_velocity_verlet_integrator_create": [_dbl, _p_f64, _int, _ph],
+    "tmb_integrator_destroy": [_h],
+    "tmb_context_initialize": [_h],
+    "tmb_context_finalize": [_h],
     "tmb_context_create": [_p_f64, _p_f64, _p_f64, _int, _h, _ph, _int, _ph],
     "tmb_context_create_with_movers": [_p_f64, _p_f64, _p_f64, _int, _h, _ph, _int, _ph, _int, _ph],
     "tmb_barostat_create": [_int, _dbl, _dbl, _p_i32, _p_i32, _int, _int, _ph, _int, _int, _int, _dbl, _ph],

@@ -29,7 +29,7 @@ template <typename F> static int guarded(F &&f) {
 
 typedef std::shared_ptr<Potential> PotPtr;
 typedef std::shared_ptr<BoundPotential> BpPtr;
-typedef std::shared_ptr<LangevinIntegrator> IntgPtr;
+typedef std::shared_ptr<Integrator> IntgPtr;
 
 static PotPtr &as_pot(tmb_potential h) {
     if (h == nullptr) {
@@ -48,6 +48,13 @@ static IntgPtr &as_intg(tmb_integrator h) {
         throw std::runtime_error("null integrator handle");
     }
     return *static_cast<IntgPtr *>(h);
+}
+static LangevinIntegrator &as_langevin(tmb_integrator h) {
+    auto p = std::dynamic_pointer_cast<LangevinIntegrator>(as_intg(h));
+    if (p == nullptr) {
+        throw std::runtime_error("integrator must be LangevinIntegrator.");
+    }
+    return *p;
 }
 static Context &as_ctx(tmb_context h) {
     if (h == nullptr) {
@@ -160,6 +167,18 @@ int tmb_flat_bottom_bond_create(int precision, const int32_t *bond_idxs, int n_v
 }
 int tmb_log_flat_bottom_bond_create(int precision, const int32_t *bond_idxs, int n_values, double beta, tmb_potential *out) {
     return create_restraint<LogFlatBottomBond>(precision, bond_idxs, n_values, nullptr, 0, beta, 0.0, out);
+}
+int tmb_centroid_restraint_create(
+    int precision, const int32_t *group_a_idxs, int n_a, const int32_t *group_b_idxs, int n_b, double kb, double b0,
+    tmb_potential *out) {
+    return guarded([&] {
+        const std::vector<int> ga(group_a_idxs, group_a_idxs + n_a), gb(group_b_idxs, group_b_idxs + n_b);
+        if (precision == TMB_F32) {
+            *out = new PotPtr(std::make_shared<CentroidRestraint<float>>(ga, gb, kb, b0));
+        } else {
+            *out = new PotPtr(std::make_shared<CentroidRestraint<double>>(ga, gb, kb, b0));
+        }
+    });
 }
 int tmb_chiral_atom_restraint_create(int precision, const int32_t *idxs, int n_values, tmb_potential *out) {
     return create_restraint<ChiralAtomRestraint>(precision, idxs, n_values, nullptr, 0, 0.0, 0.0, out);
@@ -492,13 +511,23 @@ int tmb_langevin_integrator_destroy(tmb_integrator intg) {
     return guarded([&] { delete static_cast<IntgPtr *>(intg); });
 }
 int tmb_langevin_integrator_set_noise(tmb_integrator intg, const float *noise) {
-    return guarded([&] { as_intg(intg)->set_external_noise(noise); });
+    return guarded([&] { as_langevin(intg).set_external_noise(noise); });
 }
 int tmb_langevin_integrator_set_step(tmb_integrator intg, unsigned long long step) {
-    return guarded([&] { as_intg(intg)->set_step(static_cast<long long>(step)); });
+    return guarded([&] { as_langevin(intg).set_step(static_cast<long long>(step)); });
 }
 int tmb_langevin_integrator_get_step(tmb_integrator intg, unsigned long long *step) {
-    return guarded([&] { *step = static_cast<unsigned long long>(as_intg(intg)->step_count()); });
+    return guarded([&] { *step = static_cast<unsigned long long>(as_langevin(intg).step_count()); });
+}
+
+int tmb_rmsd_align(const double *x1, const double *x2, int N, double *x2_aligned) {
+    return guarded([&] { rmsd_align_host(N, x1, x2, x2_aligned); });
+}
+int tmb_velocity_verlet_integrator_create(double dt, const double *cbs, int N, tmb_integrator *out) {
+    return guarded([&] { *out = new IntgPtr(std::make_shared<VelocityVerletIntegrator>(N, dt, cbs)); });
+}
+int tmb_integrator_destroy(tmb_integrator intg) {
+    return guarded([&] { delete static_cast<IntgPtr *>(intg); });
 }
 
 int tmb_context_create(
@@ -950,6 +979,12 @@ int tmb_context_destroy(tmb_context ctx) {
 }
 int tmb_context_step(tmb_context ctx) {
     return guarded([&] { as_ctx(ctx).step(); });
+}
+int tmb_context_initialize(tmb_context ctx) {
+    return guarded([&] { as_ctx(ctx).initialize(); });
+}
+int tmb_context_finalize(tmb_context ctx) {
+    return guarded([&] { as_ctx(ctx).finalize(); });
 }
 int tmb_context_multiple_steps(tmb_context ctx, int n_steps, int n_samples, double *h_x, double *h_box) {
     return guarded([&] { as_ctx(ctx).multiple_steps(n_steps, n_samples, h_x, h_box); });

@@ -96,6 +96,64 @@ void LangevinIntegrator::step_fwd(
     step_++;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+VelocityVerletIntegrator::VelocityVerletIntegrator(int N, double dt, const double *h_cbs)
+    : N_(N), dt_(dt), d_cbs_(N), d_du_dx_(static_cast<size_t>(N) * 3) {
+    d_cbs_.copy_from(h_cbs);
+    d_du_dx_.zero(); // the update kernels re-zero the forces
+    TMB_CUDA(cudaDeviceSynchronize());
+}
+
+void VelocityVerletIntegrator::forces_then(
+    int mode, std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box, unsigned int *d_idxs,
+    cudaStream_t stream) {
+    const int n = static_cast<int>(bps.size());
+    for (int i = 0; i < n; i++) {
+        cudaStream_t s = n > 1 ? fan_.fork(i, stream) : stream;
+        bps[i]->execute_device(N_, d_x, d_box, d_du_dx_.data, nullptr, nullptr, s);
+    }
+    if (n > 1) {
+        for (int i = 0; i < n; i++) {
+            fan_.join(i, stream);
+        }
+    }
+    VerletArgs a;
+    a.N = N_;
+    a.idxs = d_idxs;
+    a.cbs = d_cbs_.data;
+    a.x = d_x;
+    a.v = d_v;
+    a.du_dx = d_du_dx_.data;
+    a.dt = dt_;
+    launch_velocity_verlet(a, mode, stream);
+}
+
+void VelocityVerletIntegrator::step_fwd(
+    std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box, unsigned int *d_idxs,
+    cudaStream_t stream, int, Potential *) {
+    forces_then(0, bps, d_x, d_v, d_box, d_idxs, stream);
+}
+
+void VelocityVerletIntegrator::initialize(
+    std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box, unsigned int *d_idxs,
+    cudaStream_t stream) {
+    if (initialized_) {
+        throw std::runtime_error("initialized twice");
+    }
+    forces_then(1, bps, d_x, d_v, d_box, d_idxs, stream);
+    initialized_ = true;
+}
+
+void VelocityVerletIntegrator::finalize(
+    std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box, unsigned int *d_idxs,
+    cudaStream_t stream) {
+    if (!initialized_) {
+        throw std::runtime_error("not initialized");
+    }
+    forces_then(2, bps, d_x, d_v, d_box, d_idxs, stream);
+    initialized_ = false;
+}
+
 void LangevinIntegrator::publish_step_base(cudaStream_t stream) {
     TMB_LAUNCH(k_set_u64, 1, 1, 0, stream, d_step_base_.data, static_cast<unsigned long long>(step_));
 }
@@ -139,7 +197,7 @@ static bool fuse_prepare_enabled() {
 }
 
 Context::Context(
-    int N, const double *x0, const double *v0, const double *box0, std::shared_ptr<LangevinIntegrator> intg,
+    int N, const double *x0, const double *v0, const double *box0, std::shared_ptr<Integrator> intg,
     std::vector<std::shared_ptr<BoundPotential>> bps, std::vector<std::shared_ptr<Mover>> movers)
     : N_(N), d_x_(static_cast<size_t>(N) * 3), d_v_(static_cast<size_t>(N) * 3), d_box_(9), intg_(std::move(intg)),
       bps_(std::move(bps)), movers_(std::move(movers)) {
@@ -184,7 +242,7 @@ void Context::run_steps(int n, cudaStream_t stream) {
         for (auto &m : movers_) {
             cap = std::min(cap, m->idle_steps()); // a graph block must not span a step on which a mover acts
         }
-        if (use_graphs_ && cap >= GRAPH_STEPS && remaining >= GRAPH_STEPS) {
+        if (use_graphs_ && intg_->graph_capable() && cap >= GRAPH_STEPS && remaining >= GRAPH_STEPS) {
             intg_->publish_step_base(stream);
             const long long generation = g_launch_generation.load();
             if (graph_exec_ == nullptr || graph_stream_ != stream || graph_generation_ != generation) {
@@ -274,6 +332,27 @@ void Context::step() {
     check_list_overflow();
 }
 
+void Context::initialize() {
+    cudaStream_t stream = active_stream();
+    intg_->initialize(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    check_list_overflow();
+}
+
+void Context::finalize() {
+    cudaStream_t stream = active_stream();
+    intg_->finalize(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream);
+    TMB_CUDA(cudaStreamSynchronize(stream));
+    check_list_overflow();
+}
+
+double Context::langevin_temperature() const {
+    if (auto langevin = std::dynamic_pointer_cast<LangevinIntegrator>(intg_)) {
+        return langevin->get_temperature();
+    }
+    throw std::runtime_error("integrator must be LangevinIntegrator.");
+}
+
 // The tile-list buffers are sized from measured counts (4x the liquid-density count, neighborlist.cu).  Steps cannot be
 // redone the way a single evaluation can, so a build that ran out of room during them is an error: the buffers have been
 // grown by the time this throws, the caller restores its state (set_x_t / set_v_t / set_box) and runs again.
@@ -325,6 +404,7 @@ void Context::multiple_steps(int n_steps, int n_samples, double *h_x, double *h_
     }
     const int interval = n_samples > 0 ? n_steps / n_samples : n_steps + 1;
     cudaStream_t stream = active_stream();
+    intg_->initialize(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream); // reference context.cu:227
     int done = 0;
     int stored = 0;
     while (done < n_steps) {
@@ -342,6 +422,7 @@ void Context::multiple_steps(int n_steps, int n_samples, double *h_x, double *h_
             stored++;
         }
     }
+    intg_->finalize(bps_, d_x_.data, d_v_.data, d_box_.data, nullptr, stream); // reference context.cu:239
     TMB_CUDA(cudaStreamSynchronize(stream));
     check_list_overflow();
 }
@@ -366,6 +447,7 @@ void Context::run_local_steps(int n_steps, int n_samples, double *h_x, double *h
     destroy_graph();
     std::vector<std::shared_ptr<BoundPotential>> &pots = local_md_->potentials();
     try {
+        intg_->initialize(pots, d_x_.data, d_v_.data, d_box_.data, local_md_->free_idxs(), stream); // reference context.cu:141
         for (int i = 1; i <= n_steps; i++) {
             intg_->step_fwd(pots, d_x_.data, d_v_.data, d_box_.data, local_md_->free_idxs(), stream, -1);
             if (i % interval == 0) {
@@ -377,6 +459,7 @@ void Context::run_local_steps(int n_steps, int n_samples, double *h_x, double *h
                 verify_frame(xp, bp);
             }
         }
+        intg_->finalize(pots, d_x_.data, d_v_.data, d_box_.data, local_md_->free_idxs(), stream); // reference context.cu:152
     } catch (...) {
         cudaStreamSynchronize(stream);
         local_md_->reset();
@@ -400,7 +483,7 @@ void Context::multiple_steps_local(
         throw std::runtime_error("n_samples < 0");
     }
     if (local_md_ == nullptr) {
-        setup_local_md(intg_->get_temperature(), true);
+        setup_local_md(langevin_temperature(), true);
     }
     cudaStream_t stream = active_stream();
     local_md_->setup_from_idxs(d_x_.data, d_box_.data, local_idxs, seed, radius, k, stream);
@@ -414,7 +497,7 @@ void Context::multiple_steps_local_selection(
         throw std::runtime_error("n_samples < 0");
     }
     if (local_md_ == nullptr) {
-        setup_local_md(intg_->get_temperature(), true);
+        setup_local_md(langevin_temperature(), true);
     }
     cudaStream_t stream = active_stream();
     local_md_->setup_from_selection(reference_idx, selection_idxs, radius, k, stream);

@@ -169,6 +169,49 @@ template <typename Real> __global__ void __launch_bounds__(INT_THREADS) k_baoab_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Velocity Verlet, all f64 (reference k_integrator.cuh:64-130).  MODE 0: a whole step  v += cbs F, x += dt v;
+// MODE 1: the opening half kick + drift  v += (cbs / 2) F, x += dt v;  MODE 2: the closing half kick.  Each update is the
+// single FMA the reference's `a += b * c` statements compile to.  The force buffer is consumed and cleared (the reference
+// clears it with a memset before every evaluation; here the next evaluation finds it zero like the Langevin path does).
+template <int MODE> __global__ void __launch_bounds__(INT_THREADS) k_velocity_verlet(const VerletArgs a) {
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < a.N; tid += gridDim.x * blockDim.x) {
+        const int atom = a.idxs == nullptr ? tid : static_cast<int>(a.idxs[tid]);
+        if (atom < a.N) {
+            const double cb = MODE == 0 ? a.cbs[atom] : 0.5 * a.cbs[atom];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const int q = atom * 3 + d;
+                const double force = fixed_to_real<double>(a.du_dx[q]);
+                const double v_new = fma(cb, force, a.v[q]);
+                a.v[q] = v_new;
+                if (MODE != 2) {
+                    a.x[q] = fma(a.dt, v_new, a.x[q]);
+                }
+                a.du_dx[q] = 0;
+            }
+        } else if (a.idxs != nullptr) {
+            a.du_dx[tid * 3 + 0] = 0;
+            a.du_dx[tid * 3 + 1] = 0;
+            a.du_dx[tid * 3 + 2] = 0;
+        }
+    }
+}
+
+void launch_velocity_verlet(const VerletArgs &args, int mode, cudaStream_t stream) {
+    if (args.N <= 0) {
+        return;
+    }
+    const int blocks = ceil_div(args.N, INT_THREADS);
+    if (mode == 0) {
+        TMB_LAUNCH(k_velocity_verlet<0>, blocks, INT_THREADS, 0, stream, args);
+    } else if (mode == 1) {
+        TMB_LAUNCH(k_velocity_verlet<1>, blocks, INT_THREADS, 0, stream, args);
+    } else {
+        TMB_LAUNCH(k_velocity_verlet<2>, blocks, INT_THREADS, 0, stream, args);
+    }
+}
+
 void launch_baoab(const BaoabArgs &args, cudaStream_t stream) {
     if (args.N <= 0) {
         return;

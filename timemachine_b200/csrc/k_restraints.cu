@@ -343,6 +343,70 @@ template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_nonbond
     }
 }
 
+// ---- centroid restraint (reference k_centroid_restraint.cuh:7-84) ---------------------------------------------------
+// The reference clears two accumulators, sums the fixed-point coordinates of both groups with global atomics in one
+// launch and evaluates in a second.  The groups are a ligand and a pocket (tens to hundreds of atoms), so here ONE CTA
+// does all of it: fixed-point centroid sums in shared memory (integer, hence the same whatever the order), a barrier,
+// then every thread evaluates the atoms it owns with the reference's operation sequence (mixed f32 / f64 where the
+// reference mixes `RealType` with its double kb / b0; the accumulation of |delta|^2 is the FMA chain nvcc emits).
+constexpr int CR_THREADS = 256;
+template <typename Real> __global__ void __launch_bounds__(CR_THREADS) k_centroid_restraint(const CentroidArgs a) {
+    __shared__ unsigned long long s_sum[6];
+    if (threadIdx.x < 6) {
+        s_sum[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    const int n = a.n_a + a.n_b;
+    for (int t = threadIdx.x; t < n; t += CR_THREADS) {
+        const bool in_a = t < a.n_a;
+        const int atom = in_a ? a.group_a[t] : a.group_b[t - a.n_a];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            atomicAdd(s_sum + (in_a ? 0 : 3) + d, to_fixed_force<Real>(static_cast<Real>(a.x[atom * 3 + d])));
+        }
+    }
+    __syncthreads();
+    Real deltas[3];
+    Real dij = 0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        deltas[d] = fixed_to_real<Real>(s_sum[d]) / static_cast<Real>(a.n_a) - fixed_to_real<Real>(s_sum[3 + d]) / static_cast<Real>(a.n_b);
+        dij = fma(deltas[d], deltas[d], dij);
+    }
+    dij = sqrt(dij);
+    if (threadIdx.x == 0 && a.d_u != nullptr) {
+        const Real nrg = static_cast<Real>(a.kb * (static_cast<double>(dij) - a.b0) * (static_cast<double>(dij) - a.b0));
+        *a.d_u = energy_to_fixed<Real>(nrg);
+    }
+    if (a.du_dx == nullptr) {
+        return;
+    }
+    for (int t = threadIdx.x; t < n; t += CR_THREADS) {
+        const bool in_a = t < a.n_a;
+        const int atom = in_a ? a.group_a[t] : a.group_b[t - a.n_a];
+        const Real count = static_cast<Real>(in_a ? a.n_a : a.n_b);
+        const Real sign = in_a ? static_cast<Real>(1) : static_cast<Real>(-1);
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            Real delta;
+            if (a.b0 != 0) {
+                const Real du_ddij = static_cast<Real>(2 * a.kb * (static_cast<double>(dij) - a.b0));
+                const Real ddij_dxi = deltas[d] / dij;
+                delta = sign * du_ddij * ddij_dxi / count;
+            } else {
+                delta = static_cast<Real>(static_cast<double>(sign * 2) * a.kb * static_cast<double>(deltas[d]) / static_cast<double>(count));
+            }
+            atomicAdd(a.du_dx + atom * 3 + d, to_fixed_force<Real>(delta));
+        }
+    }
+}
+
+template <typename Real> void launch_centroid_restraint(const CentroidArgs &args, cudaStream_t stream) {
+    TMB_LAUNCH(k_centroid_restraint<Real>, 1, CR_THREADS, 0, stream, args);
+}
+template void launch_centroid_restraint<float>(const CentroidArgs &, cudaStream_t);
+template void launch_centroid_restraint<double>(const CentroidArgs &, cudaStream_t);
+
 #define TMB_RESTRAINT_LAUNCHER(name, kernel)                                                                          \
     template <typename Real> void name(const RestraintArgs &args, cudaStream_t stream) {                              \
         TMB_LAUNCH(kernel<Real>, bonded_grid(args.b.n_terms), RS_THREADS, 0, stream, args);                           \

@@ -181,6 +181,17 @@ template <typename Real> void launch_log_flat_bottom_bond(const RestraintArgs &a
 template <typename Real> void launch_chiral_atom_restraint(const RestraintArgs &args, cudaStream_t stream);
 template <typename Real> void launch_chiral_bond_restraint(const RestraintArgs &args, cudaStream_t stream);
 template <typename Real> void launch_nonbonded_precomputed(const RestraintArgs &args, cudaStream_t stream);
+// CentroidRestraint: kb (|centroid_a - centroid_b| - b0)^2 over two atom groups (reference k_centroid_restraint.cuh:7-84)
+struct CentroidArgs {
+    const double *x;
+    const int *group_a;
+    const int *group_b;
+    int n_a, n_b;
+    double kb, b0;
+    u64 *du_dx; // nullable
+    i128 *d_u;  // nullable, overwritten
+};
+template <typename Real> void launch_centroid_restraint(const CentroidArgs &args, cudaStream_t stream);
 template <typename Real> void launch_harmonic_bond(const BondedArgs &args, cudaStream_t stream);
 template <typename Real> void launch_harmonic_angle(const BondedArgs &args, cudaStream_t stream);
 template <typename Real> void launch_periodic_torsion(const BondedArgs &args, cudaStream_t stream);
@@ -227,6 +238,18 @@ template <typename Real> struct FusedPrepareArgs {
     unsigned int *reset_overflow;
 };
 template <typename Real> void launch_baoab_prepare(const BaoabArgs &args, const FusedPrepareArgs<Real> &f, cudaStream_t stream);
+// Velocity Verlet in f64 (reference k_integrator.cuh:64-130): mode 0 = full step, 1 = opening half kick + drift
+// (VelocityVerletIntegrator::initialize), 2 = closing half kick (finalize)
+struct VerletArgs {
+    int N;
+    const unsigned int *idxs; // nullable
+    const double *cbs;        // -dt / mass (lib/__init__.py:31-34)
+    double *x;
+    double *v;
+    u64 *du_dx; // consumed and zeroed
+    double dt;
+};
+void launch_velocity_verlet(const VerletArgs &args, int mode, cudaStream_t stream);
 void launch_fill_normal(float *out, int n, unsigned long long seed, unsigned long long step, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------

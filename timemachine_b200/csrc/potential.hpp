@@ -276,6 +276,18 @@ template <typename Real> using ChiralAtomRestraint = RestraintPotential<Real, Re
 template <typename Real> using ChiralBondRestraint = RestraintPotential<Real, RestraintKind::ChiralBond>;
 template <typename Real> using NonbondedPairListPrecomputed = RestraintPotential<Real, RestraintKind::PrecomputedPairs>;
 
+// CentroidRestraint(group_a_idxs, group_b_idxs, kb, b0): kb (|<x_a> - <x_b>| - b0)^2, geometric centroids, no parameters
+// (reference centroid_restraint.cu:10-71)
+template <typename Real> class CentroidRestraint : public Potential {
+public:
+    CentroidRestraint(const std::vector<int> &group_a_idxs, const std::vector<int> &group_b_idxs, double kb, double b0);
+    void execute_device(int, int, const double *, const double *, const double *, u64 *, u64 *, i128 *, cudaStream_t) override;
+private:
+    int n_a_, n_b_;
+    double kb_, b0_;
+    DeviceBuffer<int> d_group_a_, d_group_b_;
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 class HilbertSort {
 public:
@@ -453,24 +465,43 @@ void verify_atom_idxs(int N, const std::vector<int> &atom_idxs, bool allow_empty
 void nonbonded_du_dp_fixed_to_float(int N, int P, const u64 *du_dp, double *out);
 
 // ---------------------------------------------------------------------------------------------------------------
-class LangevinIntegrator {
+// What Context drives (reference integrator.hpp:9-39).  graph_offset / fusable: see LangevinIntegrator::step_fwd.
+class Integrator {
+public:
+    virtual ~Integrator() {}
+    virtual int num_atoms() const = 0;
+    virtual void step_fwd(std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box,
+                          unsigned int *d_idxs, cudaStream_t stream, int graph_offset = -1, Potential *fusable = nullptr) = 0;
+    // bracket a run of steps (velocity Verlet's half kicks; nothing for Langevin)
+    virtual void initialize(std::vector<std::shared_ptr<BoundPotential>> &, double *, double *, double *, unsigned int *, cudaStream_t) {}
+    virtual void finalize(std::vector<std::shared_ptr<BoundPotential>> &, double *, double *, double *, unsigned int *, cudaStream_t) {}
+    // CUDA-graph blocks of steps: only an integrator whose step has no host-side state beyond these counters
+    virtual bool graph_capable() const { return false; }
+    virtual void publish_step_base(cudaStream_t) {}
+    virtual long long step_count() const { return 0; }
+    virtual void advance(int) {}
+    virtual void set_step(long long) {}
+};
+
+class LangevinIntegrator : public Integrator {
 public:
     LangevinIntegrator(int N, const double *masses, double temperature, double dt, double friction, int seed);
-    int num_atoms() const { return N_; }
+    int num_atoms() const override { return N_; }
     double get_temperature() const { return temperature_; }
+    bool graph_capable() const override { return true; }
     // One force evaluation + BAOAB update on `stream` (reference langevin_integrator.cu:55-88)
     // graph_offset >= 0: the call is being captured into a CUDA graph; the noise counter is then
     // *d_step_base + graph_offset so that replays draw fresh noise.
     // fusable: a potential whose next prepare pass this step's update kernel takes over (Potential::fused_prepare_hook), or
     // null
     void step_fwd(std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box,
-                  unsigned int *d_idxs, cudaStream_t stream, int graph_offset = -1, Potential *fusable = nullptr);
-    void publish_step_base(cudaStream_t stream);   // *d_step_base = step_
+                  unsigned int *d_idxs, cudaStream_t stream, int graph_offset = -1, Potential *fusable = nullptr) override;
+    void publish_step_base(cudaStream_t stream) override; // *d_step_base = step_
     void set_external_noise(const float *h_noise); // tests: N x 3 normals reused every step; nullptr restores Philox
-    long long step_count() const { return step_; }
-    void advance(int n) { step_ += n; }
+    long long step_count() const override { return step_; }
+    void advance(int n) override { step_ += n; }
     // reposition the counter-based noise stream (graph replays read the counter from the device: no re-capture needed)
-    void set_step(long long step) { step_ = step; }
+    void set_step(long long step) override { step_ = step; }
 private:
     int N_;
     double temperature_;
@@ -484,6 +515,29 @@ private:
     DeviceBuffer<unsigned long long> d_step_base_;
     StreamFan fan_;
     friend class Context;
+};
+
+// Velocity Verlet in f64 (reference verlet_integrator.cu:10-110): initialize() = half kick + drift, step_fwd() = kick +
+// drift, finalize() = half kick; cbs = -dt / mass is the caller's (lib/__init__.py:25-37).
+class VelocityVerletIntegrator : public Integrator {
+public:
+    VelocityVerletIntegrator(int N, double dt, const double *h_cbs);
+    int num_atoms() const override { return N_; }
+    void step_fwd(std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box,
+                  unsigned int *d_idxs, cudaStream_t stream, int graph_offset = -1, Potential *fusable = nullptr) override;
+    void initialize(std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box,
+                    unsigned int *d_idxs, cudaStream_t stream) override;
+    void finalize(std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box,
+                  unsigned int *d_idxs, cudaStream_t stream) override;
+private:
+    int N_;
+    double dt_;
+    bool initialized_ = false;
+    DeviceBuffer<double> d_cbs_;
+    DeviceBuffer<u64> d_du_dx_;
+    StreamFan fan_;
+    void forces_then(int mode, std::vector<std::shared_ptr<BoundPotential>> &bps, double *d_x, double *d_v, double *d_box,
+                     unsigned int *d_idxs, cudaStream_t stream);
 };
 
 } // namespace tmb
@@ -524,13 +578,13 @@ private:
 
 class Context {
 public:
-    Context(int N, const double *x0, const double *v0, const double *box0, std::shared_ptr<LangevinIntegrator> intg,
+    Context(int N, const double *x0, const double *v0, const double *box0, std::shared_ptr<Integrator> intg,
             std::vector<std::shared_ptr<BoundPotential>> bps, std::vector<std::shared_ptr<Mover>> movers = {});
     ~Context();
     int num_atoms() const { return N_; }
     void step();
-    void initialize() {}
-    void finalize() {}
+    void initialize(); // reference context.cu:250-260: the integrator's initialize / finalize on the context's state
+    void finalize();
     // n_samples frames of x/box are written to h_x/h_box (reference context.cu:216-242)
     void multiple_steps(int n_steps, int n_samples, double *h_x, double *h_box);
     // local MD (reference context.cu:90-214); movers do not run during local steps
@@ -549,7 +603,7 @@ public:
     double *d_x() { return d_x_.data; }
     double *d_v() { return d_v_.data; }
     double *d_box() { return d_box_.data; }
-    std::shared_ptr<LangevinIntegrator> get_integrator() const { return intg_; }
+    std::shared_ptr<Integrator> get_integrator() const { return intg_; }
     const std::vector<std::shared_ptr<BoundPotential>> &get_potentials() const { return bps_; }
     const std::vector<std::shared_ptr<Mover>> &get_movers() const { return movers_; }
     std::shared_ptr<MonteCarloBarostat<float>> get_barostat() const; // reference context.cu:311-320
@@ -560,7 +614,8 @@ public:
 private:
     int N_;
     DeviceBuffer<double> d_x_, d_v_, d_box_;
-    std::shared_ptr<LangevinIntegrator> intg_;
+    std::shared_ptr<Integrator> intg_;
+    double langevin_temperature() const; // reference context.cu:80-88
     std::vector<std::shared_ptr<BoundPotential>> bps_;
     std::vector<std::shared_ptr<Mover>> movers_;
     std::vector<double> nb_cutoffs_with_padding_;
@@ -581,6 +636,9 @@ private:
     std::unique_ptr<LocalMD> local_md_;
     void run_local_steps(int n_steps, int n_samples, double *h_x, double *h_box, cudaStream_t stream);
 };
+
+// x2 moved rigidly (optimal rotation, no reflection; centroid onto x1's) onto x1: reference rmsd_align.cpp:11-61 (host, f64)
+void rmsd_align_host(int N, const double *x1, const double *x2, double *x2_aligned);
 
 void collect_nonbonded_cutoffs(const std::shared_ptr<Potential> &pot, std::vector<double> &out);
 

@@ -138,6 +138,48 @@ void RestraintPotential<Real, KIND>::du_dp_fixed_to_float(int N, int P, const u6
     }
 }
 
+// ---- CentroidRestraint (reference centroid_restraint.cu:10-71) -----------------------------------------------------------
+template <typename Real>
+CentroidRestraint<Real>::CentroidRestraint(
+    const std::vector<int> &group_a_idxs, const std::vector<int> &group_b_idxs, double kb, double b0)
+    : n_a_(static_cast<int>(group_a_idxs.size())), n_b_(static_cast<int>(group_b_idxs.size())), kb_(kb), b0_(b0) {
+    d_group_a_.realloc(std::max<size_t>(1, group_a_idxs.size()));
+    d_group_b_.realloc(std::max<size_t>(1, group_b_idxs.size()));
+    if (n_a_ > 0) {
+        TMB_CUDA(cudaMemcpy(d_group_a_.data, group_a_idxs.data(), group_a_idxs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (n_b_ > 0) {
+        TMB_CUDA(cudaMemcpy(d_group_b_.data, group_b_idxs.data(), group_b_idxs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+}
+
+template <typename Real>
+void CentroidRestraint<Real>::execute_device(
+    int, int, const double *d_x, const double *, const double *, u64 *d_du_dx, u64 *, i128 *d_u, cudaStream_t stream) {
+    if (n_a_ + n_b_ <= 0) {
+        if (d_u != nullptr) {
+            TMB_CUDA(cudaMemsetAsync(d_u, 0, sizeof(i128), stream)); // execute_device overwrites the energy
+        }
+        return;
+    }
+    if (d_du_dx == nullptr && d_u == nullptr) {
+        return; // no parameters: nothing to do for a du/dp-only request
+    }
+    CentroidArgs a;
+    a.x = d_x;
+    a.group_a = d_group_a_.data;
+    a.group_b = d_group_b_.data;
+    a.n_a = n_a_;
+    a.n_b = n_b_;
+    a.kb = kb_;
+    a.b0 = b0_;
+    a.du_dx = d_du_dx;
+    a.d_u = d_u;
+    launch_centroid_restraint<Real>(a, stream);
+}
+template class CentroidRestraint<float>;
+template class CentroidRestraint<double>;
+
 #define TMB_INSTANTIATE(KIND)                                                                                          \
     template class RestraintPotential<float, KIND>;                                                                    \
     template class RestraintPotential<double, KIND>;

@@ -257,28 +257,33 @@ def _new_handle() -> C.c_void_p:
     return C.c_void_p()
 
 
-def _make_bonded(name: str, create_fn, precision: int):
-    def __init__(self, idxs):
+def _make_bonded(name: str, create_fn, precision: int, arg: str):
+    """One-argument constructors; `arg` is the reference's keyword for it (custom_ops.pyi)."""
+
+    def init(self, idxs):
         idxs = _i32(idxs)
         h = _new_handle()
         _check(create_fn(precision, _ptr(idxs, C.c_int32), idxs.size, C.byref(h)))
         self._adopt(h)
 
-    return type(name, (Potential,), {"__init__": __init__, "__doc__": f"{name}(idxs) - see include/tmb200.h"})
+    ns = {"init": init}
+    exec(f"def __init__(self, {arg}):\n    init(self, {arg})\n", ns)
+    return type(name, (Potential,), {"__init__": ns["__init__"], "__doc__": f"{name}({arg}) - see include/tmb200.h"})
 
 
-HarmonicBond_f32 = _make_bonded("HarmonicBond_f32", _L.tmb_harmonic_bond_create, F32)
-HarmonicBond_f64 = _make_bonded("HarmonicBond_f64", _L.tmb_harmonic_bond_create, F64)
-HarmonicAngle_f32 = _make_bonded("HarmonicAngle_f32", _L.tmb_harmonic_angle_create, F32)
-HarmonicAngle_f64 = _make_bonded("HarmonicAngle_f64", _L.tmb_harmonic_angle_create, F64)
-PeriodicTorsion_f32 = _make_bonded("PeriodicTorsion_f32", _L.tmb_periodic_torsion_create, F32)
-PeriodicTorsion_f64 = _make_bonded("PeriodicTorsion_f64", _L.tmb_periodic_torsion_create, F64)
+HarmonicBond_f32 = _make_bonded("HarmonicBond_f32", _L.tmb_harmonic_bond_create, F32, "bond_idxs")
+HarmonicBond_f64 = _make_bonded("HarmonicBond_f64", _L.tmb_harmonic_bond_create, F64, "bond_idxs")
+HarmonicAngle_f32 = _make_bonded("HarmonicAngle_f32", _L.tmb_harmonic_angle_create, F32, "angle_idxs")
+HarmonicAngle_f64 = _make_bonded("HarmonicAngle_f64", _L.tmb_harmonic_angle_create, F64, "angle_idxs")
+# "angle_idxs" is the reference's keyword for the torsion indices too (wrap_kernels.cpp:1439-1444)
+PeriodicTorsion_f32 = _make_bonded("PeriodicTorsion_f32", _L.tmb_periodic_torsion_create, F32, "angle_idxs")
+PeriodicTorsion_f64 = _make_bonded("PeriodicTorsion_f64", _L.tmb_periodic_torsion_create, F64, "angle_idxs")
 
 
-FlatBottomBond_f32 = _make_bonded("FlatBottomBond_f32", _L.tmb_flat_bottom_bond_create, F32)
-FlatBottomBond_f64 = _make_bonded("FlatBottomBond_f64", _L.tmb_flat_bottom_bond_create, F64)
-ChiralAtomRestraint_f32 = _make_bonded("ChiralAtomRestraint_f32", _L.tmb_chiral_atom_restraint_create, F32)
-ChiralAtomRestraint_f64 = _make_bonded("ChiralAtomRestraint_f64", _L.tmb_chiral_atom_restraint_create, F64)
+FlatBottomBond_f32 = _make_bonded("FlatBottomBond_f32", _L.tmb_flat_bottom_bond_create, F32, "bond_idxs")
+FlatBottomBond_f64 = _make_bonded("FlatBottomBond_f64", _L.tmb_flat_bottom_bond_create, F64, "bond_idxs")
+ChiralAtomRestraint_f32 = _make_bonded("ChiralAtomRestraint_f32", _L.tmb_chiral_atom_restraint_create, F32, "idxs")
+ChiralAtomRestraint_f64 = _make_bonded("ChiralAtomRestraint_f64", _L.tmb_chiral_atom_restraint_create, F64, "idxs")
 
 
 class _LogFlatBottomBond(Potential):
@@ -299,6 +304,30 @@ class LogFlatBottomBond_f32(_LogFlatBottomBond):
 
 
 class LogFlatBottomBond_f64(_LogFlatBottomBond):
+    _precision = F64
+
+
+class _CentroidRestraint(Potential):
+    """CentroidRestraint_{f32,f64}(group_a_idxs, group_b_idxs, kb, b0): kb (|centroid_a - centroid_b| - b0)^2, geometric
+    centroids, no parameters (wrap_kernels.cpp:1410-1430, potentials/bonded.py:8-31)."""
+
+    def __init__(self, group_a_idxs, group_b_idxs, kb, b0):
+        ga = _i32(group_a_idxs).reshape(-1)
+        gb = _i32(group_b_idxs).reshape(-1)
+        h = _new_handle()
+        _check(
+            _L.tmb_centroid_restraint_create(
+                self._precision, _ptr(ga, C.c_int32), ga.size, _ptr(gb, C.c_int32), gb.size, float(kb), float(b0), C.byref(h)
+            )
+        )
+        self._handle = h
+
+
+class CentroidRestraint_f32(_CentroidRestraint):
+    _precision = F32
+
+
+class CentroidRestraint_f64(_CentroidRestraint):
     _precision = F64
 
 
@@ -687,6 +716,27 @@ class LangevinIntegrator(Integrator):
         return int(out.value)
 
 
+class VelocityVerletIntegrator(Integrator):
+    """VelocityVerletIntegrator(dt, cbs) - f64, cbs = -dt / masses (wrap_kernels.cpp:717-729, lib/__init__.py:25-37)"""
+
+    def __init__(self, dt, cbs):
+        cbs = _f64(cbs)
+        self._handle = None
+        h = _new_handle()
+        _check(_L.tmb_velocity_verlet_integrator_create(float(dt), _ptr(cbs, C.c_double), cbs.size, C.byref(h)))
+        self._handle = h
+        self._n = cbs.size
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _L.tmb_integrator_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+
 class Mover:
     """Base of the movers Context runs after every integrator step (wrap_kernels.cpp:1591-1617, mover.hpp:11-50)."""
 
@@ -1070,13 +1120,13 @@ def _atom_by_atom_energies(precision, target_atoms, coords, params, box, nb_beta
     return out.astype(np.float32 if precision == F32 else np.float64)
 
 
-def atom_by_atom_energies_f32(target_atoms, coords, params, box, nb_beta, cutoff):
+def atom_by_atom_energies_f32(target_atoms, coords, params, box, nb_beta, nb_cutoff):
     """Pair energies of the target atoms with every atom, [T, N] (wrap_kernels.cpp:2004-2030)."""
-    return _atom_by_atom_energies(F32, target_atoms, coords, params, box, nb_beta, cutoff)
+    return _atom_by_atom_energies(F32, target_atoms, coords, params, box, nb_beta, nb_cutoff)
 
 
-def atom_by_atom_energies_f64(target_atoms, coords, params, box, nb_beta, cutoff):
-    return _atom_by_atom_energies(F64, target_atoms, coords, params, box, nb_beta, cutoff)
+def atom_by_atom_energies_f64(target_atoms, coords, params, box, nb_beta, nb_cutoff):
+    return _atom_by_atom_energies(F64, target_atoms, coords, params, box, nb_beta, nb_cutoff)
 
 
 def _flatten_values(values):
@@ -1201,14 +1251,14 @@ def _rotate_and_translate_mol(precision, coords, box, quaternions, translations)
     return out
 
 
-def rotate_and_translate_mol_f32(coords, box, quaternions, translations):
+def rotate_and_translate_mol_f32(coords, box, quaternion, translation):
     """Rotate a molecule about its centroid and move the centroid to translation * box, per (quaternion, translation)
-    pair, [B, N, 3] (wrap_kernels.cpp:2072-2115)."""
-    return _rotate_and_translate_mol(F32, coords, box, quaternions, translations)
+    pair, [B, N, 3] (wrap_kernels.cpp:2072-2115; the keywords are singular there although both are batches)."""
+    return _rotate_and_translate_mol(F32, coords, box, quaternion, translation)
 
 
-def rotate_and_translate_mol_f64(coords, box, quaternions, translations):
-    return _rotate_and_translate_mol(F64, coords, box, quaternions, translations)
+def rotate_and_translate_mol_f64(coords, box, quaternion, translation):
+    return _rotate_and_translate_mol(F64, coords, box, quaternion, translation)
 
 
 class Context:
@@ -1228,8 +1278,8 @@ class Context:
         for m in self._movers:
             if not isinstance(m, Mover):
                 raise RuntimeError("movers must be timemachine_b200 Mover objects")
-        if not isinstance(integrator, LangevinIntegrator):
-            raise RuntimeError("integrator must be LangevinIntegrator.")
+        if not isinstance(integrator, Integrator) or getattr(integrator, "_handle", None) is None:
+            raise RuntimeError("integrator must be a timemachine_b200 Integrator object")
         self._integrator = integrator
         self._bps = list(bps)
         self._n = x0.shape[0]
@@ -1255,11 +1305,12 @@ class Context:
     def step(self) -> None:
         _check(_L.tmb_context_step(self._handle))
 
-    def initialize(self) -> None:  # no-op for Langevin (langevin_integrator.cu:90-97)
-        pass
+    def initialize(self) -> None:
+        """The integrator's opening half step (context.cu:256-260): nothing for Langevin, half kick + drift for Verlet."""
+        _check(_L.tmb_context_initialize(self._handle))
 
     def finalize(self) -> None:
-        pass
+        _check(_L.tmb_context_finalize(self._handle))
 
     def multiple_steps(self, n_steps: int, store_x_interval: int = 0):
         if store_x_interval < 0:
@@ -1413,6 +1464,21 @@ class Context:
 
 
 # ---- neighbour list / Hilbert sort ------------------------------------------------------------------------------------
+def rmsd_align(x1, x2) -> np.ndarray:
+    """x2 rotated (no reflection) and shifted onto x1 so that the RMSD is minimal (wrap_kernels.cpp:1975-2001)."""
+    x1 = _f64(x1)
+    x2 = _f64(x2)
+    if x1.shape[0] != x2.shape[0]:
+        raise RuntimeError("N1 != N2")
+    if x1.ndim != 2 or x1.shape[1] != 3:
+        raise RuntimeError("D1 != 3")
+    if x2.ndim != 2 or x2.shape[1] != 3:
+        raise RuntimeError("D2 != 3")
+    out = np.empty_like(x1)
+    _check(_L.tmb_rmsd_align(_ptr(x1, C.c_double), _ptr(x2, C.c_double), x1.shape[0], _ptr(out, C.c_double)))
+    return out
+
+
 class _Neighborlist:
     _precision = F32
 

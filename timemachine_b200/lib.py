@@ -1,8 +1,8 @@
-"""Mirror of timemachine/lib/__init__.py:12-62 for the hot path: the picklable integrator and barostat descriptions."""
+"""Mirror of timemachine/lib/__init__.py:12-62: the picklable integrator and barostat descriptions."""
 
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Any, Optional
 
 import numpy as np
@@ -20,6 +20,24 @@ class LangevinIntegrator:
 
     def impl(self) -> custom_ops.LangevinIntegrator:
         return custom_ops.LangevinIntegrator(self.masses, self.temperature, self.dt, self.friction, self.seed)
+
+
+@dataclass
+class VelocityVerletIntegrator:
+    """timemachine/lib/__init__.py:24-37: cbs = -dt / masses is part of the description."""
+
+    dt: float
+    masses: np.ndarray
+
+    cbs: np.ndarray = field(init=False)
+
+    def __post_init__(self):
+        cb = self.dt / np.asarray(self.masses, dtype=np.float64)
+        cb *= -1
+        self.cbs = cb
+
+    def impl(self) -> custom_ops.VelocityVerletIntegrator:
+        return custom_ops.VelocityVerletIntegrator(self.dt, self.cbs)
 
 
 @dataclass

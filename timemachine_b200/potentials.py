@@ -9,6 +9,7 @@ no CPU fallback) - call `.to_gpu(...)`.
 
 from __future__ import annotations
 
+import warnings
 from dataclasses import astuple, dataclass
 from typing import Any, Optional, Sequence
 
@@ -80,9 +81,34 @@ class HarmonicAngle(Potential):
     idxs: np.ndarray
 
 
+class HarmonicAngleStable(HarmonicAngle):
+    """potentials.py:36-46: deprecated name kept so that old pickles load."""
+
+    def __init__(self, *args, **kwargs):
+        warnings.warn("HarmonicAngleStable is deprecated and will be removed in a future release.", DeprecationWarning)
+        super().__init__(*args, **kwargs)
+
+    def __setstate__(self, state):
+        warnings.warn("HarmonicAngleStable is deprecated and will be removed in a future release.", DeprecationWarning)
+        self.__dict__ = state
+
+    def __getstate__(self):
+        raise NotImplementedError("HarmonicAngleStable is deprecated. Serialization is disabled.")
+
+
 @dataclass
 class PeriodicTorsion(Potential):
     idxs: np.ndarray
+
+
+@dataclass
+class CentroidRestraint(Potential):
+    """potentials.py:49-57"""
+
+    group_a_idxs: np.ndarray
+    group_b_idxs: np.ndarray
+    kb: float
+    b0: float
 
 
 @dataclass
