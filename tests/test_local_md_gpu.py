@@ -117,9 +117,10 @@ def test_shell_and_trajectory_match_the_compiled_reference(system):
         rmoved = np.flatnonzero(np.any(rxs[-1] != s["x"], axis=1))
         np.testing.assert_array_equal(moved, rmoved)  # the same reference atom and the same shell were drawn
         np.testing.assert_array_equal(moved, ours.local_md_free_idxs())
-        # 20 steps at friction 0: deterministic; the f32 force kernels differ in the bonded terms' rounding only
-        np.testing.assert_allclose(xs, rxs, rtol=0, atol=2e-5)
-        np.testing.assert_allclose(ours.get_v_t(), theirs.get_v_t(), rtol=0, atol=5e-3)
+        # 20 steps at friction 0: deterministic, and every f32 kernel involved (bonds, angles, nonbonded tiles and pair lists,
+        # the flat-bottom restraint) follows the reference's rounded-operation sequence: the same bits
+        np.testing.assert_array_equal(xs, rxs)
+        np.testing.assert_array_equal(ours.get_v_t(), theirs.get_v_t())
 
 
 def test_local_selection_and_context_is_unchanged_afterwards(system):
@@ -224,7 +225,7 @@ def test_unfrozen_reference_variant(system):
         a, _ = ours.multiple_steps_local(20, local_idxs, radius=radius, k=k, seed=8)
         b, _ = theirs.multiple_steps_local(20, local_idxs, 0, radius, k, 8)
         np.testing.assert_array_equal(np.any(a[-1] != s["x"], axis=1), np.any(b[-1] != s["x"], axis=1))
-        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+        np.testing.assert_array_equal(a, b)  # including the log flat-bottom restraint on the frozen shell
 
 
 def test_log_flat_bottom_bond_potential():
@@ -254,9 +255,10 @@ def test_log_flat_bottom_bond_potential():
         rimpl = ref.LogFlatBottomBond_f32(idxs, beta)
         rdx, rdp, ru = rimpl.execute(round_to_f32(x), round_to_f32(params), box, True, True, True)
         dx, dp, u = P.LogFlatBottomBond(idxs, beta).to_gpu(np.float32).unbound_impl.execute(round_to_f32(x), round_to_f32(params), box)
-        np.testing.assert_allclose(u, ru, rtol=1e-5)
-        np.testing.assert_allclose(dx, rdx, rtol=1e-5, atol=1e-5 * np.abs(rdx).max())
-        np.testing.assert_allclose(dp, rdp, rtol=1e-5, atol=1e-5 * np.abs(rdp).max())
+        # the reference's operation sequence, including its f64 evaluation of the two transcendental expressions: bitwise
+        assert u == ru
+        np.testing.assert_array_equal(dx, rdx)
+        np.testing.assert_array_equal(dp, rdp)
     with pytest.raises(RuntimeError, match="beta must be positive"):
         ops.LogFlatBottomBond_f32(idxs, 0.0)
     with pytest.raises(RuntimeError, match=r"bond_idxs.size\(\) must be exactly 2\*k!"):

@@ -79,30 +79,63 @@ def test_against_reference_custom_ops(name, suffix, rtol):
     x, params = round_to_f32(G["x"]), round_to_f32(params)
     dx, dp, u = impl.execute(x, params, G["box"])
     rdx, rdp, ru = rimpl.execute(x, params, G["box"])
+    if name in ("precomputed", "flat_bottom") and suffix == "f32":
+        # the kernel follows the compiled reference's rounded-operation sequence: bitwise
+        np.testing.assert_array_equal(dx, rdx)
+        np.testing.assert_array_equal(dp, rdp)
+        assert u == ru
     np.testing.assert_allclose(u, ru, rtol=rtol, atol=rtol)
     assert_forces_close(rdx, dx, rtol)
     np.testing.assert_allclose(dp, rdp, rtol=rtol * 10, atol=rtol * 10)
 
 
-def test_precomputed_keeps_electrostatic_gradient_without_lj():
-    """A pair with eps == 0 but q != 0: the compiled reference only writes gradients inside its Lennard-Jones branch
-    (k_nonbonded_precomputed.cuh:150-181) and returns zero force; the reference's Python potential, the oracle and this
-    kernel keep the electrostatic force."""
+def test_precomputed_pair_without_lj_follows_the_compiled_reference():
+    """A pair with eps == 0 but q != 0: the compiled reference adds gradients only from inside its Lennard-Jones branch
+    (k_nonbonded_precomputed.cuh:150-181), so such a pair has an electrostatic energy but no force and no du/dp.  The
+    drop-in returns what the reference returns; TMB_PRECOMPUTED_FULL_GRADIENT=1 (read once per process) keeps the
+    gradient the reference's Python potential and the oracle have."""
+    import os
+    import subprocess
+    import sys
+
     o = ops()
-    x = np.array([[0.0, 0.0, 0.0], [0.3, 0.1, 0.0]])
+    x = np.array([[0.0, 0.0, 0.0], [0.3, 0.1, 0.0], [0.5, 0.4, 0.1]])
     box = np.eye(3) * 3.0
-    pairs = np.array([[0, 1]], dtype=np.int32)
-    params = np.array([[1.5, 0.3, 0.0, 0.0]])
-    dx, dp, u = o.NonbondedPairListPrecomputed_f64(pairs, BETA, CUTOFF).execute(x, params, box)
+    pairs = np.array([[0, 1], [1, 2]], dtype=np.int32)
+    params = np.array([[1.5, 0.3, 0.0, 0.0], [0.7, 0.15, 0.4, 0.0]])
     ou, odx, odp = O.nonbonded_precomputed(x, params, box, pairs, BETA, CUTOFF)
-    np.testing.assert_allclose(u, ou, rtol=1e-10)
-    np.testing.assert_allclose(dx, odx, rtol=1e-9)
-    assert np.linalg.norm(dx[0]) > 1.0
-    ref = load_reference_ops()
-    if ref is not None:
-        rdx, _, ru = ref.NonbondedPairListPrecomputed_f64(pairs, BETA, CUTOFF).execute(x, params, box)
-        np.testing.assert_allclose(ru, u, rtol=1e-10)
-        assert not rdx.any()  # documents the reference behaviour this implementation deliberately does not copy
+    ou1, odx1, odp1 = O.nonbonded_precomputed(x, params[1:], box, pairs[1:], BETA, CUTOFF)
+    for suffix, rtol in (("f64", 1e-9), ("f32", 2e-4)):
+        dx, dp, u = getattr(o, f"NonbondedPairListPrecomputed_{suffix}")(pairs, BETA, CUTOFF).execute(x, params, box)
+        np.testing.assert_allclose(u, ou, rtol=rtol)  # both pairs in the energy
+        assert_forces_close(odx1, dx, rtol)  # only the pair with LJ in the forces
+        np.testing.assert_allclose(dp[1], odp1[0], rtol=rtol * 10)
+        assert not dp[0].any()
+        ref = load_reference_ops()
+        if ref is not None:
+            rdx, rdp, ru = getattr(ref, f"NonbondedPairListPrecomputed_{suffix}")(pairs, BETA, CUTOFF).execute(x, params, box)
+            if suffix == "f32":
+                np.testing.assert_array_equal(dx, rdx)
+                np.testing.assert_array_equal(dp, rdp)
+                assert u == ru
+            else:
+                np.testing.assert_allclose(dx, rdx, rtol=1e-10, atol=1e-10)
+                np.testing.assert_allclose(u, ru, rtol=1e-10)
+    code = (
+        "import numpy as np\n"
+        "from timemachine_b200 import custom_ops as o\n"
+        f"x = np.array({x.tolist()}); box = np.eye(3) * 3.0\n"
+        f"pairs = np.array({pairs.tolist()}, dtype=np.int32); params = np.array({params.tolist()})\n"
+        f"dx, dp, u = o.NonbondedPairListPrecomputed_f64(pairs, {BETA}, {CUTOFF}).execute(x, params, box)\n"
+        "np.save('/tmp/tmb_full_gradient.npy', np.concatenate([dx.ravel(), dp.ravel(), [u]]))\n"
+    )
+    env = dict(os.environ, TMB_PRECOMPUTED_FULL_GRADIENT="1")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=str(Path(__file__).resolve().parents[1]))
+    got = np.load("/tmp/tmb_full_gradient.npy")
+    np.testing.assert_allclose(got[:9].reshape(3, 3), odx, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(got[9:17].reshape(2, 4), odp, rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(got[17], ou, rtol=1e-10)
+    assert np.linalg.norm(odx[0]) > 1.0  # the force the default drops is not small
 
 
 def test_argument_checks():

@@ -89,9 +89,10 @@ template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_flat_bo
             // the displacement and its minimum image are formed in double, as the reference does (:108-113)
             double delta = a.b.x[src * 3 + d] - a.b.x[dst * 3 + d];
             const double bd = a.box[d * 3 + d];
-            delta -= bd * nearbyint(delta / bd);
+            // the two fused multiply-adds nvcc makes of the reference's `delta -= box * n` and `r2 += delta * delta`
+            delta = fma(-bd, nearbyint(delta / bd), delta);
             dx[d] = static_cast<Real>(delta);
-            r2 = static_cast<Real>(static_cast<double>(r2) + delta * delta);
+            r2 = static_cast<Real>(fma(delta, delta, static_cast<double>(r2)));
         }
         const Real r = sqrt(r2);
         const Real above = static_cast<Real>(r > rmax), below = static_cast<Real>(r < rmin);
@@ -131,7 +132,6 @@ template <typename Real> __device__ __forceinline__ Real log_1_exp_neg(Real x) {
 template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_log_flat_bottom_bond(const RestraintArgs a) {
     __shared__ i128 scratch[RS_THREADS / WARP];
     i128 energy = 0;
-    const Real beta = static_cast<Real>(a.beta);
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.b.n_terms; b += gridDim.x * blockDim.x) {
         const int src = a.b.idxs[b * 2 + 0], dst = a.b.idxs[b * 2 + 1];
         const Real k = static_cast<Real>(a.b.p[b * 3 + 0]);
@@ -142,20 +142,23 @@ template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_log_fla
         for (int d = 0; d < 3; d++) {
             double delta = a.b.x[src * 3 + d] - a.b.x[dst * 3 + d];
             const double bd = a.box[d * 3 + d];
-            delta -= bd * nearbyint(delta / bd);
+            // the two fused multiply-adds nvcc makes of the reference's `delta -= box * n` and `r2 += delta * delta`
+            delta = fma(-bd, nearbyint(delta / bd), delta);
             dx[d] = static_cast<Real>(delta);
-            r2 = static_cast<Real>(static_cast<double>(r2) + delta * delta);
+            r2 = static_cast<Real>(fma(delta, delta, static_cast<double>(r2)));
         }
         const Real r = sqrt(r2);
         const Real above = static_cast<Real>(r > rmax), below = static_cast<Real>(r < rmin);
         const Real d_min = r - rmin, d_max = r - rmax;
         const Real d_min2 = d_min * d_min, d_max2 = d_max * d_max;
         const Real nrg = (k / 4) * ((below * (d_min2 * d_min2)) + (above * (d_max2 * d_max2)));
+        // beta is a double in the reference's kernel (k_log_flat_bottom_bond.cuh:21,64,69): both transcendental expressions are
+        // evaluated in f64 whatever Real is, and rounded to Real afterwards
         if (a.b.d_u != nullptr) {
-            energy += energy_to_fixed<Real>(-log_1_exp_neg<Real>(beta * nrg) / beta);
+            energy += energy_to_fixed<Real>(static_cast<Real>(-log_1_exp_neg<double>(a.beta * static_cast<double>(nrg)) / a.beta));
         }
         // d/d(nrg) of the log form: -exp(-beta nrg) / (1 - exp(-beta nrg)); every flat-bottom gradient is scaled by it
-        Real pre = -exp(-beta * nrg);
+        Real pre = static_cast<Real>(-exp(-a.beta * static_cast<double>(nrg)));
         pre = pre / (static_cast<Real>(1) + pre);
         const Real d_min3 = d_min2 * d_min, d_max3 = d_max2 * d_max;
         if (a.b.du_dp != nullptr) {
@@ -261,6 +264,10 @@ template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_chiral_
 }
 
 // ---- nonbonded on precomputed pairs: params [M,4] = (q_ij, sig_ij, eps_ij, w offset) -------------------------------
+// f32: the rounded-operation sequence of the compiled reference (read off the SASS of k_nonbonded_precomputed<float> under
+// oracle/_ref, as for the tile kernel): d^2 = fma(dw,dw, fma(dz,dz, fma(dx,dx, dy*dy))), IEEE sqrt and reciprocal,
+// damping' = fma(erfc, S', -(2/sqrt(pi) e^(-b^2d^2) b) S), es_factor = fma(damping, -(1/d)^2, damping' (1/d)), every
+// force term converted to fixed point for atom i and, from the negated float, for atom j.
 template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_nonbonded_precomputed(const RestraintArgs a) {
     __shared__ i128 scratch[RS_THREADS / WARP];
     i128 energy = 0;
@@ -277,32 +284,37 @@ template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_nonbond
         const Real dx = min_image(xi.x - xj.x, box.x, box.inv_x);
         const Real dy = min_image(xi.y - xj.y, box.y, box.inv_y);
         const Real dz = min_image(xi.z - xj.z, box.z, box.inv_z);
-        const Real d2 = dx * dx + dy * dy + dz * dz + dw * dw;
+        const Real d2 = fma_(dw, dw, dist2_3d(dx, dy, dz));
         if (!(d2 < cutoff2)) {
             continue;
         }
         const Real d = sqrt(d2);
         const Real inv_d = 1 / d;
         // each term is rounded to fixed point on its own, as in the reference (:95-105,150-158)
-        u64 fx = 0, fy = 0, fz = 0, g_q = 0, g_sig = 0, g_eps = 0, g_w = 0;
+        u64 fix = 0, fiy = 0, fiz = 0, fjx = 0, fjy = 0, fjz = 0, g_q = 0, g_sig = 0, g_eps = 0, g_w = 0;
         if (q != 0) {
             Real debd, dsdr;
             const Real ebd = erfc_and_deriv(beta * d, debd);
             debd = beta * debd;
             const Real sr = switch_and_deriv(d, dsdr);
+            const Real damping_prime = fma_(ebd, dsdr, debd * sr);
             const Real damping = ebd * sr;
-            const Real d_es_dr = (ebd * dsdr + debd * sr) * inv_d - damping * (inv_d * inv_d);
+            const Real es_factor = fma_(damping, -(inv_d * inv_d), damping_prime * inv_d);
             if (a.b.d_u != nullptr) {
                 energy += energy_to_fixed<Real>(damping * (q * inv_d));
             }
-            const Real pre = (q * d_es_dr) * inv_d;
-            fx += to_fixed_force(dx * pre);
-            fy += to_fixed_force(dy * pre);
-            fz += to_fixed_force(dz * pre);
+            const Real pre = (q * es_factor) * inv_d;
+            fix += to_fixed_force(dx * pre);
+            fiy += to_fixed_force(dy * pre);
+            fiz += to_fixed_force(dz * pre);
+            fjx += to_fixed_force(-dx * pre);
+            fjy += to_fixed_force(-dy * pre);
+            fjz += to_fixed_force(-dz * pre);
             g_q = to_fixed<FIXED_EXPONENT_DU_DCHARGE>(damping * inv_d);
             g_w += to_fixed<FIXED_EXPONENT_DU_DW>(dw * pre);
         }
-        if (eps != 0 && sig != 0) {
+        const bool lj = eps != 0 && sig != 0;
+        if (lj) {
             const Real s1 = sig * inv_d;
             const Real s2 = s1 * s1;
             const Real s6 = s2 * s2 * s2;
@@ -316,20 +328,28 @@ template <typename Real> __global__ void __launch_bounds__(RS_THREADS) k_nonbond
             const Real d12 = d6 * d6;
             const Real du_dr = eps * static_cast<Real>(24) * sig6 * (d6 - static_cast<Real>(2) * sig6) / (d12 * d);
             const Real pre = du_dr * inv_d;
-            fx += to_fixed_force(dx * pre);
-            fy += to_fixed_force(dy * pre);
-            fz += to_fixed_force(dz * pre);
+            fix += to_fixed_force(dx * pre);
+            fiy += to_fixed_force(dy * pre);
+            fiz += to_fixed_force(dz * pre);
+            fjx += to_fixed_force(-dx * pre);
+            fjy += to_fixed_force(-dy * pre);
+            fjz += to_fixed_force(-dz * pre);
             g_w += to_fixed<FIXED_EXPONENT_DU_DW>(dw * pre);
             g_eps = to_fixed<FIXED_EXPONENT_DU_DEPS>(du_de);
             g_sig = to_fixed<FIXED_EXPONENT_DU_DSIG>(
                 static_cast<Real>(-24) * eps * (sig2 * sig2 * sig) * (d6 - static_cast<Real>(2) * sig6) / d12);
         }
-        // NOTE the compiled reference only writes gradients inside its Lennard-Jones branch
-        // (k_nonbonded_precomputed.cuh:150-181), so a pair with eps == 0 but q != 0 gets no force there; the reference's
-        // Python potential (potentials/nonbonded.py:403-446) and this kernel keep the electrostatic gradient.
+        // The compiled reference adds a pair's gradients from inside its Lennard-Jones branch
+        // (k_nonbonded_precomputed.cuh:150-181): a pair with eps_ij == 0 (or sig_ij == 0) contributes its electrostatic
+        // ENERGY there but neither force nor du/dp.  A drop-in returns what the reference returns, so that is the default;
+        // TMB_PRECOMPUTED_FULL_GRADIENT=1 keeps the electrostatic gradient of such pairs, as the reference's Python
+        // potential (potentials/nonbonded.py:403-446) does.
+        if (!lj && !a.full_gradient) {
+            continue;
+        }
         if (a.b.du_dx != nullptr) {
-            add3(a.b.du_dx, i, fx, fy, fz);
-            add3(a.b.du_dx, j, 0ull - fx, 0ull - fy, 0ull - fz);
+            add3(a.b.du_dx, i, fix, fiy, fiz);
+            add3(a.b.du_dx, j, fjx, fjy, fjz);
         }
         if (a.b.du_dp != nullptr) {
             atomicAdd(a.b.du_dp + m * 4 + P_CHARGE, g_q);

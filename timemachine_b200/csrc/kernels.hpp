@@ -175,6 +175,7 @@ struct RestraintArgs {
     const int *signs = nullptr;  // chiral bond restraint [R]
     double beta = 0;             // precomputed pairs; log flat-bottom bond (1 / kT)
     double cutoff = 0;
+    bool full_gradient = false;  // precomputed pairs: keep the ES gradient of pairs without LJ (the reference drops it)
 };
 template <typename Real> void launch_flat_bottom_bond(const RestraintArgs &args, cudaStream_t stream);
 template <typename Real> void launch_log_flat_bottom_bond(const RestraintArgs &args, cudaStream_t stream);

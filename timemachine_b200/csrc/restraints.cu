@@ -4,6 +4,8 @@
 #include "fixed_point.cuh"
 #include "potential.hpp"
 
+#include <cstdlib>
+
 namespace tmb {
 
 template <typename Real, RestraintKind KIND>
@@ -110,6 +112,13 @@ void RestraintPotential<Real, KIND>::execute_device(
     a.signs = d_signs_.data;
     a.beta = beta_;
     a.cutoff = cutoff_;
+    if (KIND == RestraintKind::PrecomputedPairs) {
+        static const bool full = [] {
+            const char *e = std::getenv("TMB_PRECOMPUTED_FULL_GRADIENT");
+            return e != nullptr && e[0] == '1';
+        }();
+        a.full_gradient = full;
+    }
     switch (KIND) {
     case RestraintKind::FlatBottomBond:
         launch_flat_bottom_bond<Real>(a, stream);
