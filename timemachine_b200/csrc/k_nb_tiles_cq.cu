@@ -38,12 +38,19 @@
 // The exact 38-instruction round per 32 pairs becomes ~29 instructions per 64 pairs (ncu r1 -> r2 in profiles/).
 #include "nb_tiles_cq.cuh"
 
+#ifndef CQ_ROW_RUNS
+#define CQ_ROW_RUNS 1 // 0: the code-queue phase A / B of round 1 (cq_tile_prefilter), kept for A/B measurements
+#endif
+
 namespace tmb {
+
+// per-warp shared words
+__host__ __device__ constexpr int cq_words(bool, bool p) { return p ? S_WORDS_P : S_WORDS_X; }
 
 template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, CQ_MIN_CTAS) k_nb_tiles_cq(const NbTileArgs<float> a) {
     extern __shared__ __align__(16) float cq_smem[];
     __shared__ i128 scratch[CQ_WARPS];
-    constexpr int WORDS = P ? S_WORDS_P : S_WORDS_X;
+    constexpr int WORDS = cq_words(X, P);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float *S = cq_smem + warp * WORDS;
@@ -87,16 +94,31 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
     int cur_row = -1;
     int i_slot = 0;
     bool i_valid = false;
-    u64 gi[3] = {0, 0, 0};     // row-atom du/dx accumulated over a run of tiles with the same row block
+    // row-atom du/dx accumulated over a run of tiles with the same row block
+#if CQ_ROW_RUNS
+    // touched once per tile, so it lives in shared memory (lane-private u64[3][32] slots in the part of the code queue's space
+    // the row-run tables leave free) and leaves its six registers to the phase-B loop.  NOT in extra shared memory: 6 KB more
+    // per CTA moves the L1 / shared carve-out from 196 to 228 KB and costs more than the registers gain (measured).
+    u64 *G = reinterpret_cast<u64 *>(S + S_RG);
+#define CQ_GI(c) G[(c) * 32 + lane]
+#else
+    u64 gi[3];
+#define CQ_GI(c) gi[c]
+#endif
+    if (X) {
+        CQ_GI(0) = 0;
+        CQ_GI(1) = 0;
+        CQ_GI(2) = 0;
+    }
     u64 gpi[4] = {0, 0, 0, 0}; // row-atom du/dp
 
     auto flush_row = [&]() {
         if (cur_row >= 0 && i_valid) {
             const size_t atom = a.perm[i_slot];
             if (X) {
-                atomicAdd(a.du_dx + atom * 3 + 0, gi[0]);
-                atomicAdd(a.du_dx + atom * 3 + 1, gi[1]);
-                atomicAdd(a.du_dx + atom * 3 + 2, gi[2]);
+                atomicAdd(a.du_dx + atom * 3 + 0, CQ_GI(0));
+                atomicAdd(a.du_dx + atom * 3 + 1, CQ_GI(1));
+                atomicAdd(a.du_dx + atom * 3 + 2, CQ_GI(2));
             }
             if (P) {
                 for (int c = 0; c < 4; c++) {
@@ -104,7 +126,11 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
                 }
             }
         }
-        gi[0] = gi[1] = gi[2] = 0;
+        if (X) {
+            CQ_GI(0) = 0;
+            CQ_GI(1) = 0;
+            CQ_GI(2) = 0;
+        }
         gpi[0] = gpi[1] = gpi[2] = gpi[3] = 0;
     };
 
@@ -227,8 +253,13 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
                 }
             }
             if (prefilter) {
+#if CQ_ROW_RUNS
+                cq_tile_prefilter_runs<U, X, P>(
+                    S, cqbox, cutoff2, thr2, beta, hx, hy, hz, half >= 0 ? half : 0, half >= 0 ? half + 1 : 2, sink, energy);
+#else
                 cq_tile_prefilter<U, X, P>(
                     S, cqbox, cutoff2, thr2, beta, hx, hy, hz, half >= 0 ? half : 0, half >= 0 ? half + 1 : 2, sink, energy);
+#endif
             } else if (vanilla && !diag) {
                 if (half >= 0) {
                     cq_tile<false, false, U, X, P, 16>(S, bx, by, bz, inv_bx, inv_by, inv_bz, cutoff2, beta, i_slot, half * 16, sink, energy);
@@ -247,7 +278,7 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
             // fold this tile's limb sums: row atoms into registers, column atoms (negated) to the sorted accumulators
             if (X) {
                 for (int c = 0; c < 3; c++) {
-                    gi[c] += limbs_take(SI + S_ACCX + c * 128, lane);
+                    CQ_GI(c) += limbs_take(SI + S_ACCX + c * 128, lane);
                     const u64 gj = 0ull - limbs_take(SI + S_ACCX + c * 128, 32 + lane);
                     if (j_valid && gj != 0) {
                         atomicAdd(a.du_dx + j_atom * 3 + c, gj);
@@ -274,7 +305,7 @@ template <bool U, bool X, bool P> __global__ void __launch_bounds__(CQ_THREADS, 
 }
 
 template <bool U, bool X, bool P> static void cq_launch(const NbTileArgs<float> &args, int grid, cudaStream_t stream) {
-    const size_t smem = CQ_WARPS * (P ? S_WORDS_P : S_WORDS_X) * sizeof(float);
+    const size_t smem = CQ_WARPS * cq_words(X, P) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         TMB_CUDA(cudaFuncSetAttribute(k_nb_tiles_cq<U, X, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -286,7 +317,7 @@ template <bool U, bool X, bool P> static void cq_launch(const NbTileArgs<float> 
 int nb_tiles_cq_max_grid() {
     static int cached = 0;
     if (cached == 0) {
-        const size_t smem = CQ_WARPS * S_WORDS_X * sizeof(float);
+        const size_t smem = CQ_WARPS * cq_words(true, false) * sizeof(float);
         TMB_CUDA(cudaFuncSetAttribute(
             k_nb_tiles_cq<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         int per_sm = 0;

@@ -75,10 +75,12 @@ struct CqSink {
 
 // One pair inside the cutoff: evaluate, round every term to fixed point, add the limbs to the row atom i (0..31) and
 // the column atom j (32..63) of the warp's shared block.
-template <bool ALCH, bool U, bool X, bool P>
+// ROWREG: the row atom's force limbs are added to `racc` (registers: {x lo, x hi, y lo, y hi, z lo, z hi}) instead of the
+// shared accumulators - the caller walks a row's pairs consecutively and flushes once per run (cq_tile_prefilter_runs).
+template <bool ALCH, bool U, bool X, bool P, bool ROWREG = false>
 __device__ __forceinline__ void cq_pair(
     float *S, const int i, const int j, const float dx, const float dy, const float dz, const float dw, const float d2,
-    const float beta, const CqSink &sink, i128 &energy) {
+    const float beta, const CqSink &sink, i128 &energy, int *racc = nullptr) {
     int *SI = reinterpret_cast<int *>(S);
     const float qi = S[S_Q + i], qj = S[S_Q + j];
     const float ei = S[S_EPS + i], ej = S[S_EPS + j];
@@ -86,16 +88,29 @@ __device__ __forceinline__ void cq_pair(
     const int si = sink.row_base + i; // sorted slots, translated to atoms on the (rare) direct path only
     const int sj = SI[S_JSLOT + j - 32];
     if (X) {
-        const float rx = t.prefactor * dx, ry = t.prefactor * dy, rz = t.prefactor * dz;
+        // The fixed-point scale goes into the prefactor: (p 2^36) d == (p d) 2^36 bit for bit, scaling by a power of two
+        // commutes with rounding - except where p d is subnormal (both forms then convert to 0) or p 2^36 overflows (the
+        // test below fails and the rare path starts again from the unscaled product).  Two multiplies less per pair.
+        const float ps = t.prefactor * static_cast<float>(FIXED_EXPONENT);
+        const float sx = ps * dx, sy = ps * dy, sz = ps * dz;
         int *acc = SI + S_ACCX;
         // all three fixed-point values below 2^52 in magnitude (two limbs hold 2^53); NaN / inf compare false
-        if (fabsf(rx) + fabsf(ry) + fabsf(rz) < 65536.0f) {
-            const u64 fx = to_fixed_in_range<FIXED_EXPONENT>(rx);
-            const u64 fy = to_fixed_in_range<FIXED_EXPONENT>(ry);
-            const u64 fz = to_fixed_in_range<FIXED_EXPONENT>(rz);
-            limb_add(acc + 0 * 128, i, fx);
-            limb_add(acc + 1 * 128, i, fy);
-            limb_add(acc + 2 * 128, i, fz);
+        if (fabsf(sx) + fabsf(sy) + fabsf(sz) < 4503599627370496.0f) {
+            const u64 fx = static_cast<u64>(round_to_i64_in_range(sx));
+            const u64 fy = static_cast<u64>(round_to_i64_in_range(sy));
+            const u64 fz = static_cast<u64>(round_to_i64_in_range(sz));
+            if (ROWREG) {
+                racc[0] += static_cast<int>(static_cast<unsigned int>(fx) & LIMB_MASK);
+                racc[1] += static_cast<int>(static_cast<i64>(fx) >> LIMB_BITS);
+                racc[2] += static_cast<int>(static_cast<unsigned int>(fy) & LIMB_MASK);
+                racc[3] += static_cast<int>(static_cast<i64>(fy) >> LIMB_BITS);
+                racc[4] += static_cast<int>(static_cast<unsigned int>(fz) & LIMB_MASK);
+                racc[5] += static_cast<int>(static_cast<i64>(fz) >> LIMB_BITS);
+            } else {
+                limb_add(acc + 0 * 128, i, fx);
+                limb_add(acc + 1 * 128, i, fy);
+                limb_add(acc + 2 * 128, i, fz);
+            }
             // the column atom receives the exact negation; it is accumulated positively and negated once at the fold
             limb_add(acc + 0 * 128, j, fx);
             limb_add(acc + 1 * 128, j, fy);
@@ -104,6 +119,7 @@ __device__ __forceinline__ void cq_pair(
             // clashing atoms: too large for two limbs, add to the global accumulators directly.  Terms beyond the int64 range
             // are converted exactly as the reference converts them, the column atom's from -v like the reference's
             // (k_nonbonded.cuh:248-254): fixed(-v) == -fixed(v) only holds in range
+            const float rx = t.prefactor * dx, ry = t.prefactor * dy, rz = t.prefactor * dz;
             u64 *gi = sink.du_dx + static_cast<size_t>(sink.perm[si]) * 3;
             u64 *gj = sink.du_dx + static_cast<size_t>(sink.perm[sj]) * 3;
             atomicAdd(gi + 0, to_fixed_force(rx));
@@ -284,6 +300,128 @@ __device__ __forceinline__ void cq_tile_prefilter(
             __syncwarp();
             if (lane < count) {
                 Q[lane] = v;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// "Row runs" (round 2): the same prefilter tile with the candidates kept as one 32-bit mask per row atom instead of a
+// queue of codes.  Phase A is then 11 instructions per double round (no ballots, no prefix popcounts, no queue stores:
+// HSET2.BM gives 0xffff per passing half and one LOP3 files both results under bits R and 16 + R of the lane's mask).  An
+// exclusive scan of the popcounts makes the masks an implicit ROW-SORTED list of n candidates; lane l evaluates the K =
+// ceil(n / 32) consecutive entries [l K, (l + 1) K) - perfectly balanced - and because consecutive entries share the row
+// atom, its force limbs are summed in registers and flushed with shared atomics only where the row changes (~2 flushes per
+// lane and tile instead of K): per evaluated batch 6 nearly conflict-free ATOMS wavefronts on the row side instead of
+// 6 x 2.8 (profiles/r2_summary.md section 5 has the conflict model), in a kernel bound by that pipe.  The column side and
+// every rounded operation are unchanged: bitwise the same sums.
+// Bit b of row i's mask <-> column position (i + 2 (b & 15) + (b >> 4)) mod 32: a row's candidates are walked even offsets
+// first, then odd.  (Staging the column words as {c_k, c_(k+16)} makes the bit number the offset itself and saves four
+// instructions per step, but walking in plain offset order raises the column-side conflicts from 3.9 to 4.25 passes per
+// ATOMS - profiles/study_row_runs.py - and measured 1.9 % slower, profiles/r2_summary.md section 10.)
+constexpr int S_RM = S_QC;      // u32[32]: candidate mask per row
+constexpr int S_RO = S_QC + 32; // u32[32]: exclusive prefix sum of the candidate counts
+constexpr int S_RG = S_QC + 64; // u64[3][32]: row-atom force sums over a run of tiles (k_nb_tiles_cq.cu)
+static_assert(64 + 192 <= CQ_CODES / 2 && S_RG % 2 == 0 && S_WORDS_X % 2 == 0 && S_WORDS_P % 2 == 0, "row-run tables live in the code queue's space, u64 aligned");
+
+template <bool U, bool X, bool P>
+__device__ __forceinline__ void cq_tile_prefilter_runs(
+    float *S, const CqBox &b, const float cutoff2, const unsigned int thr2, const float beta, const __half2 hx,
+    const __half2 hy, const __half2 hz, const int h0, const int h1, const CqSink &sink, i128 &energy) {
+    const int lane = threadIdx.x & 31;
+    unsigned int *SU = reinterpret_cast<unsigned int *>(S);
+    int *SI = reinterpret_cast<int *>(S);
+    // ---- phase A: this lane's row atom against all (or one half of the) column positions
+    unsigned int m = 0;
+    const __half2 thr = bits_h2(thr2);
+#pragma unroll 1
+    for (int h = h0; h < h1; h++) {
+        const unsigned int *H = SU + S_H2 + lane + 16 * h;
+        unsigned int mh = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const __half2 dx = __hsub2(hx, bits_h2(H[2 * r]));
+            const __half2 dy = __hsub2(hy, bits_h2(H[64 + 2 * r]));
+            const __half2 dz = __hsub2(hz, bits_h2(H[128 + 2 * r]));
+            const __half2 d2 = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
+            mh |= __hlt2_mask(d2, thr) & (0x00010001u << r); // NaN padding compares false
+        }
+        m |= mh << (8 * h);
+    }
+    // ---- the implicit row-sorted candidate list
+    const int c = __popc(m);
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < WARP; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) {
+            incl += up;
+        }
+    }
+    const int n = __shfl_sync(0xffffffffu, incl, WARP - 1);
+    if (n == 0) {
+        return;
+    }
+    const unsigned int nonempty = __ballot_sync(0xffffffffu, c != 0);
+    SU[S_RM + lane] = m;
+    SU[S_RO + lane] = static_cast<unsigned int>(incl - c);
+    __syncwarp();
+    const int K = (n + WARP - 1) >> 5;
+    const int e0 = lane * K;
+    const int todo = min(K, n - e0); // <= 0: nothing for this lane
+    int i = 0;
+    unsigned int cur = 0;
+    if (todo > 0) {
+        // the row holding entry e0: the last row whose prefix is <= e0 (empty rows tie with the next non-empty one)
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            if (SU[S_RO + i + step] <= static_cast<unsigned int>(e0)) {
+                i += step;
+            }
+        }
+        int skip = e0 - static_cast<int>(SU[S_RO + i]);
+        cur = SU[S_RM + i];
+        // drop the `skip` lowest candidates of that row (select by rank, five halvings)
+        int pos = 0;
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) {
+            const int cnt = __popc((cur >> pos) & ((1u << w) - 1u));
+            if (cnt <= skip) {
+                skip -= cnt;
+                pos += w;
+            }
+        }
+        cur = (cur >> pos) << pos;
+    }
+    // ---- phase B: K steps, one candidate per lane and step
+    int racc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+        if (k < todo) {
+            const int bpos = __ffs(static_cast<int>(cur)) - 1;
+            const int j = 32 + ((i + ((bpos & 15) << 1) + (bpos >> 4)) & 31);
+            const float dx = min_image(S[S_X + i] - S[S_X + j], b.bx, b.inv_bx);
+            const float dy = min_image(S[S_Y + i] - S[S_Y + j], b.by, b.inv_by);
+            const float dz = min_image(S[S_Z + i] - S[S_Z + j], b.bz, b.inv_bz);
+            const float d2 = dist2_3d(dx, dy, dz);
+            if (d2 < cutoff2) {
+                cq_pair<false, U, X, P, true>(S, i, j, dx, dy, dz, 0.0f, d2, beta, sink, energy, racc);
+            }
+            cur &= cur - 1u;
+            if (cur == 0u || k == todo - 1) {
+                if (X) {
+                    int *acc = SI + S_ACCX + i;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) {
+                        atomicAdd(acc + q * 64, racc[q]); // [comp][limb][atom]: x lo, x hi, y lo, ...
+                        racc[q] = 0;
+                    }
+                }
+                const unsigned int above = nonempty & ~((2u << i) - 1u);
+                if (above != 0u) {
+                    i = __ffs(static_cast<int>(above)) - 1;
+                    cur = SU[S_RM + i];
+                }
             }
         }
     }
