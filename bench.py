@@ -411,7 +411,7 @@ def water_sampling_arm(args, s, ops, impl, flat, lam, x_eq, v_eq, dev, torch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--md-steps", type=int, default=400, help="MD steps per bench step (one HREX frame)")
