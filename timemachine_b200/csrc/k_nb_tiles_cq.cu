@@ -36,6 +36,12 @@
 //     d <= 1.5 nm; the three half roundings of the squared sum add <= 3 * 2^-10.  Total < 0.0158: the threshold is
 //     cutoff^2 + 0.02 rounded up to half, and the prefilter is only used for cutoff <= 1.5 nm (else: exact path).
 // The exact 38-instruction round per 32 pairs becomes ~29 instructions per 64 pairs (ncu r1 -> r2 in profiles/).
+//
+// Row runs (round 2, the production form of a prefilter tile; nb_tiles_cq.cuh: cq_tile_prefilter_runs): instead of queueing
+// codes, every lane keeps the candidates of its row atom as one 32-bit mask (11 instructions per 64 pairs), a scan of the
+// popcounts makes the masks an implicit row-sorted list, the lanes walk it in equal contiguous chunks and keep the row atom's
+// force limbs in registers until the row changes.  Same pairs, same terms, same sums; 112.8 -> 109.7 us per launch
+// (profiles/r2_summary.md section 10).  -DCQ_ROW_RUNS=0 builds the code-queue form for A/B runs.
 #include "nb_tiles_cq.cuh"
 
 #ifndef CQ_ROW_RUNS
