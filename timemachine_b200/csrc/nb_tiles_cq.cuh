@@ -80,7 +80,7 @@ struct CqSink {
 template <bool ALCH, bool U, bool X, bool P, bool ROWREG = false>
 __device__ __forceinline__ void cq_pair(
     float *S, const int i, const int j, const float dx, const float dy, const float dz, const float dw, const float d2,
-    const float beta, const CqSink &sink, i128 &energy, int *racc = nullptr) {
+    const float beta, const CqSink &sink, i128 &energy, unsigned int *racc = nullptr) {
     int *SI = reinterpret_cast<int *>(S);
     const float qi = S[S_Q + i], qj = S[S_Q + j];
     const float ei = S[S_EPS + i], ej = S[S_EPS + j];
@@ -100,12 +100,13 @@ __device__ __forceinline__ void cq_pair(
             const u64 fy = static_cast<u64>(round_to_i64_in_range(sy));
             const u64 fz = static_cast<u64>(round_to_i64_in_range(sz));
             if (ROWREG) {
-                racc[0] += static_cast<int>(static_cast<unsigned int>(fx) & LIMB_MASK);
-                racc[1] += static_cast<int>(static_cast<i64>(fx) >> LIMB_BITS);
-                racc[2] += static_cast<int>(static_cast<unsigned int>(fy) & LIMB_MASK);
-                racc[3] += static_cast<int>(static_cast<i64>(fy) >> LIMB_BITS);
-                racc[4] += static_cast<int>(static_cast<unsigned int>(fz) & LIMB_MASK);
-                racc[5] += static_cast<int>(static_cast<i64>(fz) >> LIMB_BITS);
+                // unsigned: the low-limb sum of a row's <= 32 terms needs all 32 bits, the high limbs are two's complement
+                racc[0] += static_cast<unsigned int>(fx) & LIMB_MASK;
+                racc[1] += static_cast<unsigned int>(static_cast<i64>(fx) >> LIMB_BITS);
+                racc[2] += static_cast<unsigned int>(fy) & LIMB_MASK;
+                racc[3] += static_cast<unsigned int>(static_cast<i64>(fy) >> LIMB_BITS);
+                racc[4] += static_cast<unsigned int>(fz) & LIMB_MASK;
+                racc[5] += static_cast<unsigned int>(static_cast<i64>(fz) >> LIMB_BITS);
             } else {
                 limb_add(acc + 0 * 128, i, fx);
                 limb_add(acc + 1 * 128, i, fy);
@@ -394,7 +395,7 @@ __device__ __forceinline__ void cq_tile_prefilter_runs(
         cur = (cur >> pos) << pos;
     }
     // ---- phase B: K steps, one candidate per lane and step
-    int racc[6] = {0, 0, 0, 0, 0, 0};
+    unsigned int racc[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll 1
     for (int k = 0; k < K; k++) {
         if (k < todo) {
@@ -413,7 +414,7 @@ __device__ __forceinline__ void cq_tile_prefilter_runs(
                     int *acc = SI + S_ACCX + i;
 #pragma unroll
                     for (int q = 0; q < 6; q++) {
-                        atomicAdd(acc + q * 64, racc[q]); // [comp][limb][atom]: x lo, x hi, y lo, ...
+                        atomicAdd(acc + q * 64, static_cast<int>(racc[q])); // [comp][limb][atom]: x lo, x hi, y lo, ...
                         racc[q] = 0;
                     }
                 }
