@@ -245,6 +245,58 @@ class HREXDiagnostics:
         return get_normalized_kl_divergence(self.replica_idx_by_state_by_iter)
 
 
+def _batches(n: int, batch_size: int):
+    """timemachine/utils.py:6-13"""
+    assert n >= 0 and batch_size > 0
+    quot, rem = divmod(n, batch_size)
+    for _ in range(quot):
+        yield batch_size
+    if rem:
+        yield rem
+
+
+def run_hrex(
+    replicas: Sequence,
+    sample_replica: Callable,
+    replica_from_samples: Callable,
+    neighbor_pairs: Sequence,
+    get_log_q: Callable,
+    n_samples: int,
+    n_samples_per_iter: int,
+    seed: int,
+    n_swap_attempts_per_iter: Optional[int] = None,
+):
+    """The reference's generic HREX loop (md/hrex.py:397-491): per iteration a batch of neighbour swap attempts on the log
+    weights of the current replicas (seed + iteration), then local sampling of every (state, replica) pair.
+
+    sample_replica(replica, state_idx, n_samples) -> samples; replica_from_samples(samples) -> replica;
+    get_log_q(replicas) -> (n_replicas, n_states) array, or a function (replica_idx, state_idx) -> log weight.
+    Returns (samples by iteration and state, HREXDiagnostics)."""
+    n_replicas = len(replicas)
+    if n_swap_attempts_per_iter is None:
+        n_swap_attempts_per_iter = get_swap_attempts_per_iter_heuristic(n_replicas)
+    hrex = HREX.from_replicas(replicas)
+    samples_by_state_by_iter: list = []
+    replica_idx_by_state_by_iter: list = []
+    fraction_accepted_by_pair_by_iter: list = []
+    for iteration, n_samples_batch in enumerate(_batches(n_samples, n_samples_per_iter)):
+        log_q = get_log_q(hrex.replicas)
+        if callable(log_q):
+            log_q_kl = np.array([[log_q(r, s) for s in range(n_replicas)] for r in range(n_replicas)])
+        else:
+            log_q_kl = np.asarray(log_q)
+        hrex, fraction_accepted_by_pair = hrex.attempt_neighbor_swaps_fast(
+            neighbor_pairs, log_q_kl, n_swap_attempts_per_iter, seed + iteration
+        )
+        hrex, samples_by_state = hrex.sample_replicas(
+            lambda replica, state_idx: sample_replica(replica, state_idx, n_samples_batch), replica_from_samples
+        )
+        fraction_accepted_by_pair_by_iter.append(fraction_accepted_by_pair)
+        replica_idx_by_state_by_iter.append(hrex.replica_idx_by_state)
+        samples_by_state_by_iter.append(samples_by_state)
+    return samples_by_state_by_iter, HREXDiagnostics(replica_idx_by_state_by_iter, fraction_accepted_by_pair_by_iter)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def _sparse_batch_idxs(replica_idx_by_state, replica_idxs, max_delta_states: Optional[int]):
     """For each replica in `replica_idxs`: the states within max_delta_states of the state it currently holds (all states
