@@ -93,3 +93,35 @@ def test_nan_log_weights_are_never_accepted():
     states = [gaussian(loc, 0.3) for loc in (0.0, 0.5, 1.0)]
     _, diag, _ = run(states, [0.0, 0.5, 1.0], 0, n_samples=400, poison=True)
     np.testing.assert_array_equal(diag.cumulative_swap_acceptance_rates[-1], 0.0)
+
+
+def test_plain_and_fast_swap_batches_agree_statistically():
+    """HREX.attempt_neighbor_swaps (a mixture of NeighborSwapMoves, md/hrex.py:155-188) against attempt_neighbor_swaps_fast on
+    the same log weights: same acceptance rate per pair, same distribution of final permutations."""
+    from timemachine_b200.hrex import HREX, NeighborSwapMove
+
+    rng = np.random.default_rng(0)
+    n = 4
+    log_q_kl = rng.normal(0, 1.0, (n, n))
+    pairs = [(0, 1), (1, 2), (2, 3)]
+    hrex = HREX.from_replicas(list("abcd"))
+    np.random.seed(1)
+    acc_plain, acc_fast = np.zeros((3, 2)), np.zeros((3, 2))
+    perms_plain, perms_fast = {}, {}
+    for it in range(300):
+        h1, f1 = hrex.attempt_neighbor_swaps(pairs, lambda r, s: log_q_kl[r, s], 40)
+        h2, f2 = hrex.attempt_neighbor_swaps_fast(pairs, log_q_kl, 40, seed=it)
+        acc_plain += np.array(f1)
+        acc_fast += np.array(f2)
+        perms_plain[tuple(h1.replica_idx_by_state)] = perms_plain.get(tuple(h1.replica_idx_by_state), 0) + 1
+        perms_fast[tuple(h2.replica_idx_by_state)] = perms_fast.get(tuple(h2.replica_idx_by_state), 0) + 1
+        assert sorted(h1.replica_idx_by_state) == [0, 1, 2, 3] and h1.replicas == hrex.replicas
+    np.testing.assert_allclose(acc_plain[:, 0] / acc_plain[:, 1], acc_fast[:, 0] / acc_fast[:, 1], atol=0.03)
+    assert abs(acc_plain[:, 1].sum() - 300 * 40) < 1e-9
+    top = max(perms_fast, key=perms_fast.get)
+    assert abs(perms_plain.get(top, 0) - perms_fast[top]) < 60
+    # a single move: the acceptance probability is min(1, exp(sum of the swapped log weights - sum of the current ones))
+    move = NeighborSwapMove(lambda r, s: log_q_kl[r, s], 0, 1)
+    proposed, log_p = move.propose([0, 1, 2, 3])
+    assert proposed == [1, 0, 2, 3]
+    assert log_p == pytest.approx(min(0.0, log_q_kl[0, 1] + log_q_kl[1, 0] - log_q_kl[0, 0] - log_q_kl[1, 1]))

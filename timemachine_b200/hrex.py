@@ -123,6 +123,87 @@ class Trajectory:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+class MonteCarloMove:
+    """propose() -> (proposal, log acceptance probability); move() accepts with that probability (NumPy's global stream, like
+    the reference's md/moves.py:52-85) and counts."""
+
+    def __init__(self):
+        self._n_proposed = 0
+        self._n_accepted = 0
+
+    def propose(self, x):
+        raise NotImplementedError
+
+    def move(self, x):
+        proposal, log_acceptance_probability = self.propose(x)
+        self._n_proposed += 1
+        # NaN compares false: a proposal with an indeterminate weight is rejected
+        if np.random.rand() < np.exp(log_acceptance_probability):
+            self._n_accepted += 1
+            return proposal
+        return x
+
+    def sample_chain(self, x, n_samples: int) -> list:
+        out = []
+        for _ in range(n_samples):
+            x = self.move(x)
+            out.append(x)
+        return out
+
+    @property
+    def n_proposed(self) -> int:
+        return self._n_proposed
+
+    @property
+    def n_accepted(self) -> int:
+        return self._n_accepted
+
+    @property
+    def acceptance_fraction(self) -> float:
+        return self._n_accepted / self._n_proposed if self._n_proposed else float("nan")
+
+
+class MixtureOfMoves:
+    """One move per step, chosen uniformly (md/moves.py:101-128)."""
+
+    def __init__(self, moves: Sequence[MonteCarloMove]):
+        self.moves = list(moves)
+
+    @property
+    def n_accepted_by_move(self) -> list:
+        return [m.n_accepted for m in self.moves]
+
+    @property
+    def n_proposed_by_move(self) -> list:
+        return [m.n_proposed for m in self.moves]
+
+    def move(self, x):
+        return self.moves[np.random.choice(len(self.moves))].move(x)
+
+    def move_n(self, x, n: int):
+        for idx in np.random.choice(len(self.moves), size=n, replace=True):
+            x = self.moves[idx].move(x)
+        return x
+
+
+class NeighborSwapMove(MonteCarloMove):
+    """Swap the replicas at a fixed pair of states (md/hrex.py:25-48).  The state of the move is the list replica-by-state."""
+
+    def __init__(self, log_q: Callable, s_a: int, s_b: int):
+        super().__init__()
+        self.log_q = log_q
+        self.s_a = s_a
+        self.s_b = s_b
+
+    def propose(self, state: list):
+        s_a, s_b = self.s_a, self.s_b
+        proposed = list(state)
+        proposed[s_a], proposed[s_b] = state[s_b], state[s_a]
+        r_a, r_b = state[s_a], state[s_b]
+        log_q_diff = self.log_q(r_a, s_b) + self.log_q(r_b, s_a) - self.log_q(r_a, s_a) - self.log_q(r_b, s_b)
+        return proposed, np.minimum(log_q_diff, 0.0)
+
+
 @dataclass(frozen=True)
 class HREX:
     """Replicas and the permutation state -> replica (reference md/hrex.py:132-240)."""
@@ -145,6 +226,13 @@ class HREX:
         for s, samples in enumerate(samples_by_state):
             replicas[self.replica_idx_by_state[s]] = replica_from_samples(samples)
         return HREX(replicas, self.replica_idx_by_state), samples_by_state
+
+    def attempt_neighbor_swaps(self, neighbor_pairs, log_q: Callable, n_swap_attempts: int):
+        """The reference's plain version (md/hrex.py:155-188): a mixture of NeighborSwapMoves on log_q(replica_idx, state_idx),
+        NumPy's global stream.  Same distribution as attempt_neighbor_swaps_fast, not the same sequence (as in the reference)."""
+        move = MixtureOfMoves([NeighborSwapMove(log_q, s_a, s_b) for s_a, s_b in neighbor_pairs])
+        replica_idx_by_state = move.move_n(list(self.replica_idx_by_state), n_swap_attempts)
+        return HREX(self.replicas, replica_idx_by_state), list(zip(move.n_accepted_by_move, move.n_proposed_by_move))
 
     def attempt_neighbor_swaps_fast(self, neighbor_pairs, log_q_kl, n_swap_attempts: int, seed: int):
         """A batch of swap attempts, each between a uniformly chosen neighbour pair (md/hrex.py:195-235).
