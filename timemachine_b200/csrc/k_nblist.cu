@@ -250,7 +250,10 @@ template <typename Real, bool TRI> __global__ void __launch_bounds__(BT_THREADS)
     // atom-atom test below reads them with broadcast 128-bit loads instead of four shuffles per row atom.
     __shared__ Vec4<Real> s_row[TILE];
     if (warp == 0) {
-        s_row[lane] = Vec4<Real>{pos_i_x, pos_i_y, pos_i_z, np_i};
+        // a padding slot of the last row block is infinitely far from everything (the atom test below looks at every
+        // atom of a group)
+        const bool real_i = atom_i < static_cast<unsigned int>(N);
+        s_row[lane] = Vec4<Real>{pos_i_x, pos_i_y, pos_i_z, real_i ? np_i : static_cast<Real>(INFINITY)};
     }
     __syncthreads();
     const Real half_cutoff2 = half * cutoff2;
@@ -367,8 +370,10 @@ template <typename Real, bool TRI> __global__ void __launch_bounds__(BT_THREADS)
                 pos_j_y -= by * nearbyint((pos_j_y - row_ctr_y) * inv_by);
                 pos_j_z -= bz * nearbyint((pos_j_z - row_ctr_z) * inv_bz);
                 const Real np_j = half * (pos_j_x * pos_j_x + pos_j_y * pos_j_y + pos_j_z * pos_j_z);
-                // four row atoms per step, straight-line; atoms whose row_near bit is clear get an unreachable
-                // threshold, so membership is exactly "some row_near atom within the cutoff" as in the reference
+                // four row atoms per step, straight-line.  Groups none of whose atoms reaches the column box are skipped;
+                // inside a group every atom is tested (one that does not reach the box cannot be within the cutoff of an
+                // atom inside it, so membership is still "some row atom within the cutoff" as in the reference).  The
+                // distance is three explicit FMAs: this file is compiled without contraction.
                 for (int base = 0; base < TILE; base += 4) {
                     const unsigned int bits = (row_flags >> base) & 0xFu;
                     if (bits == 0) {
@@ -377,9 +382,8 @@ template <typename Real, bool TRI> __global__ void __launch_bounds__(BT_THREADS)
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const Vec4<Real> r = s_row[base + u];
-                        const Real half_d2 = r.w + np_j - r.x * pos_j_x - r.y * pos_j_y - r.z * pos_j_z;
-                        const Real limit = ((bits >> u) & 1u) ? half_cutoff2 : static_cast<Real>(-1);
-                        interacts |= half_d2 < limit;
+                        const Real half_d2 = fma(-r.z, pos_j_z, fma(-r.y, pos_j_y, fma(-r.x, pos_j_x, r.w + np_j)));
+                        interacts |= half_d2 < half_cutoff2;
                     }
                     // once every column atom is known to interact there is nothing left to learn
                     if (__all_sync(0xffffffffu, interacts)) {
